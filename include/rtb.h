@@ -1,0 +1,265 @@
+/*
+ * rtb.h — C ABI of the B200-native wavefront path tracer (rtcuda_b200).
+ *
+ * This is the drop-in boundary for the render path of lashhw/rtcuda.  Every
+ * entry point cites the reference interface (file:line, relative to the
+ * reference repo) that it replaces.  Signatures carry plain pointers and
+ * sizes only; there are no C++ or torch types on this boundary.
+ *
+ * Conventions
+ *   - every function returns RTB_OK (0) or a negative rtb_status; it never
+ *     exits or throws across the boundary (the reference's CHECK_CUDA exits,
+ *     utility.cuh:4-13).  rtb_last_error() returns a thread-local message.
+ *   - "h_" pointers are host memory, "d_" pointers are device memory of the
+ *     context's GPU.
+ *   - struct layouts marked [ref layout] are byte-compatible with the
+ *     reference structs so that reference-side host code can pass its own
+ *     arrays without conversion.
+ */
+#ifndef RTB_H
+#define RTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_API __attribute__((visibility("default")))
+
+typedef enum rtb_status {
+    RTB_OK = 0,
+    RTB_ERR_INVALID = -1,   /* bad argument */
+    RTB_ERR_CUDA = -2,      /* CUDA runtime error, see rtb_last_error() */
+    RTB_ERR_NO_DEVICE = -3, /* no usable sm_100 device: the library has NO CPU fallback */
+    RTB_ERR_IO = -4,
+    RTB_ERR_OOM = -5
+} rtb_status;
+
+/* material.cuh:4-8 */
+enum { RTB_MATTE = 0, RTB_MIRROR = 1, RTB_GLASS = 2 };
+/* light.cuh:4-7 */
+enum { RTB_POINT_LIGHT = 0, RTB_AREA_LIGHT = 1 };
+
+/* [ref layout] Material, material.cuh:10-25 (20 B: albedo@0, ior@12, type@16) */
+typedef struct rtb_material {
+    float albedo[3];
+    float ior;
+    int32_t type;
+} rtb_material;
+
+/* Light, light.cuh:9-28.  Same 40-byte footprint; the reference's
+ * `Triangle *d_triangle` (offset 16) is replaced by the triangle's index in
+ * the scene's triangle list (the pointer form is accepted by
+ * rtb_scene_create_from_primitives). */
+typedef struct rtb_light {
+    int32_t type;
+    float pos[3];      /* point light position */
+    int64_t triangle;  /* area light: index of its triangle */
+    float L[3];        /* radiance (area) / intensity (point) */
+    int32_t _pad;
+} rtb_light;
+
+/* [ref layout] Camera, camera.cuh:4-13 (48 B) */
+typedef struct rtb_camera {
+    float lookfrom[3];
+    float upper_left[3];
+    float horizontal[3];
+    float vertical[3];
+} rtb_camera;
+
+/* [ref layout] Ray, ray.cuh:4-18 (28 B) */
+typedef struct rtb_ray {
+    float origin[3];
+    float dir[3]; /* unit length */
+    float tmax;
+} rtb_ray;
+
+/* Intersection (intersection.hpp:4-6) + hit primitive.  `prim` is the index
+ * of the triangle in the caller's triangle list (== d_triangle - d_triangles
+ * in the reference), or -1 for a miss (then t,u,v are 0). */
+typedef struct rtb_hit {
+    float t, u, v;
+    int32_t prim;
+} rtb_hit;
+
+/* Flat scene description (host memory).  Triangles are given as vertices;
+ * {p0, e1=p0-p1, e2=p2-p0, n=cross(e1,e2)} are derived without FMA
+ * contraction exactly like the reference's host constructor
+ * (triangle.cuh:6-7 run from main.cu:80). */
+typedef struct rtb_scene_desc {
+    int64_t num_triangles;
+    const float *vertices;       /* 9 floats per triangle: p0 p1 p2 */
+    const int32_t *material_ids; /* per triangle, index into materials */
+    const int32_t *light_ids;    /* per triangle, index into lights or -1 (Primitive::d_area_light) */
+    int32_t num_materials;
+    const rtb_material *materials;
+    int32_t num_lights;
+    const rtb_light *lights;
+} rtb_scene_desc;
+
+/* BVH builder selection (rtb_build_params.builder) */
+enum { RTB_BUILDER_PLOC = 0, RTB_BUILDER_LBVH = 1 };
+
+typedef struct rtb_build_params {
+    int32_t builder;      /* RTB_BUILDER_* */
+    int32_t ploc_radius;  /* nearest-neighbour search radius, 0 = default (16) */
+    int32_t max_leaf_tris;/* 1..3, 0 = default (3) */
+    int32_t _reserved;
+} rtb_build_params;
+
+typedef struct rtb_bvh_stats {
+    int64_t num_triangles;
+    int64_t num_bvh2_nodes;
+    int64_t num_nodes;        /* 80-byte 8-wide nodes */
+    int64_t node_bytes;
+    int64_t triangle_bytes;
+    float sah_cost;           /* SAH cost of the 8-wide tree (Cn=1, Ct=0.3) */
+    float build_ms;           /* GPU build time, CUDA events */
+    int32_t ploc_iterations;
+    int32_t collapse_levels;
+    float scene_bounds[6];    /* xmin xmax ymin ymax zmin zmax */
+} rtb_bvh_stats;
+
+/* Runtime replacement of the reference's compile-time constants
+ * (constant.hpp:4-10, render.cuh:413-417, main.cu:159-170). */
+typedef struct rtb_render_params {
+    int32_t width, height;
+    int32_t spp;            /* samples rendered by THIS call */
+    int32_t max_bounces;    /* MAX_BOUNCES, main.cu:170 */
+    int32_t rr_start;       /* RR_START, constant.hpp:10 (default 4) */
+    float rr_threshold;     /* RR_THRESHOLD, constant.hpp:9 (default 1) */
+    uint32_t seed;          /* RAND_SEED, render.cuh:417 (default 1) */
+    int32_t first_sample;   /* index of the first sample of this call (sample-pass sharding) */
+    int32_t total_spp;      /* divisor used by the tonemap; 0 means spp */
+    int32_t pool_size;      /* path slots (NUM_WORKING_PATHS, constant.hpp:8); 0 = auto */
+    int32_t flags;          /* RTB_RENDER_* */
+    int32_t _reserved;
+} rtb_render_params;
+
+enum {
+    RTB_RENDER_DEFAULT = 0,
+    RTB_RENDER_PIXEL_CENTRE = 1, /* no sub-pixel jitter: camera rays through pixel centres */
+    RTB_RENDER_NO_SHADOW = 2,    /* skip next-event estimation (debug) */
+    RTB_RENDER_NONPERSISTENT = 4 /* one-thread-per-ray traversal launch (A/B for the persistent kernel) */
+};
+
+typedef struct rtb_render_stats {
+    uint64_t paths;        /* camera paths started */
+    uint64_t extend_rays;  /* closest-hit traversals */
+    uint64_t shadow_rays;  /* any-hit traversals */
+    uint64_t iterations;   /* wavefront iterations */
+    uint64_t kernel_launches;
+    float ms_total;        /* generate..accumulate, CUDA events on the render stream */
+    float ms_extend;       /* filled only with RTB_PROFILE_STAGES */
+    float ms_shadow;
+    float ms_shade;
+    float ms_generate;
+} rtb_render_stats;
+
+typedef struct rtb_context rtb_context; /* one per GPU */
+typedef struct rtb_scene rtb_scene;     /* device-resident scene + BVH */
+
+/* ---- context / errors (replaces CHECK_CUDA, utility.cuh:4-13) ---- */
+RTB_API const char *rtb_last_error(void);
+RTB_API const char *rtb_version(void);
+RTB_API int rtb_context_create(int device_ordinal, rtb_context **out);
+RTB_API int rtb_context_destroy(rtb_context *ctx);
+RTB_API int rtb_context_device(const rtb_context *ctx);
+
+/* ---- scene + BVH build (replaces Bvh::Bvh, bvh.cuh:30-219, and the Scene
+ *      aggregate scene.cuh:4-8; uploads that main.cu:46-138 does by hand) ---- */
+RTB_API int rtb_build_params_default(rtb_build_params *p);
+RTB_API int rtb_scene_create(rtb_context *ctx, const rtb_scene_desc *desc,
+                             const rtb_build_params *bp, rtb_scene **out);
+/* Reference-pointer ingest: `h_primitives` is the host vector of reference
+ * Primitive structs (primitive.cuh:4-12; 24 B each, holding DEVICE pointers)
+ * exactly as passed to Bvh::Bvh (bvh.cuh:17); d_triangles / d_materials /
+ * d_lights are the device arrays those pointers point into (main.cu:49,120,135).
+ * A device gather kernel dereferences the pointers into the SoA layout. */
+RTB_API int rtb_scene_create_from_primitives(rtb_context *ctx, const void *h_primitives,
+                                             int64_t num_primitives, const void *d_triangles,
+                                             const void *d_materials, int32_t num_materials,
+                                             const void *d_lights, int32_t num_lights,
+                                             const rtb_build_params *bp, rtb_scene **out);
+RTB_API int rtb_scene_destroy(rtb_scene *scene);
+RTB_API int rtb_scene_stats(const rtb_scene *scene, rtb_bvh_stats *out);
+
+/* ---- ray queries (replace Bvh::traverse closest-hit bvh.cuh:251-303 with
+ *      kernel ch render.cuh:297-328, and any-hit bvh.cuh:306-357 with kernel
+ *      ah render.cuh:278-294) ---- */
+RTB_API int rtb_trace_closest(rtb_scene *scene, const rtb_ray *h_rays, int64_t n, rtb_hit *h_hits);
+/* h_excluded[i]: triangle index that may not occlude ray i (the light's own
+ * triangle, render.cuh:197) or -1.  h_occluded[i] = 1 if any other triangle
+ * is hit with 0 < t <= tmax. */
+RTB_API int rtb_trace_any(rtb_scene *scene, const rtb_ray *h_rays, const int32_t *h_excluded,
+                          int64_t n, uint8_t *h_occluded);
+/* device-buffer variants, timed on the GPU; *ms may be NULL */
+RTB_API int rtb_trace_closest_device(rtb_scene *scene, const rtb_ray *d_rays, int64_t n,
+                                     rtb_hit *d_hits, float *ms);
+RTB_API int rtb_trace_any_device(rtb_scene *scene, const rtb_ray *d_rays,
+                                 const int32_t *d_excluded, int64_t n, uint8_t *d_occluded,
+                                 float *ms);
+/* traversal work counters for the roofline model: mean 80-byte nodes fetched
+ * and triangles tested per ray (closest-hit), from a counting kernel variant */
+RTB_API int rtb_trace_closest_counts(rtb_scene *scene, const rtb_ray *h_rays, int64_t n,
+                                     double *nodes_per_ray, double *tris_per_ray);
+
+/* ---- camera (replaces Camera::Camera, camera.cuh:15-29; host arithmetic) ---- */
+RTB_API int rtb_camera_look_at(const float lookfrom[3], const float lookat[3], const float up[3],
+                               float vfov_deg, float aspect, rtb_camera *out);
+/* camera rays through pixel centres, Camera::get_ray((i+.5)/W,(j+.5)/H), camera.cuh:31-34 */
+RTB_API int rtb_camera_primary_rays(const rtb_camera *cam, int32_t width, int32_t height,
+                                    rtb_ray *h_rays);
+
+/* ---- render (replaces render(), render.cuh:366-457) ---- */
+RTB_API int rtb_render_params_default(rtb_render_params *p);
+/* whole call with host output: fb is float[3*W*H], sqrt(sum/total_spp), row 0 = top
+ * (render.cuh:330-338,455-456). */
+RTB_API int rtb_render(rtb_scene *scene, const rtb_camera *cam, const rtb_render_params *p,
+                       float *h_rgb_out, rtb_render_stats *stats);
+/* adds the radiance SUM of this call's samples into d_accum (float[3*W*H],
+ * device memory, not cleared) — the per-GPU accumulation of a sample-pass
+ * shard; reduce across GPUs, then rtb_tonemap_device. */
+RTB_API int rtb_render_accumulate(rtb_scene *scene, const rtb_camera *cam,
+                                  const rtb_render_params *p, float *d_accum,
+                                  rtb_render_stats *stats);
+/* d_out[i] = sqrt(d_accum[i] / total_spp)  (post_process_framebuffer, render.cuh:330-338);
+ * d_out may alias d_accum */
+RTB_API int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t num_floats,
+                               int32_t total_spp, float *d_out);
+
+/* ---- host-side scene I/O and procedural scenes (host C++, no GPU work) ---- */
+typedef struct rtb_host_scene rtb_host_scene; /* owns the arrays a rtb_scene_desc points to */
+/* ASCII PLY (what main.cu:60-62 reads through happly.h:1289,1451,1498) */
+RTB_API int rtb_mesh_load_ply(const char *path, float **verts_out, int64_t *num_verts,
+                              int32_t **faces_out, int64_t *num_faces);
+/* compact binary mesh fixture: "RTBM" u32 nv u32 nf, f32 verts[3nv], i32 faces[3nf] */
+RTB_API int rtb_mesh_load_bin(const char *path, float **verts_out, int64_t *num_verts,
+                              int32_t **faces_out, int64_t *num_faces);
+RTB_API int rtb_mesh_save_bin(const char *path, const float *verts, int64_t num_verts,
+                              const int32_t *faces, int64_t num_faces);
+RTB_API void rtb_free(void *p);
+
+enum {
+    RTB_SCENE_S1 = 1,  /* main.cu:41-148 Cornell box + bunny, all matte (configs C1, C2) */
+    RTB_SCENE_S1_MIXED = 2, /* same geometry, MATTE/MIRROR/GLASS round-robin by triangle index (C4) */
+    RTB_SCENE_S2 = 3   /* Cornell shell + grid x grid bunny instances, ~10M triangles at grid=12 (C3, C5) */
+};
+RTB_API int rtb_host_scene_build(int32_t kind, const float *mesh_verts, int64_t num_verts,
+                                 const int32_t *mesh_faces, int64_t num_faces, int32_t grid,
+                                 uint32_t seed, rtb_host_scene **out);
+RTB_API int rtb_host_scene_desc(const rtb_host_scene *hs, rtb_scene_desc *out);
+RTB_API int rtb_host_scene_camera(const rtb_host_scene *hs, float aspect, rtb_camera *out);
+RTB_API int rtb_host_scene_destroy(rtb_host_scene *hs);
+/* scene file shared with the reference harness: see csrc/host/scene_io.cpp */
+RTB_API int rtb_scene_desc_save(const char *path, const rtb_scene_desc *desc);
+RTB_API int rtb_host_scene_load(const char *path, rtb_host_scene **out);
+/* P3 PPM with clamp(int(256*c),0,255), main.cu:178-191 */
+RTB_API int rtb_write_ppm(const char *path, const float *rgb, int32_t width, int32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */

@@ -1,0 +1,271 @@
+"""ctypes binding of the C ABI in include/rtb.h (plumbing only).
+
+`load()` opens the CUDA library `librtb.so` next to this file and raises if
+it is missing: there is no CPU fallback in the product path.  Tests may pass
+an explicit path (tests/emu/librtb_emu.so is a host build of the same kernel
+bodies used only to check logic without a GPU).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "librtb.so")
+BUNNY_BIN = os.path.join(HERE, "data", "bunny.rtbm")
+
+RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2 = 1, 2, 3
+RTB_RENDER_PIXEL_CENTRE, RTB_RENDER_NO_SHADOW, RTB_RENDER_NONPERSISTENT = 1, 2, 4
+
+
+class Material(C.Structure):
+    _fields_ = [("albedo", C.c_float * 3), ("ior", C.c_float), ("type", C.c_int32)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_int32), ("pos", C.c_float * 3), ("triangle", C.c_int64),
+                ("L", C.c_float * 3), ("_pad", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("lookfrom", C.c_float * 3), ("upper_left", C.c_float * 3),
+                ("horizontal", C.c_float * 3), ("vertical", C.c_float * 3)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("num_triangles", C.c_int64), ("vertices", C.c_void_p), ("material_ids", C.c_void_p),
+                ("light_ids", C.c_void_p), ("num_materials", C.c_int32), ("materials", C.c_void_p),
+                ("num_lights", C.c_int32), ("lights", C.c_void_p)]
+
+
+class BuildParams(C.Structure):
+    _fields_ = [("builder", C.c_int32), ("ploc_radius", C.c_int32), ("max_leaf_tris", C.c_int32),
+                ("_reserved", C.c_int32)]
+
+
+class BvhStats(C.Structure):
+    _fields_ = [("num_triangles", C.c_int64), ("num_bvh2_nodes", C.c_int64), ("num_nodes", C.c_int64),
+                ("node_bytes", C.c_int64), ("triangle_bytes", C.c_int64), ("sah_cost", C.c_float),
+                ("build_ms", C.c_float), ("ploc_iterations", C.c_int32), ("collapse_levels", C.c_int32),
+                ("scene_bounds", C.c_float * 6)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_bounces", C.c_int32),
+                ("rr_start", C.c_int32), ("rr_threshold", C.c_float), ("seed", C.c_uint32),
+                ("first_sample", C.c_int32), ("total_spp", C.c_int32), ("pool_size", C.c_int32),
+                ("flags", C.c_int32), ("_reserved", C.c_int32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_total", C.c_float),
+                ("ms_extend", C.c_float), ("ms_shadow", C.c_float), ("ms_shade", C.c_float),
+                ("ms_generate", C.c_float)]
+
+
+RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("dir", np.float32, 3), ("tmax", np.float32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("prim", np.int32)])
+
+# every symbol include/rtb.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "rtb_last_error", "rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_context_device",
+    "rtb_build_params_default", "rtb_scene_create", "rtb_scene_create_from_primitives", "rtb_scene_destroy",
+    "rtb_scene_stats", "rtb_trace_closest", "rtb_trace_any", "rtb_trace_closest_device", "rtb_trace_any_device",
+    "rtb_trace_closest_counts", "rtb_camera_look_at", "rtb_camera_primary_rays", "rtb_render_params_default",
+    "rtb_render", "rtb_render_accumulate", "rtb_tonemap_device", "rtb_mesh_load_ply", "rtb_mesh_load_bin",
+    "rtb_mesh_save_bin", "rtb_free", "rtb_host_scene_build", "rtb_host_scene_desc", "rtb_host_scene_camera",
+    "rtb_host_scene_destroy", "rtb_scene_desc_save", "rtb_host_scene_load", "rtb_write_ppm",
+]
+
+
+class RtbError(RuntimeError):
+    pass
+
+
+def load(path=None):
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise RtbError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(the CUDA library is required; there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.rtb_last_error.restype = C.c_char_p
+    lib.rtb_version.restype = C.c_char_p
+    lib.rtb_free.restype = None
+    return lib
+
+
+class Lib:
+    """Thin object wrapper; every call raises RtbError on a non-zero status."""
+
+    def __init__(self, path=None):
+        self.lib = load(path)
+
+    def check(self, rc):
+        if rc != 0:
+            raise RtbError(f"rtb status {rc}: {self.lib.rtb_last_error().decode()}")
+
+    # ---- host side ----
+    def load_mesh(self, path=BUNNY_BIN):
+        v, f = C.c_void_p(), C.c_void_p()
+        nv, nf = C.c_int64(), C.c_int64()
+        fn = self.lib.rtb_mesh_load_ply if path.endswith(".ply") else self.lib.rtb_mesh_load_bin
+        self.check(fn(path.encode(), C.byref(v), C.byref(nv), C.byref(f), C.byref(nf)))
+        verts = np.ctypeslib.as_array(C.cast(v, C.POINTER(C.c_float)), (nv.value, 3)).copy()
+        faces = np.ctypeslib.as_array(C.cast(f, C.POINTER(C.c_int32)), (nf.value, 3)).copy()
+        self.lib.rtb_free(v)
+        self.lib.rtb_free(f)
+        return verts, faces
+
+    def host_scene(self, kind, verts, faces, grid=0, seed=1234):
+        return HostScene(self, kind, verts, faces, grid, seed)
+
+    def camera_look_at(self, lookfrom, lookat, up, vfov, aspect):
+        cam = Camera()
+        a = (C.c_float * 3)(*lookfrom); b = (C.c_float * 3)(*lookat); c = (C.c_float * 3)(*up)
+        self.check(self.lib.rtb_camera_look_at(a, b, c, C.c_float(vfov), C.c_float(aspect), C.byref(cam)))
+        return cam
+
+    def primary_rays(self, cam, w, h):
+        rays = np.zeros(w * h, dtype=RAY_DTYPE)
+        self.check(self.lib.rtb_camera_primary_rays(C.byref(cam), w, h, rays.ctypes.data_as(C.c_void_p)))
+        return rays
+
+    def write_ppm(self, path, rgb, w, h):
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        self.check(self.lib.rtb_write_ppm(path.encode(), rgb.ctypes.data_as(C.c_void_p), w, h))
+
+    # ---- device side ----
+    def context(self, device=0):
+        return Context(self, device)
+
+
+class HostScene:
+    def __init__(self, L, kind, verts, faces, grid, seed):
+        self.L = L
+        self.h = C.c_void_p()
+        verts = np.ascontiguousarray(verts, dtype=np.float32)
+        faces = np.ascontiguousarray(faces, dtype=np.int32)
+        L.check(L.lib.rtb_host_scene_build(kind, verts.ctypes.data_as(C.c_void_p), C.c_int64(len(verts)),
+                                           faces.ctypes.data_as(C.c_void_p), C.c_int64(len(faces)), grid,
+                                           C.c_uint32(seed), C.byref(self.h)))
+        self.desc = SceneDesc()
+        L.check(L.lib.rtb_host_scene_desc(self.h, C.byref(self.desc)))
+
+    def arrays(self):
+        """numpy views of the description (valid while this object lives)."""
+        d = self.desc
+        n = d.num_triangles
+        return dict(
+            vertices=np.ctypeslib.as_array(C.cast(d.vertices, C.POINTER(C.c_float)), (n, 9)),
+            material_ids=np.ctypeslib.as_array(C.cast(d.material_ids, C.POINTER(C.c_int32)), (n,)),
+            light_ids=np.ctypeslib.as_array(C.cast(d.light_ids, C.POINTER(C.c_int32)), (n,)),
+            materials=np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(Material)), (d.num_materials,)),
+            lights=np.ctypeslib.as_array(C.cast(d.lights, C.POINTER(Light)), (d.num_lights,)) if d.num_lights else None,
+        )
+
+    def camera(self, aspect):
+        cam = Camera()
+        self.L.check(self.L.lib.rtb_host_scene_camera(self.h, C.c_float(aspect), C.byref(cam)))
+        return cam
+
+    def save(self, path):
+        self.L.check(self.L.lib.rtb_scene_desc_save(path.encode(), C.byref(self.desc)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.lib.rtb_host_scene_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, L, device=0):
+        self.L = L
+        self.h = C.c_void_p()
+        L.check(L.lib.rtb_context_create(device, C.byref(self.h)))
+
+    def scene(self, desc, build_params=None):
+        return Scene(self, desc, build_params)
+
+    def tonemap_device(self, d_accum_ptr, num_floats, total_spp, d_out_ptr):
+        self.L.check(self.L.lib.rtb_tonemap_device(self.h, C.c_void_p(d_accum_ptr), C.c_int64(num_floats),
+                                                   total_spp, C.c_void_p(d_out_ptr)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.lib.rtb_context_destroy(self.h)
+        except Exception:
+            pass
+
+
+def render_params(L, **kw):
+    p = RenderParams()
+    L.check(L.lib.rtb_render_params_default(C.byref(p)))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Scene:
+    def __init__(self, ctx, desc, build_params=None):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        bp = C.byref(build_params) if build_params is not None else None
+        self.L.check(self.L.lib.rtb_scene_create(ctx.h, C.byref(desc), bp, C.byref(self.h)))
+
+    def stats(self):
+        s = BvhStats()
+        self.L.check(self.L.lib.rtb_scene_stats(self.h, C.byref(s)))
+        return s
+
+    def trace_closest(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        self.L.check(self.L.lib.rtb_trace_closest(self.h, rays.ctypes.data_as(C.c_void_p), C.c_int64(len(rays)),
+                                                  hits.ctypes.data_as(C.c_void_p)))
+        return hits
+
+    def trace_any(self, rays, excluded=None):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        occ = np.zeros(len(rays), dtype=np.uint8)
+        ex = None
+        if excluded is not None:
+            excluded = np.ascontiguousarray(excluded, dtype=np.int32)
+            ex = excluded.ctypes.data_as(C.c_void_p)
+        self.L.check(self.L.lib.rtb_trace_any(self.h, rays.ctypes.data_as(C.c_void_p), ex, C.c_int64(len(rays)),
+                                              occ.ctypes.data_as(C.c_void_p)))
+        return occ
+
+    def trace_counts(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        a, b = C.c_double(), C.c_double()
+        self.L.check(self.L.lib.rtb_trace_closest_counts(self.h, rays.ctypes.data_as(C.c_void_p),
+                                                         C.c_int64(len(rays)), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def render(self, cam, params):
+        out = np.zeros((params.height, params.width, 3), dtype=np.float32)
+        st = RenderStats()
+        self.L.check(self.L.lib.rtb_render(self.h, C.byref(cam), C.byref(params), out.ctypes.data_as(C.c_void_p),
+                                           C.byref(st)))
+        return out, st
+
+    def render_accumulate(self, cam, params, d_accum_ptr):
+        st = RenderStats()
+        self.L.check(self.L.lib.rtb_render_accumulate(self.h, C.byref(cam), C.byref(params),
+                                                      C.c_void_p(d_accum_ptr), C.byref(st)))
+        return st
+
+    def close(self):
+        if self.h:
+            self.L.lib.rtb_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

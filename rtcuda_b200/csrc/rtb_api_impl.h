@@ -1,0 +1,231 @@
+// rtb_api_impl.h — the extern "C" entry points of include/rtb.h, written
+// against `RTB_BACKEND` (a type defined by the including translation unit:
+// CudaBackend in rtb_cuda.cu for the shipped library).  No entry point lets a
+// C++ exception escape; errors become rtb_status codes + rtb_last_error().
+#pragma once
+#include "host/host_util.h"
+#include "rtb_engine.h"
+
+struct rtb_context {
+    RTB_BACKEND be;
+    explicit rtb_context(int device) : be(device) {}
+};
+struct rtb_scene {
+    rtb_context *ctx;
+    rtb::SceneT<RTB_BACKEND> *impl;
+};
+
+namespace rtb {
+template <class F>
+int guarded(F f) {
+    try {
+        f();
+        return RTB_OK;
+    } catch (const Error &e) {
+        return set_error(e.code, e.what());
+    } catch (const std::bad_alloc &) {
+        return set_error(RTB_ERR_OOM, "out of host memory");
+    } catch (const std::exception &e) {
+        return set_error(RTB_ERR_CUDA, e.what());
+    }
+}
+inline rtb_build_params build_defaults() {
+    rtb_build_params p;
+    p.builder = RTB_BUILDER_PLOC; p.ploc_radius = 16; p.max_leaf_tris = 3; p._reserved = 0;
+    return p;
+}
+}  // namespace rtb
+
+extern "C" {
+
+int rtb_context_create(int device, rtb_context **out) {
+    if (!out) return rtb::set_error(RTB_ERR_INVALID, "rtb_context_create: null out");
+    *out = nullptr;
+    return rtb::guarded([&] { *out = new rtb_context(device); });
+}
+int rtb_context_destroy(rtb_context *ctx) {
+    return rtb::guarded([&] { delete ctx; });
+}
+int rtb_context_device(const rtb_context *ctx) { return ctx ? ctx->be.device() : -1; }
+
+int rtb_build_params_default(rtb_build_params *p) {
+    if (!p) return rtb::set_error(RTB_ERR_INVALID, "null");
+    *p = rtb::build_defaults();
+    return RTB_OK;
+}
+int rtb_render_params_default(rtb_render_params *p) {
+    if (!p) return rtb::set_error(RTB_ERR_INVALID, "null");
+    memset(p, 0, sizeof *p);
+    p->width = 600; p->height = 600; p->spp = 10; p->max_bounces = 10;  // main.cu:159-170
+    p->rr_start = 4; p->rr_threshold = 1.f;                               // constant.hpp:9-10
+    p->seed = 1;                                                          // render.cuh:417
+    return RTB_OK;
+}
+
+int rtb_scene_create(rtb_context *ctx, const rtb_scene_desc *desc, const rtb_build_params *bp, rtb_scene **out) {
+    if (!ctx || !desc || !out) return rtb::set_error(RTB_ERR_INVALID, "rtb_scene_create: null argument");
+    *out = nullptr;
+    return rtb::guarded([&] {
+        ctx->be.make_current();
+        rtb_build_params p = bp ? *bp : rtb::build_defaults();
+        auto *impl = rtb::scene_from_desc(ctx->be, *desc, p);
+        *out = new rtb_scene{ctx, impl};
+    });
+}
+int rtb_scene_create_from_primitives(rtb_context *ctx, const void *h_primitives, int64_t n, const void *d_triangles,
+                                     const void *d_materials, int32_t num_materials, const void *d_lights,
+                                     int32_t num_lights, const rtb_build_params *bp, rtb_scene **out) {
+    if (!ctx || !out) return rtb::set_error(RTB_ERR_INVALID, "rtb_scene_create_from_primitives: null argument");
+    *out = nullptr;
+    return rtb::guarded([&] {
+        ctx->be.make_current();
+        rtb_build_params p = bp ? *bp : rtb::build_defaults();
+        auto *impl = rtb::scene_from_primitives(ctx->be, h_primitives, n, d_triangles, d_materials, num_materials,
+                                                d_lights, num_lights, p);
+        *out = new rtb_scene{ctx, impl};
+    });
+}
+int rtb_scene_destroy(rtb_scene *s) {
+    return rtb::guarded([&] {
+        if (!s) return;
+        s->ctx->be.make_current();
+        delete s->impl;
+        delete s;
+    });
+}
+int rtb_scene_stats(const rtb_scene *s, rtb_bvh_stats *out) {
+    if (!s || !out) return rtb::set_error(RTB_ERR_INVALID, "rtb_scene_stats: null");
+    *out = s->impl->stats;
+    return RTB_OK;
+}
+
+int rtb_trace_closest_device(rtb_scene *s, const rtb_ray *d_rays, int64_t n, rtb_hit *d_hits, float *ms) {
+    if (!s || n < 0 || (n && (!d_rays || !d_hits)) || n > 0x7fffffff) return rtb::set_error(RTB_ERR_INVALID, "rtb_trace_closest_device: bad arguments");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = s->ctx->be;
+        be.make_current();
+        rtb::TraceClosestK k; k.B = s->impl->view().bvh; k.rays = d_rays; k.hits = d_hits; k.n = n; k.counts = nullptr;
+        auto t0 = be.now();
+        if (n) be.launch_trace((int)n, k);
+        if (ms) *ms = be.elapsed_ms(t0, be.now());
+    });
+}
+int rtb_trace_any_device(rtb_scene *s, const rtb_ray *d_rays, const int32_t *d_excluded, int64_t n, uint8_t *d_occ, float *ms) {
+    if (!s || n < 0 || (n && (!d_rays || !d_occ)) || n > 0x7fffffff) return rtb::set_error(RTB_ERR_INVALID, "rtb_trace_any_device: bad arguments");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = s->ctx->be;
+        be.make_current();
+        rtb::TraceAnyK k; k.B = s->impl->view().bvh; k.rays = d_rays; k.excluded = d_excluded;
+        k.leaf_of_prim = s->impl->leaf_of_prim; k.occluded = d_occ; k.n = n;
+        auto t0 = be.now();
+        if (n) be.launch_trace((int)n, k);
+        if (ms) *ms = be.elapsed_ms(t0, be.now());
+    });
+}
+int rtb_trace_closest(rtb_scene *s, const rtb_ray *h_rays, int64_t n, rtb_hit *h_hits) {
+    if (!s || n < 0 || (n && (!h_rays || !h_hits)) || n > 0x7fffffff) return rtb::set_error(RTB_ERR_INVALID, "rtb_trace_closest: bad arguments");
+    if (n == 0) return RTB_OK;
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = s->ctx->be;
+        be.make_current();
+        rtb_ray *dr = be.template alloc<rtb_ray>((size_t)n);
+        rtb_hit *dh = be.template alloc<rtb_hit>((size_t)n);
+        be.upload(dr, h_rays, (size_t)n);
+        int rc = rtb_trace_closest_device(s, dr, n, dh, nullptr);
+        if (rc == RTB_OK) be.download(h_hits, dh, (size_t)n);
+        be.free(dr); be.free(dh);
+        if (rc != RTB_OK) throw rtb::Error(rc, rtb_last_error());
+    });
+}
+int rtb_trace_any(rtb_scene *s, const rtb_ray *h_rays, const int32_t *h_excluded, int64_t n, uint8_t *h_occ) {
+    if (!s || n < 0 || (n && (!h_rays || !h_occ)) || n > 0x7fffffff) return rtb::set_error(RTB_ERR_INVALID, "rtb_trace_any: bad arguments");
+    if (n == 0) return RTB_OK;
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = s->ctx->be;
+        be.make_current();
+        rtb_ray *dr = be.template alloc<rtb_ray>((size_t)n);
+        uint8_t *dout = be.template alloc<uint8_t>((size_t)n);
+        int32_t *dex = nullptr;
+        be.upload(dr, h_rays, (size_t)n);
+        if (h_excluded) {
+            for (int64_t i = 0; i < n; ++i)
+                if (h_excluded[i] >= s->impl->n) { be.free(dr); be.free(dout); throw rtb::Error(RTB_ERR_INVALID, "excluded triangle out of range"); }
+            dex = be.template alloc<int32_t>((size_t)n);
+            be.upload(dex, h_excluded, (size_t)n);
+        }
+        int rc = rtb_trace_any_device(s, dr, dex, n, dout, nullptr);
+        if (rc == RTB_OK) be.download(h_occ, dout, (size_t)n);
+        be.free(dr); be.free(dout); be.free(dex);
+        if (rc != RTB_OK) throw rtb::Error(rc, rtb_last_error());
+    });
+}
+int rtb_trace_closest_counts(rtb_scene *s, const rtb_ray *h_rays, int64_t n, double *nodes_per_ray, double *tris_per_ray) {
+    if (!s || n <= 0 || !h_rays || n > 0x7fffffff) return rtb::set_error(RTB_ERR_INVALID, "rtb_trace_closest_counts: bad arguments");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = s->ctx->be;
+        be.make_current();
+        rtb_ray *dr = be.template alloc<rtb_ray>((size_t)n);
+        rtb_hit *dh = be.template alloc<rtb_hit>((size_t)n);
+        unsigned long long *dc = be.template alloc<unsigned long long>(2);
+        unsigned long long z[2] = {0, 0};
+        be.upload(dr, h_rays, (size_t)n);
+        be.upload(dc, z, 2);
+        rtb::TraceClosestK k; k.B = s->impl->view().bvh; k.rays = dr; k.hits = dh; k.n = n; k.counts = dc;
+        be.launch_trace((int)n, k);
+        be.download(z, dc, 2);
+        be.free(dr); be.free(dh); be.free(dc);
+        if (nodes_per_ray) *nodes_per_ray = (double)z[0] / (double)n;
+        if (tris_per_ray) *tris_per_ray = (double)z[1] / (double)n;
+    });
+}
+
+int rtb_camera_primary_rays(const rtb_camera *cam, int32_t w, int32_t h, rtb_ray *rays) {
+    if (!cam || !rays || w <= 0 || h <= 0) return rtb::set_error(RTB_ERR_INVALID, "rtb_camera_primary_rays: bad arguments");
+    for (int j = 0; j < h; ++j)
+        for (int i = 0; i < w; ++i) {
+            rtb::V3 o, d;
+            rtb::camera_ray(*cam, rtb::fdiv(rtb::fadd((float)i, 0.5f), (float)w), rtb::fdiv(rtb::fadd((float)j, 0.5f), (float)h), o, d);
+            rtb_ray &r = rays[(size_t)j * w + i];
+            r.origin[0] = o.x; r.origin[1] = o.y; r.origin[2] = o.z;
+            r.dir[0] = d.x; r.dir[1] = d.y; r.dir[2] = d.z;
+            r.tmax = FLT_MAX;
+        }
+    return RTB_OK;
+}
+
+int rtb_render_accumulate(rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, float *d_accum, rtb_render_stats *stats) {
+    if (!s || !cam || !p) return rtb::set_error(RTB_ERR_INVALID, "rtb_render_accumulate: null argument");
+    return rtb::guarded([&] {
+        s->ctx->be.make_current();
+        rtb::render_accumulate(s->ctx->be, *s->impl, *cam, *p, d_accum, stats);
+    });
+}
+int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t n, int32_t total_spp, float *d_out) {
+    if (!ctx || !d_accum || !d_out) return rtb::set_error(RTB_ERR_INVALID, "rtb_tonemap_device: null argument");
+    return rtb::guarded([&] {
+        ctx->be.make_current();
+        rtb::tonemap(ctx->be, d_accum, n, total_spp, d_out);
+        ctx->be.sync();
+    });
+}
+int rtb_render(rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, float *h_rgb, rtb_render_stats *stats) {
+    if (!s || !cam || !p || !h_rgb) return rtb::set_error(RTB_ERR_INVALID, "rtb_render: null argument");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = s->ctx->be;
+        be.make_current();
+        auto &sc = *s->impl;
+        const int64_t nf = 3 * (int64_t)p->width * (int64_t)p->height;
+        if (nf <= 0) throw rtb::Error(RTB_ERR_INVALID, "rtb_render: bad image size");
+        if (sc.own_accum_floats != nf) {
+            be.free(sc.own_accum);
+            sc.own_accum = be.template alloc<float>((size_t)nf);
+            sc.own_accum_floats = nf;
+        }
+        be.zero(sc.own_accum, (size_t)nf);  // init_framebuffer, render.cuh:61-66
+        rtb::render_accumulate(be, sc, *cam, *p, sc.own_accum, stats);
+        rtb::tonemap(be, sc.own_accum, nf, p->total_spp > 0 ? p->total_spp : p->spp, sc.own_accum);
+        be.download(h_rgb, sc.own_accum, (size_t)nf);  // render.cuh:455-456
+    });
+}
+
+}  // extern "C"

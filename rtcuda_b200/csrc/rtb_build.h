@@ -1,0 +1,334 @@
+// rtb_build.h — bodies of the GPU BVH builder kernels.
+//
+// Replaces Bvh::Bvh (bvh.cuh:30-219: single-threaded host full-sweep SAH over
+// three std::sort'ed index arrays, ~260 ms for 69k triangles, minutes for
+// 10M).  Pipeline, all on the device:
+//   1. prim_setup     per-triangle record {p0,e1,e2,n}, bounds, scene bounds
+//   2. morton         63-bit Morton code of the centroid, radix sort
+//   3. PLOC           parallel locally-ordered clustering (Meister & Bittner
+//                     2018): nearest neighbour within a window of the Morton
+//                     order, merge mutual pairs, compact; repeat to one root
+//   4. collapse       top-down, level-synchronous: pull up to 8 children per
+//                     node (largest surface area opened first), subtrees of
+//                     <= 3 triangles become leaf children, slot assignment
+//                     for octant-ordered traversal, 8-bit quantisation,
+//                     triangles rewritten in leaf order
+// Bodies are RTB_HD; see rtb_wavefront.h for why.
+#pragma once
+#include "rtb_shade.h"
+
+namespace rtb {
+
+struct B2Node {  // binary node, 32 bytes
+    float lox, loy, loz; int32_t left;   // leaf: left = caller's triangle index
+    float hix, hiy, hiz; int32_t right;  // leaf: right = -1
+};
+
+#if defined(__CUDA_ARCH__)
+RTB_HD int atomic_add_i(int32_t *p, int v) { return atomicAdd(p, v); }
+RTB_HD void atomic_min_i(int32_t *p, int v) { atomicMin(p, v); }
+RTB_HD void atomic_max_i(int32_t *p, int v) { atomicMax(p, v); }
+RTB_HD void atomic_add_f(float *p, float v) { atomicAdd(p, v); }
+#else
+RTB_HD int atomic_add_i(int32_t *p, int v) { int o = *p; *p += v; return o; }
+RTB_HD void atomic_min_i(int32_t *p, int v) { if (v < *p) *p = v; }
+RTB_HD void atomic_max_i(int32_t *p, int v) { if (v > *p) *p = v; }
+RTB_HD void atomic_add_f(float *p, float v) { *p += v; }
+#endif
+
+// order-preserving float <-> int map for atomic min/max on floats
+RTB_HD int32_t float_to_ordered(float f) { int32_t b = f2i(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+RTB_HD float ordered_to_float(int32_t b) { return i2f(b >= 0 ? b : b ^ 0x7fffffff); }
+
+RTB_HD float half_area(float ex, float ey, float ez) { return ffma(fadd(ex, ey), ez, fmul(ex, ey)); }
+RTB_HD float b2_half_area(const B2Node &n) {
+    return half_area(fsub(n.hix, n.lox), fsub(n.hiy, n.loy), fsub(n.hiz, n.loz));
+}
+RTB_HD float union_half_area(const B2Node &a, const B2Node &b) {
+    return half_area(fsub(fmaxf(a.hix, b.hix), fminf(a.lox, b.lox)), fsub(fmaxf(a.hiy, b.hiy), fminf(a.loy, b.loy)),
+                     fsub(fmaxf(a.hiz, b.hiz), fminf(a.loz, b.loz)));
+}
+
+// ------------------------------------------------------------ 1. prim setup
+struct PrimSetupArgs {
+    const float *vertices;        // 9 per triangle, or null when tri_in is pre-filled
+    Tri48 *tri_in;                // [n] caller order
+    F4 *prim_lo, *prim_hi;        // [n] bounds (w unused)
+    int32_t *scene_bounds;        // 6 ordered ints: min xyz, max xyz
+    int32_t n;
+};
+RTB_HD void prim_setup_body(const PrimSetupArgs &a, int i) {
+    if (i >= a.n) return;
+    Tri48 t;
+    if (a.vertices) {
+        const float *v = a.vertices + 9 * (size_t)i;
+        t = tri_from_vertices(v3(v[0], v[1], v[2]), v3(v[3], v[4], v[5]), v3(v[6], v[7], v[8]));
+        a.tri_in[i] = t;
+    } else {
+        t = a.tri_in[i];
+    }
+    // Triangle::bounding_box, triangle.cuh:23-37 (p1 = p0 - e1, p2 = p0 + e2)
+    V3 p0 = tri_p0(t), p1 = vsub(p0, tri_e1(t)), p2 = vadd(p0, tri_e2(t));
+    V3 lo = v3(fminf(p0.x, fminf(p1.x, p2.x)), fminf(p0.y, fminf(p1.y, p2.y)), fminf(p0.z, fminf(p1.z, p2.z)));
+    V3 hi = v3(fmaxf(p0.x, fmaxf(p1.x, p2.x)), fmaxf(p0.y, fmaxf(p1.y, p2.y)), fmaxf(p0.z, fmaxf(p1.z, p2.z)));
+    F4 l; l.x = lo.x; l.y = lo.y; l.z = lo.z; l.w = 0.f;
+    F4 h; h.x = hi.x; h.y = hi.y; h.z = hi.z; h.w = 0.f;
+    a.prim_lo[i] = l; a.prim_hi[i] = h;
+    atomic_min_i(a.scene_bounds + 0, float_to_ordered(lo.x));
+    atomic_min_i(a.scene_bounds + 1, float_to_ordered(lo.y));
+    atomic_min_i(a.scene_bounds + 2, float_to_ordered(lo.z));
+    atomic_max_i(a.scene_bounds + 3, float_to_ordered(hi.x));
+    atomic_max_i(a.scene_bounds + 4, float_to_ordered(hi.y));
+    atomic_max_i(a.scene_bounds + 5, float_to_ordered(hi.z));
+}
+
+// ------------------------------------------------------------ 2. morton
+RTB_HD uint64_t spread21(uint64_t x) {  // 21 bits -> every third bit
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+struct MortonArgs {
+    const F4 *prim_lo, *prim_hi;
+    const int32_t *scene_bounds;
+    uint64_t *keys; int32_t *vals;
+    int32_t n;
+};
+RTB_HD void morton_body(const MortonArgs &a, int i) {
+    if (i >= a.n) return;
+    float sx = ordered_to_float(a.scene_bounds[0]), sy = ordered_to_float(a.scene_bounds[1]), sz = ordered_to_float(a.scene_bounds[2]);
+    float ex = fsub(ordered_to_float(a.scene_bounds[3]), sx), ey = fsub(ordered_to_float(a.scene_bounds[4]), sy),
+          ez = fsub(ordered_to_float(a.scene_bounds[5]), sz);
+    float e = fmaxf(ex, fmaxf(ey, ez));
+    float inv = e > 0.f ? fdiv(2097151.f, e) : 0.f;  // same scale on all axes keeps cells cubic
+    const F4 lo = a.prim_lo[i], hi = a.prim_hi[i];
+    float cx = fmul(0.5f, fadd(lo.x, hi.x)), cy = fmul(0.5f, fadd(lo.y, hi.y)), cz = fmul(0.5f, fadd(lo.z, hi.z));
+    float qx = fminf(fmaxf(fmul(fsub(cx, sx), inv), 0.f), 2097151.f);
+    float qy = fminf(fmaxf(fmul(fsub(cy, sy), inv), 0.f), 2097151.f);
+    float qz = fminf(fmaxf(fmul(fsub(cz, sz), inv), 0.f), 2097151.f);
+    a.keys[i] = spread21((uint64_t)qx) | (spread21((uint64_t)qy) << 1) | (spread21((uint64_t)qz) << 2);
+    a.vals[i] = i;
+}
+
+// ------------------------------------------------------------ 3. PLOC
+struct PlocArgs {
+    B2Node *nodes;        // [2n-1]; leaves 0..n-1 in Morton order
+    int32_t *count;       // [2n-1] triangles below each node
+    const int32_t *cin;   // clusters (node indices), Morton order kept
+    int32_t *cout;        // after merge: node index or -1
+    int32_t *nn;          // nearest neighbour position
+    int32_t *node_counter;  // next free inner node, starts at n
+    int32_t ncl;          // current cluster count
+    int32_t radius;
+};
+RTB_HD void ploc_leaf_body(const F4 *prim_lo, const F4 *prim_hi, const int32_t *sorted, B2Node *nodes,
+                           int32_t *count, int32_t *clusters, int n, int i) {
+    if (i >= n) return;
+    const int p = sorted[i];
+    const F4 lo = prim_lo[p], hi = prim_hi[p];
+    B2Node b;
+    b.lox = lo.x; b.loy = lo.y; b.loz = lo.z; b.left = p;
+    b.hix = hi.x; b.hiy = hi.y; b.hiz = hi.z; b.right = -1;
+    nodes[i] = b;
+    count[i] = 1;
+    clusters[i] = i;
+}
+// nearest neighbour by merged surface area within +-radius positions; ties go
+// to the lowest position, which guarantees at least one mutual pair per round
+RTB_HD void ploc_nn_body(const PlocArgs &a, int i) {
+    if (i >= a.ncl) return;
+    const B2Node me = a.nodes[a.cin[i]];
+    float best = FLT_MAX;
+    int bj = -1;
+    const int j0 = i - a.radius < 0 ? 0 : i - a.radius;
+    const int j1 = i + a.radius > a.ncl - 1 ? a.ncl - 1 : i + a.radius;
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const float ar = union_half_area(me, a.nodes[a.cin[j]]);
+        if (ar < best) { best = ar; bj = j; }
+    }
+    a.nn[i] = bj;
+}
+RTB_HD void ploc_merge_body(const PlocArgs &a, int n_leaves, int i) {
+    if (i >= a.ncl) return;
+    const int j = a.nn[i];
+    const int ci = a.cin[i];
+    if (j >= 0 && a.nn[j] == i) {
+        if (i < j) {
+            const int cj = a.cin[j];
+            const int id = atomic_add_i(a.node_counter, 1);
+            const B2Node x = a.nodes[ci], y = a.nodes[cj];
+            B2Node m;
+            m.lox = fminf(x.lox, y.lox); m.loy = fminf(x.loy, y.loy); m.loz = fminf(x.loz, y.loz);
+            m.hix = fmaxf(x.hix, y.hix); m.hiy = fmaxf(x.hiy, y.hiy); m.hiz = fmaxf(x.hiz, y.hiz);
+            m.left = ci; m.right = cj;
+            a.nodes[id] = m;
+            a.count[id] = a.count[ci] + a.count[cj];
+            a.cout[i] = id;
+        } else {
+            a.cout[i] = -1;
+        }
+    } else {
+        a.cout[i] = ci;
+    }
+    (void)n_leaves;
+}
+
+// ------------------------------------------------------------ 4. collapse
+struct WorkItem {
+    int32_t b2;    // binary node to expand
+    int32_t wide;  // index of the 8-wide node to write
+};
+struct CollapseArgs {
+    const B2Node *nodes;
+    const int32_t *count;
+    const Tri48 *tri_in;       // caller order
+    const TriMeta *meta_in;    // caller order
+    Q4 *nodes8;
+    Tri48 *tris_out;           // leaf order
+    TriMeta *meta_out;
+    int32_t *prim_out;         // leaf order -> caller index
+    int32_t *leaf_of_prim;     // caller index -> leaf order
+    int32_t *node_counter;     // next free wide node (root = 0 pre-allocated)
+    int32_t *tri_counter;
+    const WorkItem *work_in; int32_t n_in;
+    WorkItem *work_out; int32_t *n_out;
+    float *sah;                // accumulated SAH cost (unnormalised)
+    int32_t max_leaf;          // 1..3
+};
+
+RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
+    if (tid >= a.n_in) return;
+    const WorkItem item = a.work_in[tid];
+    const B2Node self = a.nodes[item.b2];
+    int ch[8];
+    int nc;
+    if (a.count[item.b2] <= a.max_leaf) { ch[0] = item.b2; nc = 1; }  // tiny scene: root is one leaf
+    else { ch[0] = self.left; ch[1] = self.right; nc = 2; }
+    // open the largest child until 8 children or only leaves remain
+    while (nc < 8) {
+        int best = -1; float best_a = -1.f;
+        for (int k = 0; k < nc; ++k) {
+            if (a.count[ch[k]] > a.max_leaf) {
+                const float ar = b2_half_area(a.nodes[ch[k]]);
+                if (ar > best_a) { best_a = ar; best = k; }
+            }
+        }
+        if (best < 0) break;
+        const B2Node o = a.nodes[ch[best]];
+        ch[best] = o.left;
+        ch[nc++] = o.right;
+    }
+    B2Node cb[8];
+    for (int k = 0; k < nc; ++k) cb[k] = a.nodes[ch[k]];
+    // slot assignment (greedy): slot s "looks" towards (s&1?+:-, s&2?+:-, s&4?+:-);
+    // a child goes to the slot best aligned with its offset from the node
+    // centre, so that `slot ^ octinv` orders children front to back
+    const float pcx = fmul(0.5f, fadd(self.lox, self.hix)), pcy = fmul(0.5f, fadd(self.loy, self.hiy)),
+                pcz = fmul(0.5f, fadd(self.loz, self.hiz));
+    float cost[8][8];
+    for (int k = 0; k < nc; ++k) {
+        const float dx = fsub(fmul(0.5f, fadd(cb[k].lox, cb[k].hix)), pcx);
+        const float dy = fsub(fmul(0.5f, fadd(cb[k].loy, cb[k].hiy)), pcy);
+        const float dz = fsub(fmul(0.5f, fadd(cb[k].loz, cb[k].hiz)), pcz);
+        for (int s = 0; s < 8; ++s)
+            cost[k][s] = fadd(fadd((s & 1) ? dx : -dx, (s & 2) ? dy : -dy), (s & 4) ? dz : -dz);
+    }
+    int slot_child[8];
+    for (int s = 0; s < 8; ++s) slot_child[s] = -1;
+    bool child_done[8];
+    for (int k = 0; k < 8; ++k) child_done[k] = false;
+    for (int round = 0; round < nc; ++round) {
+        float bc = -FLT_MAX; int bk = -1, bs = -1;
+        for (int k = 0; k < nc; ++k) {
+            if (child_done[k]) continue;
+            for (int s = 0; s < 8; ++s) {
+                if (slot_child[s] >= 0) continue;
+                if (cost[k][s] > bc) { bc = cost[k][s]; bk = k; bs = s; }
+            }
+        }
+        slot_child[bs] = bk;
+        child_done[bk] = true;
+    }
+    // allocate children and triangles
+    int n_inner = 0, n_tris = 0;
+    for (int k = 0; k < nc; ++k) {
+        const int cnt = a.count[ch[k]];
+        if (cnt > a.max_leaf) n_inner++; else n_tris += cnt;
+    }
+    const int child_base = n_inner ? atomic_add_i(a.node_counter, n_inner) : 0;
+    const int tri_base = n_tris ? atomic_add_i(a.tri_counter, n_tris) : 0;
+    const int work_base = n_inner ? atomic_add_i(a.n_out, n_inner) : 0;
+    // quantisation frame
+    const uint32_t ex = quant_exponent(fsub(self.hix, self.lox)), ey = quant_exponent(fsub(self.hiy, self.loy)),
+                   ez = quant_exponent(fsub(self.hiz, self.loz));
+    uint32_t meta[8], qlx[8], qly[8], qlz[8], qhx[8], qhy[8], qhz[8];
+    uint32_t imask = 0;
+    int inner_seen = 0, tri_off = 0;
+    float sah = fmul(b2_half_area(self), kSahNodeCost);
+    for (int s = 0; s < 8; ++s) {
+        const int k = slot_child[s];
+        if (k < 0) {
+            meta[s] = 0; qlx[s] = qly[s] = qlz[s] = 255u; qhx[s] = qhy[s] = qhz[s] = 0u;
+            continue;
+        }
+        const B2Node &c = cb[k];
+        qlx[s] = quant_lo(c.lox, self.lox, ex); qhx[s] = quant_hi(c.hix, self.lox, ex);
+        qly[s] = quant_lo(c.loy, self.loy, ey); qhy[s] = quant_hi(c.hiy, self.loy, ey);
+        qlz[s] = quant_lo(c.loz, self.loz, ez); qhz[s] = quant_hi(c.hiz, self.loz, ez);
+        const int cnt = a.count[ch[k]];
+        if (cnt > a.max_leaf) {
+            meta[s] = 0x20u | (24u + (uint32_t)s);
+            imask |= 1u << s;
+            WorkItem w; w.b2 = ch[k]; w.wide = child_base + inner_seen;
+            a.work_out[work_base + inner_seen] = w;
+            inner_seen++;
+        } else {
+            meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)tri_off;
+            sah = ffma(b2_half_area(c), fmul(kSahTriCost, (float)cnt), sah);
+            // gather the (<= 3) triangles of this subtree
+            int st[4]; int sp = 0; st[sp++] = ch[k];
+            while (sp) {
+                const int ni = st[--sp];
+                const B2Node x = a.nodes[ni];
+                if (x.right < 0) {
+                    const int dst = tri_base + tri_off;
+                    a.tris_out[dst] = a.tri_in[x.left];
+                    a.meta_out[dst] = a.meta_in[x.left];
+                    a.prim_out[dst] = x.left;
+                    a.leaf_of_prim[x.left] = dst;
+                    tri_off++;
+                } else {
+                    st[sp++] = x.right; st[sp++] = x.left;
+                }
+            }
+        }
+    }
+    atomic_add_f(a.sah, sah);
+    Q4 w0, w1, w2, w3, w4;
+    w0.x = f2u(self.lox); w0.y = f2u(self.loy); w0.z = f2u(self.loz);
+    w0.w = ex | (ey << 8) | (ez << 16) | (imask << 24);
+    w1.x = (uint32_t)child_base; w1.y = (uint32_t)tri_base;
+    w1.z = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
+    w1.w = meta[4] | (meta[5] << 8) | (meta[6] << 16) | (meta[7] << 24);
+#define RTB_PACK4(q, o) ((q)[o] | ((q)[o + 1] << 8) | ((q)[o + 2] << 16) | ((q)[o + 3] << 24))
+    w2.x = RTB_PACK4(qlx, 0); w2.y = RTB_PACK4(qlx, 4); w2.z = RTB_PACK4(qly, 0); w2.w = RTB_PACK4(qly, 4);
+    w3.x = RTB_PACK4(qlz, 0); w3.y = RTB_PACK4(qlz, 4); w3.z = RTB_PACK4(qhx, 0); w3.w = RTB_PACK4(qhx, 4);
+    w4.x = RTB_PACK4(qhy, 0); w4.y = RTB_PACK4(qhy, 4); w4.z = RTB_PACK4(qhz, 0); w4.w = RTB_PACK4(qhz, 4);
+#undef RTB_PACK4
+    Q4 *dst = a.nodes8 + (size_t)item.wide * kNodeWords;
+    dst[0] = w0; dst[1] = w1; dst[2] = w2; dst[3] = w3; dst[4] = w4;
+}
+
+// area lights refer to their triangle by leaf-order index after the build
+RTB_HD void light_fix_body(LightDev *lights, const int64_t *light_tri, const int32_t *leaf_of_prim, int n, int i) {
+    if (i >= n) return;
+    if (lights[i].type == RTB_AREA_LIGHT) lights[i].tri = leaf_of_prim[light_tri[i]];
+    else lights[i].tri = -1;
+}
+
+}  // namespace rtb

@@ -1,0 +1,205 @@
+// rtb_bvh8.h — compressed 8-wide BVH: node format, quantisation and the
+// per-ray traversal loop (closest-hit and any-hit).
+//
+// Replaces the reference's 32-byte binary Bvh::Node (bvh.cuh:5-14), the slab
+// test AABBIntersector (aabb_intersector.cuh:4-36), the 29-int local stack
+// DeviceStack (device_stack.cuh:4-11) and both Bvh::traverse overloads
+// (bvh.cuh:251-357).  Layout follows the compressed wide BVH of Ylitie,
+// Karras & Laine (HPG 2017): 80-byte nodes = five 128-bit words, child boxes
+// quantised to 8 bits per plane relative to the node origin with per-axis
+// power-of-two scales, children of one node stored contiguously, triangles of
+// one node stored contiguously (<= 24), octant-ordered traversal through the
+// slot permutation `slot ^ octinv`.
+//
+//   word0: origin.xyz (f32) | ex | ey | ez | imask          (biased exponents)
+//   word1: child_base (u32) | tri_base (u32) | meta[0..7]
+//   word2: qlo_x[0..7] | qlo_y[0..7]
+//   word3: qlo_z[0..7] | qhi_x[0..7]
+//   word4: qhi_y[0..7] | qhi_z[0..7]
+//
+//   meta[s] = 0                         empty slot
+//           = 0x20 | (24 + s)           inner child in slot s
+//           = unary(count) << 5 | off   leaf child: `count` (1..3) triangles
+//                                       starting at tri_base + off
+#pragma once
+#include "rtb_core.h"
+
+namespace rtb {
+
+constexpr int kNodeWords = 5;       // 80 bytes
+constexpr float kSahNodeCost = 1.0f;
+constexpr float kSahTriCost = 0.3f;
+
+struct Bvh8View {
+    const Q4 *nodes;     // kNodeWords per node
+    const F4 *tris;      // 3 words per triangle, leaf order
+    const int32_t *prim; // leaf order -> caller's triangle index
+    int32_t num_nodes;
+    int32_t num_tris;
+};
+
+struct HitRec {
+    float t, u, v;
+    int32_t tri;  // leaf-order triangle index, -1 = miss
+};
+
+struct TraceCounters {
+    uint32_t nodes, tris;
+};
+
+RTB_HD Tri48 load_tri(const F4 *tris, int idx) {
+    F4 a = ldg(tris + 3 * (size_t)idx), b = ldg(tris + 3 * (size_t)idx + 1), c = ldg(tris + 3 * (size_t)idx + 2);
+    Tri48 t;
+    t.p0x = a.x; t.p0y = a.y; t.p0z = a.z; t.e1x = a.w;
+    t.e1y = b.x; t.e1z = b.y; t.e2x = b.z; t.e2y = b.w;
+    t.e2z = c.x; t.nx = c.y; t.ny = c.z; t.nz = c.w;
+    return t;
+}
+
+// ------------------------------------------------------------ quantisation
+// smallest biased exponent e with 255 * 2^(e-127) >= extent (with margin)
+RTB_HD uint32_t quant_exponent(float extent) {
+    float f = fmul(fmul(extent, 1.0f / 255.0f), 1.000001f);
+    uint32_t b = f2u(f);
+    uint32_t e = (b >> 23) & 0xffu;
+    if (b & 0x7fffffu) e += 1;
+    if (e < 40u) e = 40u;
+    if (e > 250u) e = 250u;
+    return e;
+}
+RTB_HD uint32_t quant_lo(float lo, float p, uint32_t e) {
+    float scale = u2f(e << 23), inv = u2f((254u - e) << 23);
+    float q = floorf(fmul(fsub(lo, p), inv));
+    q = fminf(fmaxf(q, 0.f), 255.f);
+    if (q > 0.f && ffma(q, scale, p) > lo) q -= 1.f;
+    return (uint32_t)q;
+}
+RTB_HD uint32_t quant_hi(float hi, float p, uint32_t e) {
+    float scale = u2f(e << 23), inv = u2f((254u - e) << 23);
+    float q = ceilf(fmul(fsub(hi, p), inv));
+    q = fminf(fmaxf(q, 0.f), 255.f);
+    if (q < 255.f && ffma(q, scale, p) < hi) q += 1.f;
+    return (uint32_t)q;
+}
+
+// ------------------------------------------------------------ ray setup
+struct RaySetup {
+    V3 o, d, idir;
+    uint32_t octinv;  // bit a set iff d_a >= 0
+};
+RTB_HD RaySetup ray_setup(V3 o, V3 d) {
+    RaySetup r;
+    r.o = o; r.d = d;
+    const float tiny = 8.271806125530277e-25f;  // 2^-80: keeps q*2^e*idir finite
+    float dx = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
+    float dy = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
+    float dz = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
+    r.idir = v3(frcp(dx), frcp(dy), frcp(dz));
+    r.octinv = (dx >= 0.f ? 1u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 4u : 0u);
+    return r;
+}
+
+RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
+
+// Slab-test the 8 quantised child boxes of one node against the ray segment
+// [0, tmax]; returns the hit mask: inner children in bits 24..31 at position
+// 24 + (slot ^ octinv) (so the highest set bit is the nearest child in octant
+// order), triangles of leaf children in bits 0..23.
+RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 &n3, const Q4 &n4,
+                             const RaySetup &r, float tmax) {
+    const float ax = fmul(u2f(byte_of(n0.w, 0) << 23), r.idir.x);
+    const float ay = fmul(u2f(byte_of(n0.w, 1) << 23), r.idir.y);
+    const float az = fmul(u2f(byte_of(n0.w, 2) << 23), r.idir.z);
+    const float bx = fmul(fsub(u2f(n0.x), r.o.x), r.idir.x);
+    const float by = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
+    const float bz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
+    const bool px = (r.octinv & 1u) != 0, py = (r.octinv & 2u) != 0, pz = (r.octinv & 4u) != 0;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
+        const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
+        const uint32_t nx4 = px ? lox : hix, fx4 = px ? hix : lox;
+        const uint32_t ny4 = py ? loy : hiy, fy4 = py ? hiy : loy;
+        const uint32_t nz4 = pz ? loz : hiz, fz4 = pz ? hiz : loz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t meta = byte_of(meta4, j);
+            float tnx = ffma((float)byte_of(nx4, j), ax, bx);
+            float tny = ffma((float)byte_of(ny4, j), ay, by);
+            float tnz = ffma((float)byte_of(nz4, j), az, bz);
+            float tfx = ffma((float)byte_of(fx4, j), ax, bx);
+            float tfy = ffma((float)byte_of(fy4, j), ay, by);
+            float tfz = ffma((float)byte_of(fz4, j), az, bz);
+            float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
+            float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+            // outward padding of the far plane: the slab arithmetic carries
+            // ~2^-22 relative error and must never cull a triangle the exact
+            // reference test (triangle.cuh:39-58) would accept
+            if (tn <= fmul(tf, 1.0000019f)) {
+                const uint32_t bits = meta >> 5;                       // unary count, or 1 for inner
+                const bool inner = (meta & 0x18u) == 0x18u;            // low 5 bits in 24..31
+                const uint32_t pos = inner ? ((meta & 0x1fu) ^ r.octinv) : (meta & 0x1fu);
+                mask |= bits << pos;
+            }
+        }
+    }
+    return mask;
+}
+
+constexpr int kStackSize = 48;
+
+// One ray through the tree.  ANY: stop at the first accepted triangle whose
+// leaf-order index differs from `excluded` (the light's own triangle,
+// bvh.cuh:239-248) and return true.  Otherwise find the closest hit with the
+// reference's accept rule 0 < t <= tmax, tmax shrinking (bvh.cuh:222-236).
+template <bool ANY, bool COUNT>
+RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, HitRec &hit,
+                       TraceCounters *cnt) {
+    const RaySetup r = ray_setup(o, d);
+    uint32_t stack_x[kStackSize], stack_y[kStackSize];
+    int sp = 0;
+    uint32_t gx = 0, gy = 0x80000000u;  // node group: child base | hits<<24 | imask
+    uint32_t tx = 0, ty = 0;            // triangle group: tri base | hit bits
+    hit.t = 0.f; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
+    bool found = false;
+    while (true) {
+        if (gy & 0xff000000u) {
+            const int bit = bfind(gy);
+            gy &= ~(1u << bit);
+            const uint32_t base = gx, imask = gy & 0xffu;
+            if (gy & 0xff000000u) { stack_x[sp] = gx; stack_y[sp] = gy; ++sp; }
+            const uint32_t slot = ((uint32_t)bit - 24u) ^ r.octinv;
+            const uint32_t rel = popc(imask & ~(0xffffffffu << slot));
+            const Q4 *np = B.nodes + (size_t)(base + rel) * kNodeWords;
+            const Q4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
+            if (COUNT) cnt->nodes++;
+            const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, tmax);
+            gx = n1.x; gy = (hm & 0xff000000u) | (n0.w >> 24);
+            tx = n1.y; ty = hm & 0x00ffffffu;
+        }
+        while (ty) {
+            const int bit = bfind(ty);
+            ty &= ~(1u << bit);
+            const int idx = (int)(tx + (uint32_t)bit);
+            const Tri48 tr = load_tri(B.tris, idx);
+            if (COUNT) cnt->tris++;
+            float t, u, v;
+            if (tri_intersect(tr, o, d, tmax, t, u, v)) {
+                if (ANY) {
+                    if (idx != excluded) return true;
+                } else {
+                    tmax = t; hit.t = t; hit.u = u; hit.v = v; hit.tri = idx; found = true;
+                }
+            }
+        }
+        if ((gy & 0xff000000u) == 0) {
+            if (sp == 0) break;
+            --sp; gx = stack_x[sp]; gy = stack_y[sp];
+        }
+    }
+    return found;
+}
+
+}  // namespace rtb

@@ -1,0 +1,468 @@
+// rtb_engine.h — host-side orchestration of the builder and of the wavefront
+// loop, written once against a small backend interface.
+//
+// The product backend is CudaBackend (rtb_cuda.cu): device memory, named
+// sm_100a kernels, CUB radix sort / select, CUDA events.  tests/emu has a
+// HostBackend that runs the same kernel bodies in plain loops so the logic
+// can be checked against the oracle on a machine without a GPU; the shipped
+// library never contains it (no CPU fallback).
+//
+// Host loop being replaced: render(), render.cuh:366-457 (13 launches and 4
+// blocking 4-byte device->host copies per iteration); here an iteration is 7
+// launches, and the host looks at one `done` word every few iterations.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rtb_build.h"
+#include "rtb_wavefront.h"
+
+namespace rtb {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+// ---- kernel functors (named types => readable kernel names in ncu) ----
+struct PrimSetupK { PrimSetupArgs a; RTB_HD void operator()(int i) const { prim_setup_body(a, i); } };
+struct MortonK { MortonArgs a; RTB_HD void operator()(int i) const { morton_body(a, i); } };
+struct PlocLeafK {
+    const F4 *lo, *hi; const int32_t *sorted; B2Node *nodes; int32_t *count, *clusters; int n;
+    RTB_HD void operator()(int i) const { ploc_leaf_body(lo, hi, sorted, nodes, count, clusters, n, i); }
+};
+struct PlocNnK { PlocArgs a; RTB_HD void operator()(int i) const { ploc_nn_body(a, i); } };
+struct PlocMergeK { PlocArgs a; int n_leaves; RTB_HD void operator()(int i) const { ploc_merge_body(a, n_leaves, i); } };
+struct CollapseK { CollapseArgs a; RTB_HD void operator()(int i) const { collapse_body(a, i); } };
+struct LightFixK {
+    LightDev *lights; const int64_t *light_tri; const int32_t *leaf_of_prim; int n;
+    RTB_HD void operator()(int i) const { light_fix_body(lights, light_tri, leaf_of_prim, n, i); }
+};
+// gather of reference-layout primitives (primitive.cuh:4-12 holding device pointers)
+struct RefPrimitive { const void *tri, *mat, *light; };
+struct IngestK {
+    const RefPrimitive *prims; const char *tri_base, *mat_base, *light_base;
+    const rtb_material *materials; Tri48 *tri_in; TriMeta *meta_in; int64_t *light_tri; int n;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        const RefPrimitive p = prims[i];
+        const float *t = (const float *)p.tri;  // Triangle {p0,e1,e2,n}, 12 floats, triangle.cuh:20
+        Tri48 r;
+        r.p0x = t[0]; r.p0y = t[1]; r.p0z = t[2]; r.e1x = t[3]; r.e1y = t[4]; r.e1z = t[5];
+        r.e2x = t[6]; r.e2y = t[7]; r.e2z = t[8]; r.nx = t[9]; r.ny = t[10]; r.nz = t[11];
+        tri_in[i] = r;
+        const int m = (int)(((const char *)p.mat - mat_base) / 20);
+        TriMeta tm;
+        tm.material = m | (materials[m].type << 24);
+        tm.light = p.light ? (int)(((const char *)p.light - light_base) / 40) : -1;
+        meta_in[i] = tm;
+        if (tm.light >= 0) light_tri[tm.light] = i;
+    }
+};
+struct GenerateK { WaveState W; RenderConsts rc; RTB_HD void operator()(int i) const { generate_body(W, rc, i); } };
+struct ShadeK { WaveState W; SceneView S; RenderConsts rc; int type; RTB_HD void operator()(int i) const { shade_body(W, S, rc, type, i); } };
+struct ControlAK { WaveState W; RTB_HD void operator()(int) const { control_a_body(W); } };
+struct ControlBK { WaveState W; RTB_HD void operator()(int) const { control_b_body(W); } };
+struct IotaK { int32_t *p; int n; RTB_HD void operator()(int i) const { if (i < n) p[i] = i; } };
+struct TonemapK {  // post_process_framebuffer, render.cuh:330-338
+    const float *in; float *out; int64_t n; float inv_spp;
+    RTB_HD void operator()(int i) const { if (i < n) out[i] = fsqrt(fmul(in[i], inv_spp)); }
+};
+struct TraceClosestK {
+    Bvh8View B; const rtb_ray *rays; rtb_hit *hits; int64_t n; unsigned long long *counts;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        const rtb_ray r = rays[i];
+        HitRec h;
+        if (counts) {
+            TraceCounters c; c.nodes = 0; c.tris = 0;
+            bvh8_trace<false, true>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, -1, h, &c);
+#if defined(__CUDA_ARCH__)
+            atomicAdd(counts, (unsigned long long)c.nodes); atomicAdd(counts + 1, (unsigned long long)c.tris);
+#else
+            counts[0] += c.nodes; counts[1] += c.tris;
+#endif
+        } else {
+            bvh8_trace<false, false>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, -1, h, nullptr);
+        }
+        rtb_hit o;
+        o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.tri >= 0 ? B.prim[h.tri] : -1;
+        hits[i] = o;
+    }
+};
+struct TraceAnyK {
+    Bvh8View B; const rtb_ray *rays; const int32_t *excluded; const int32_t *leaf_of_prim; uint8_t *occluded; int64_t n;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        const rtb_ray r = rays[i];
+        int ex = excluded ? excluded[i] : -1;
+        if (ex >= 0) ex = leaf_of_prim[ex];
+        HitRec h;
+        occluded[i] = bvh8_trace<true, false>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, ex, h, nullptr) ? 1 : 0;
+    }
+};
+
+// ---- scene ----
+template <class BE>
+struct SceneT {
+    BE *be = nullptr;
+    int64_t n = 0;
+    Q4 *nodes8 = nullptr;
+    F4 *tris = nullptr;
+    TriMeta *meta = nullptr;
+    int32_t *prim = nullptr, *leaf_of_prim = nullptr;
+    rtb_material *materials = nullptr;
+    LightDev *lights = nullptr;
+    int32_t num_materials = 0, num_lights = 0, num_nodes = 0;
+    uint32_t type_mask = 0;  // bit t set iff some material has type t
+    rtb_bvh_stats stats{};
+    // render state kept between calls (the reference re-allocates ~293 MB per
+    // render() and never frees it, render.cuh:374-391)
+    WaveState W{};
+    int32_t pool = 0;
+    float *own_accum = nullptr; int64_t own_accum_floats = 0;
+
+    SceneView view() const {
+        SceneView S;
+        S.bvh.nodes = nodes8; S.bvh.tris = tris; S.bvh.prim = prim;
+        S.bvh.num_nodes = num_nodes; S.bvh.num_tris = (int32_t)n;
+        S.tri_meta = meta; S.materials = materials; S.lights = lights;
+        S.num_lights = num_lights; S.num_materials = num_materials;
+        return S;
+    }
+    void free_wave() {
+        if (!pool) return;
+        be->free(W.ray_o); be->free(W.ray_d); be->free(W.hit); be->free(W.beta); be->free(W.pixel); be->free(W.sample);
+        be->free(W.sh_o); be->free(W.sh_d); be->free(W.sh_L); be->free(W.extend_q); be->free(W.mat_q); be->free(W.free_q);
+        be->free(W.c);
+        pool = 0;
+    }
+    void ensure_wave(int32_t p) {
+        if (pool == p) return;
+        free_wave();
+        W.ray_o = be->template alloc<F4>(p); W.ray_d = be->template alloc<F4>(p);
+        W.hit = be->template alloc<F4>(p); W.beta = be->template alloc<F4>(p);
+        W.pixel = be->template alloc<uint32_t>(p); W.sample = be->template alloc<uint32_t>(p);
+        W.sh_o = be->template alloc<F4>(p); W.sh_d = be->template alloc<F4>(p); W.sh_L = be->template alloc<F4>(p);
+        W.extend_q = be->template alloc<int32_t>(p); W.mat_q = be->template alloc<int32_t>(3 * (size_t)p);
+        W.free_q = be->template alloc<int32_t>(p);
+        W.c = be->template alloc<Counters>(1);
+        W.pool = p;
+        pool = p;
+    }
+    ~SceneT() {
+        if (!be) return;
+        free_wave();
+        be->free(own_accum);
+        be->free(nodes8); be->free(tris); be->free(meta); be->free(prim); be->free(leaf_of_prim);
+        be->free(materials); be->free(lights);
+    }
+};
+
+// ---- builder ----
+// tri_in / meta_in / light_tri are device arrays in caller order; vertices may
+// be null when tri_in is already filled (reference-pointer ingest).
+template <class BE>
+void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, TriMeta *meta_in,
+               const int64_t *d_light_tri, const rtb_build_params &bp) {
+    const int64_t n64 = sc.n;
+    if (n64 > 0x3fffffff) throw Error(RTB_ERR_INVALID, "too many triangles (max 2^30-1)");
+    const int n = (int)n64;
+    const int max_leaf = bp.max_leaf_tris >= 1 && bp.max_leaf_tris <= 3 ? bp.max_leaf_tris : 3;
+    const int radius = bp.ploc_radius > 0 ? bp.ploc_radius : 16;
+    auto t0 = be.now();
+    sc.stats = rtb_bvh_stats{};
+    sc.stats.num_triangles = n;
+    sc.tris = (F4 *)be.template alloc<Tri48>(n > 0 ? n : 1);
+    sc.meta = be.template alloc<TriMeta>(n > 0 ? n : 1);
+    sc.prim = be.template alloc<int32_t>(n > 0 ? n : 1);
+    sc.leaf_of_prim = be.template alloc<int32_t>(n > 0 ? n : 1);
+    if (n == 0) {  // empty scene: one node with eight empty slots
+        std::vector<Q4> root(kNodeWords);
+        memset(root.data(), 0, sizeof(Q4) * kNodeWords);
+        root[2].x = root[2].y = root[2].z = root[2].w = 0xffffffffu;  // qlo = 255 > qhi = 0
+        root[3].x = root[3].y = 0xffffffffu;
+        root[0].w = 127u | (127u << 8) | (127u << 16);
+        sc.nodes8 = be.template alloc<Q4>(kNodeWords);
+        be.upload(sc.nodes8, root.data(), kNodeWords);
+        sc.num_nodes = 1;
+        sc.stats.num_nodes = 1;
+        sc.stats.node_bytes = 80;
+        return;
+    }
+    // 1. per-triangle records, bounds
+    F4 *prim_lo = be.template alloc<F4>(n), *prim_hi = be.template alloc<F4>(n);
+    int32_t *bounds = be.template alloc<int32_t>(6);
+    {
+        int32_t init[6];
+        for (int k = 0; k < 3; ++k) { init[k] = float_to_ordered(FLT_MAX); init[3 + k] = float_to_ordered(-FLT_MAX); }
+        be.upload(bounds, init, 6);
+        PrimSetupK k; k.a.vertices = d_vertices; k.a.tri_in = tri_in; k.a.prim_lo = prim_lo; k.a.prim_hi = prim_hi;
+        k.a.scene_bounds = bounds; k.a.n = n;
+        be.launch(n, k);
+    }
+    // 2. Morton codes + sort
+    uint64_t *keys = be.template alloc<uint64_t>(n);
+    int32_t *sorted = be.template alloc<int32_t>(n);
+    {
+        MortonK k; k.a.prim_lo = prim_lo; k.a.prim_hi = prim_hi; k.a.scene_bounds = bounds; k.a.keys = keys; k.a.vals = sorted; k.a.n = n;
+        be.launch(n, k);
+        be.sort_pairs(keys, sorted, n);
+    }
+    // 3. PLOC
+    const int n_b2 = 2 * n - 1;
+    B2Node *b2 = be.template alloc<B2Node>(n_b2);
+    int32_t *count = be.template alloc<int32_t>(n_b2);
+    int32_t *ca = be.template alloc<int32_t>(n), *cb = be.template alloc<int32_t>(n), *nn = be.template alloc<int32_t>(n);
+    int32_t *ctr = be.template alloc<int32_t>(4);  // [0] b2 node counter, [1] wide node counter, [2] tri counter, [3] work out
+    {
+        PlocLeafK k; k.lo = prim_lo; k.hi = prim_hi; k.sorted = sorted; k.nodes = b2; k.count = count; k.clusters = ca; k.n = n;
+        be.launch(n, k);
+        int32_t init[4] = {n, 1, 0, 0};
+        be.upload(ctr, init, 4);
+    }
+    int ncl = n, iters = 0;
+    while (ncl > 1) {
+        PlocArgs a; a.nodes = b2; a.count = count; a.cin = ca; a.cout = cb; a.nn = nn; a.node_counter = ctr; a.ncl = ncl; a.radius = radius;
+        PlocNnK k1; k1.a = a; be.launch(ncl, k1);
+        PlocMergeK k2; k2.a = a; k2.n_leaves = n; be.launch(ncl, k2);
+        ncl = be.compact_nonneg(cb, ca, ncl);
+        ++iters;
+    }
+    int32_t root_b2 = 0;
+    be.download(&root_b2, ca, 1);
+    sc.stats.ploc_iterations = iters;
+    sc.stats.num_bvh2_nodes = n_b2;
+    be.free(prim_lo); be.free(prim_hi); be.free(keys); be.free(sorted); be.free(cb); be.free(nn); be.free(ca);
+    // 4. collapse to the 8-wide compressed tree
+    const int max_nodes = n > 1 ? n : 1;
+    Q4 *nodes_tmp = be.template alloc<Q4>((size_t)max_nodes * kNodeWords);
+    WorkItem *wa = be.template alloc<WorkItem>(max_nodes), *wb = be.template alloc<WorkItem>(max_nodes);
+    float *sah = be.template alloc<float>(1);
+    {
+        float z = 0.f; be.upload(sah, &z, 1);
+        WorkItem r; r.b2 = root_b2; r.wide = 0;
+        be.upload(wa, &r, 1);
+    }
+    int n_in = 1, levels = 0;
+    while (n_in > 0) {
+        int32_t zero = 0;
+        be.upload(ctr + 3, &zero, 1);
+        CollapseK k;
+        k.a.nodes = b2; k.a.count = count; k.a.tri_in = tri_in; k.a.meta_in = meta_in;
+        k.a.nodes8 = nodes_tmp; k.a.tris_out = (Tri48 *)sc.tris; k.a.meta_out = sc.meta; k.a.prim_out = sc.prim;
+        k.a.leaf_of_prim = sc.leaf_of_prim; k.a.node_counter = ctr + 1; k.a.tri_counter = ctr + 2;
+        k.a.work_in = wa; k.a.n_in = n_in; k.a.work_out = wb; k.a.n_out = ctr + 3; k.a.sah = sah; k.a.max_leaf = max_leaf;
+        be.launch(n_in, k);
+        int32_t n_out = 0;
+        be.download(&n_out, ctr + 3, 1);
+        n_in = n_out;
+        WorkItem *t = wa; wa = wb; wb = t;
+        ++levels;
+    }
+    if (levels >= kStackSize) throw Error(RTB_ERR_INVALID, "BVH too deep for the traversal stack");
+    int32_t c4[4];
+    be.download(c4, ctr, 4);
+    sc.num_nodes = c4[1];
+    if (c4[2] != n) throw Error(RTB_ERR_INVALID, "internal: collapse lost triangles");
+    sc.nodes8 = be.template alloc<Q4>((size_t)sc.num_nodes * kNodeWords);
+    be.copy(sc.nodes8, nodes_tmp, (size_t)sc.num_nodes * kNodeWords);
+    be.free(nodes_tmp); be.free(wa); be.free(wb);
+    if (sc.num_lights > 0) {
+        LightFixK k; k.lights = sc.lights; k.light_tri = d_light_tri; k.leaf_of_prim = sc.leaf_of_prim; k.n = sc.num_lights;
+        be.launch(sc.num_lights, k);
+    }
+    // stats
+    float sah_h = 0.f;
+    be.download(&sah_h, sah, 1);
+    int32_t bnd[6];
+    be.download(bnd, bounds, 6);
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = ordered_to_float(bnd[k]); hi[k] = ordered_to_float(bnd[3 + k]); }
+    const float root_area = half_area(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+    sc.stats.sah_cost = root_area > 0.f ? sah_h / root_area : 0.f;
+    sc.stats.num_nodes = sc.num_nodes;
+    sc.stats.node_bytes = (int64_t)sc.num_nodes * 80;
+    sc.stats.triangle_bytes = (int64_t)n * 48;
+    sc.stats.collapse_levels = levels;
+    sc.stats.scene_bounds[0] = lo[0]; sc.stats.scene_bounds[1] = hi[0]; sc.stats.scene_bounds[2] = lo[1];
+    sc.stats.scene_bounds[3] = hi[1]; sc.stats.scene_bounds[4] = lo[2]; sc.stats.scene_bounds[5] = hi[2];
+    be.free(b2); be.free(count); be.free(ctr); be.free(sah); be.free(bounds);
+    sc.stats.build_ms = be.elapsed_ms(t0, be.now());
+}
+
+template <class BE>
+SceneT<BE> *scene_from_desc(BE &be, const rtb_scene_desc &d, const rtb_build_params &bp) {
+    if (d.num_triangles < 0 || (d.num_triangles > 0 && (!d.vertices || !d.material_ids)) || d.num_materials <= 0 || !d.materials)
+        throw Error(RTB_ERR_INVALID, "rtb_scene_create: incomplete scene description");
+    if (d.num_lights > 0 && !d.lights) throw Error(RTB_ERR_INVALID, "rtb_scene_create: lights missing");
+    const int64_t n = d.num_triangles;
+    std::vector<TriMeta> meta((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int m = d.material_ids[i];
+        if (m < 0 || m >= d.num_materials) throw Error(RTB_ERR_INVALID, "material id out of range");
+        const int l = d.light_ids ? d.light_ids[i] : -1;
+        if (l >= d.num_lights) throw Error(RTB_ERR_INVALID, "light id out of range");
+        meta[(size_t)i].material = m | (d.materials[m].type << 24);
+        meta[(size_t)i].light = l;
+    }
+    std::vector<LightDev> lights((size_t)d.num_lights);
+    std::vector<int64_t> light_tri((size_t)d.num_lights);
+    for (int i = 0; i < d.num_lights; ++i) {
+        const rtb_light &l = d.lights[i];
+        if (l.type == RTB_AREA_LIGHT && (l.triangle < 0 || l.triangle >= n)) throw Error(RTB_ERR_INVALID, "area light triangle out of range");
+        LightDev &o = lights[(size_t)i];
+        o.type = l.type; o.px = l.pos[0]; o.py = l.pos[1]; o.pz = l.pos[2]; o.tri = -1;
+        o.Lx = l.L[0]; o.Ly = l.L[1]; o.Lz = l.L[2];
+        light_tri[(size_t)i] = l.type == RTB_AREA_LIGHT ? l.triangle : 0;
+    }
+    SceneT<BE> *sc = new SceneT<BE>();
+    try {
+        sc->be = &be;
+        sc->n = n;
+        sc->num_materials = d.num_materials;
+        sc->num_lights = d.num_lights;
+        sc->materials = be.template alloc<rtb_material>(d.num_materials);
+        be.upload(sc->materials, d.materials, d.num_materials);
+        for (int i = 0; i < d.num_materials; ++i) sc->type_mask |= 1u << (d.materials[i].type & 3);
+        sc->lights = be.template alloc<LightDev>(d.num_lights > 0 ? d.num_lights : 1);
+        int64_t *d_light_tri = be.template alloc<int64_t>(d.num_lights > 0 ? d.num_lights : 1);
+        if (d.num_lights) { be.upload(sc->lights, lights.data(), d.num_lights); be.upload(d_light_tri, light_tri.data(), d.num_lights); }
+        float *d_vertices = be.template alloc<float>(n > 0 ? 9 * (size_t)n : 1);
+        Tri48 *tri_in = be.template alloc<Tri48>(n > 0 ? n : 1);
+        TriMeta *meta_in = be.template alloc<TriMeta>(n > 0 ? n : 1);
+        if (n) { be.upload(d_vertices, d.vertices, 9 * (size_t)n); be.upload(meta_in, meta.data(), (size_t)n); }
+        build_bvh(be, *sc, d_vertices, tri_in, meta_in, d_light_tri, bp);
+        be.free(d_vertices); be.free(tri_in); be.free(meta_in); be.free(d_light_tri);
+    } catch (...) {
+        delete sc;
+        throw;
+    }
+    return sc;
+}
+
+// Bvh::Bvh(triangles, primitives) + Scene{bvh,num_lights,d_lights} through the
+// reference's own device arrays (bvh.cuh:30, scene.cuh:4-8, main.cu:141-156)
+template <class BE>
+SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const void *d_tris, const void *d_mats,
+                                  int num_mats, const void *d_lights, int num_lights, const rtb_build_params &bp) {
+    if (n < 0 || (n > 0 && (!h_prims || !d_tris)) || !d_mats || num_mats <= 0 || (num_lights > 0 && !d_lights))
+        throw Error(RTB_ERR_INVALID, "rtb_scene_create_from_primitives: bad arguments");
+    SceneT<BE> *sc = new SceneT<BE>();
+    try {
+        sc->be = &be;
+        sc->n = n;
+        sc->num_materials = num_mats;
+        sc->num_lights = num_lights;
+        sc->materials = be.template alloc<rtb_material>(num_mats);
+        be.copy((char *)sc->materials, (const char *)d_mats, 20 * (size_t)num_mats);  // same 20-byte layout
+        {
+            std::vector<rtb_material> hm((size_t)num_mats);
+            be.download(hm.data(), sc->materials, (size_t)num_mats);
+            for (int i = 0; i < num_mats; ++i) sc->type_mask |= 1u << (hm[(size_t)i].type & 3);
+        }
+        // Light (light.cuh:9-28): type@0 pos@4 d_triangle@16 L@24, 40 bytes
+        std::vector<char> hl(40 * (size_t)(num_lights > 0 ? num_lights : 1));
+        if (num_lights) be.download(hl.data(), (const char *)d_lights, 40 * (size_t)num_lights);
+        std::vector<LightDev> lights((size_t)(num_lights > 0 ? num_lights : 1));
+        std::vector<int64_t> light_tri((size_t)(num_lights > 0 ? num_lights : 1), 0);
+        for (int i = 0; i < num_lights; ++i) {
+            const char *p = hl.data() + 40 * (size_t)i;
+            LightDev &o = lights[(size_t)i];
+            memcpy(&o.type, p, 4); memcpy(&o.px, p + 4, 12); memcpy(&o.Lx, p + 24, 12);
+            o.tri = -1;
+            const void *tp; memcpy(&tp, p + 16, 8);
+            if (o.type == RTB_AREA_LIGHT) light_tri[(size_t)i] = ((const char *)tp - (const char *)d_tris) / 48;
+        }
+        sc->lights = be.template alloc<LightDev>(num_lights > 0 ? num_lights : 1);
+        int64_t *d_light_tri = be.template alloc<int64_t>(num_lights > 0 ? num_lights : 1);
+        be.upload(sc->lights, lights.data(), lights.size());
+        be.upload(d_light_tri, light_tri.data(), light_tri.size());
+        RefPrimitive *d_prims = be.template alloc<RefPrimitive>(n > 0 ? n : 1);
+        Tri48 *tri_in = be.template alloc<Tri48>(n > 0 ? n : 1);
+        TriMeta *meta_in = be.template alloc<TriMeta>(n > 0 ? n : 1);
+        if (n) {
+            be.upload(d_prims, (const RefPrimitive *)h_prims, (size_t)n);
+            IngestK k; k.prims = d_prims; k.tri_base = (const char *)d_tris; k.mat_base = (const char *)d_mats;
+            k.light_base = (const char *)d_lights; k.materials = sc->materials; k.tri_in = tri_in; k.meta_in = meta_in;
+            k.light_tri = d_light_tri; k.n = (int)n;
+            be.launch((int)n, k);
+        }
+        build_bvh(be, *sc, nullptr, tri_in, meta_in, d_light_tri, bp);
+        be.free(d_prims); be.free(tri_in); be.free(meta_in); be.free(d_light_tri);
+    } catch (...) {
+        delete sc;
+        throw;
+    }
+    return sc;
+}
+
+// ---- wavefront loop ----
+template <class BE>
+void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_render_params &p, float *d_accum,
+                       rtb_render_stats *stats) {
+    if (p.width <= 0 || p.height <= 0 || p.spp <= 0 || p.max_bounces < 0 || !d_accum)
+        throw Error(RTB_ERR_INVALID, "rtb_render: bad parameters");
+    const unsigned long long total = (unsigned long long)p.width * (unsigned long long)p.height * (unsigned long long)p.spp;
+    if ((unsigned long long)p.width * (unsigned long long)p.height > 0x7fffffffull) throw Error(RTB_ERR_INVALID, "image too large");
+    int pool = p.pool_size > 0 ? p.pool_size : be.default_pool();
+    if ((unsigned long long)pool > total) pool = (int)total;
+    pool = (pool + 31) & ~31;
+    sc.ensure_wave(pool);
+    WaveState W = sc.W;
+    W.accum = d_accum;
+    const SceneView S = sc.view();
+    RenderConsts rc;
+    rc.cam = cam; rc.width = p.width; rc.height = p.height; rc.spp = p.spp; rc.first_sample = p.first_sample;
+    rc.max_bounces = p.max_bounces; rc.rr_start = p.rr_start; rc.rr_threshold = p.rr_threshold; rc.seed = p.seed; rc.flags = p.flags;
+    Counters c0;
+    memset(&c0, 0, sizeof c0);
+    c0.n_free = pool;
+    c0.total_paths = total;
+    auto t0 = be.now();
+    be.upload(W.c, &c0, 1);
+    { IotaK k; k.p = W.free_q; k.n = pool; be.launch(pool, k); }
+    unsigned long long launches = 1;
+    const int batch = 4;
+    while (true) {
+        for (int it = 0; it < batch; ++it) {
+            for (int type = 0; type < 3; ++type) {
+                if (!(sc.type_mask >> type & 1u)) continue;
+                ShadeK k; k.W = W; k.S = S; k.rc = rc; k.type = type;
+                be.launch_shade(pool, k);
+                ++launches;
+            }
+            { GenerateK k; k.W = W; k.rc = rc; be.launch_generate(pool, k); }
+            { ControlAK k; k.W = W; be.launch(1, k); }
+            be.extend(W, S, pool, (p.flags & RTB_RENDER_NONPERSISTENT) != 0);
+            be.shadow(W, S, pool, (p.flags & RTB_RENDER_NONPERSISTENT) != 0);
+            { ControlBK k; k.W = W; be.launch(1, k); }
+            launches += 5;
+        }
+        int32_t done = 0;
+        be.download(&done, &W.c->done, 1);
+        if (done) break;
+    }
+    auto t1 = be.now();
+    if (stats) {
+        Counters c;
+        be.download(&c, W.c, 1);
+        memset(stats, 0, sizeof *stats);
+        stats->paths = c.stat_paths;
+        stats->extend_rays = c.stat_extend;
+        stats->shadow_rays = c.stat_shadow;
+        stats->iterations = c.stat_iters;
+        stats->kernel_launches = launches;
+        stats->ms_total = be.elapsed_ms(t0, t1);
+    }
+}
+
+template <class BE>
+void tonemap(BE &be, const float *d_in, int64_t n, int total_spp, float *d_out) {
+    if (n <= 0 || total_spp <= 0) throw Error(RTB_ERR_INVALID, "rtb_tonemap: bad arguments");
+    TonemapK k; k.in = d_in; k.out = d_out; k.n = n; k.inv_spp = 1.0f / (float)total_spp;
+    be.launch((int)n, k);
+}
+
+}  // namespace rtb

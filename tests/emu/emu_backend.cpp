@@ -1,0 +1,74 @@
+// emu_backend.cpp — TEST INFRASTRUCTURE, not product code.
+//
+// Compiles the kernel bodies of rtcuda_b200/csrc (rtb_*.h) for the host and
+// runs them in plain sequential loops behind the same C ABI (include/rtb.h),
+// so that `pytest -m "not gpu"` can check the builder, the traversal and the
+// wavefront state machine against the oracle on a machine without a GPU.
+// It is built into tests/emu/librtb_emu.so, loaded only by tests/, never by
+// the rtcuda_b200 package: the shipped library (librtb.so) has no CPU path
+// and fails with RTB_ERR_NO_DEVICE when no sm_100 GPU is present.
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "rtb_engine.h"
+
+namespace rtb {
+
+struct HostBackend {
+    explicit HostBackend(int) {}
+    int device() const { return -1; }
+    void make_current() {}
+    void sync() {}
+    int default_pool() const { return 1 << 16; }
+
+    template <class T> T *alloc(size_t n) {
+        void *p = nullptr;
+        if (posix_memalign(&p, 64, sizeof(T) * (n ? n : 1)) != 0) throw Error(RTB_ERR_OOM, "emu: out of memory");
+        return (T *)p;
+    }
+    void free(void *p) { ::free(p); }
+    template <class T> void upload(T *dst, const T *src, size_t n) { memcpy(dst, src, sizeof(T) * n); }
+    template <class T> void download(T *dst, const T *src, size_t n) { memcpy(dst, src, sizeof(T) * n); }
+    template <class T> void copy(T *dst, const T *src, size_t n) { memcpy(dst, src, sizeof(T) * n); }
+    template <class T> void zero(T *p, size_t n) { memset(p, 0, sizeof(T) * n); }
+
+    template <class F> void launch(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
+    template <class F> void launch_shade(int n, F f) { launch(n, f); }
+    template <class F> void launch_generate(int n, F f) { launch(n, f); }
+    template <class F> void launch_trace(int n, F f) { launch(n, f); }
+    void extend(const WaveState &W, const SceneView &S, int, bool) {
+        const int n = W.c->n_extend;
+        for (int i = 0; i < n; ++i) extend_body(W, S, i);
+    }
+    void shadow(const WaveState &W, const SceneView &S, int, bool) {
+        const int n = W.c->n_shadow;
+        for (int i = 0; i < n; ++i) shadow_body(W, S, i);
+    }
+    void sort_pairs(uint64_t *keys, int32_t *vals, int n) {
+        std::vector<int> idx(n);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+        std::vector<uint64_t> k(n);
+        std::vector<int32_t> v(n);
+        for (int i = 0; i < n; ++i) { k[i] = keys[idx[i]]; v[i] = vals[idx[i]]; }
+        memcpy(keys, k.data(), sizeof(uint64_t) * n);
+        memcpy(vals, v.data(), sizeof(int32_t) * n);
+    }
+    int compact_nonneg(const int32_t *in, int32_t *out, int n) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) if (in[i] >= 0) out[m++] = in[i];
+        return m;
+    }
+    using Time = std::chrono::steady_clock::time_point;
+    Time now() { return std::chrono::steady_clock::now(); }
+    float elapsed_ms(Time a, Time b) { return std::chrono::duration<float, std::milli>(b - a).count(); }
+};
+
+}  // namespace rtb
+
+#define RTB_BACKEND rtb::HostBackend
+#include "rtb_api_impl.h"
