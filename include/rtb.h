@@ -100,7 +100,7 @@ typedef struct rtb_scene_desc {
 } rtb_scene_desc;
 
 /* BVH builder selection (rtb_build_params.builder) */
-enum { RTB_BUILDER_PLOC = 0, RTB_BUILDER_LBVH = 1 };
+enum { RTB_BUILDER_PLOC = 0 }; /* the only builder so far; other values are rejected */
 
 typedef struct rtb_build_params {
     int32_t builder;      /* RTB_BUILDER_* */
@@ -142,7 +142,8 @@ enum {
     RTB_RENDER_DEFAULT = 0,
     RTB_RENDER_PIXEL_CENTRE = 1, /* no sub-pixel jitter: camera rays through pixel centres */
     RTB_RENDER_NO_SHADOW = 2,    /* skip next-event estimation (debug) */
-    RTB_RENDER_NONPERSISTENT = 4 /* one-thread-per-ray traversal launch (A/B for the persistent kernel) */
+    RTB_RENDER_NONPERSISTENT = 4, /* one-thread-per-ray traversal launch (A/B for the persistent kernel) */
+    RTB_RENDER_COUNT_WORK = 8     /* counting kernel variants: fill the *_nodes / *_tris statistics (slower) */
 };
 
 typedef struct rtb_render_stats {
@@ -151,11 +152,13 @@ typedef struct rtb_render_stats {
     uint64_t shadow_rays;  /* any-hit traversals */
     uint64_t iterations;   /* wavefront iterations */
     uint64_t kernel_launches;
+    uint64_t extend_nodes, extend_tris; /* 80-byte nodes fetched / triangles tested by extend rays */
+    uint64_t shadow_nodes, shadow_tris; /* same for shadow rays (only with RTB_RENDER_COUNT_WORK) */
+    uint64_t extend_launches, shadow_launches; /* launches of the two traversal kernels */
     float ms_total;        /* generate..accumulate, CUDA events on the render stream */
-    float ms_extend;       /* filled only with RTB_PROFILE_STAGES */
-    float ms_shadow;
-    float ms_shade;
-    float ms_generate;
+    float ms_extend;       /* summed duration of the extend launches (CUDA events) */
+    float ms_shadow;       /* summed duration of the shadow launches */
+    float ms_other;        /* ms_total - ms_extend - ms_shadow: shade, generate, control, host gaps */
 } rtb_render_stats;
 
 typedef struct rtb_context rtb_context; /* one per GPU */

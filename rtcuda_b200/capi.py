@@ -15,7 +15,7 @@ DEFAULT_LIB = os.path.join(HERE, "librtb.so")
 BUNNY_BIN = os.path.join(HERE, "data", "bunny.rtbm")
 
 RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2 = 1, 2, 3
-RTB_RENDER_PIXEL_CENTRE, RTB_RENDER_NO_SHADOW, RTB_RENDER_NONPERSISTENT = 1, 2, 4
+RTB_RENDER_PIXEL_CENTRE, RTB_RENDER_NO_SHADOW, RTB_RENDER_NONPERSISTENT, RTB_RENDER_COUNT_WORK = 1, 2, 4, 8
 
 
 class Material(C.Structure):
@@ -59,9 +59,10 @@ class RenderParams(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_total", C.c_float),
-                ("ms_extend", C.c_float), ("ms_shadow", C.c_float), ("ms_shade", C.c_float),
-                ("ms_generate", C.c_float)]
+                ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("extend_nodes", C.c_uint64), ("extend_tris", C.c_uint64), ("shadow_nodes", C.c_uint64),
+                ("shadow_tris", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
+                ("ms_total", C.c_float), ("ms_extend", C.c_float), ("ms_shadow", C.c_float), ("ms_other", C.c_float)]
 
 
 RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("dir", np.float32, 3), ("tmax", np.float32)])

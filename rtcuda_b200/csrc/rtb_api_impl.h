@@ -107,7 +107,8 @@ int rtb_trace_closest_device(rtb_scene *s, const rtb_ray *d_rays, int64_t n, rtb
         rtb::TraceClosestK k; k.B = s->impl->view().bvh; k.rays = d_rays; k.hits = d_hits; k.n = n; k.counts = nullptr;
         auto t0 = be.now();
         if (n) be.launch_trace((int)n, k);
-        if (ms) *ms = be.elapsed_ms(t0, be.now());
+        const float e = be.elapsed_ms(t0, be.now());  // also waits for the launch
+        if (ms) *ms = e;
     });
 }
 int rtb_trace_any_device(rtb_scene *s, const rtb_ray *d_rays, const int32_t *d_excluded, int64_t n, uint8_t *d_occ, float *ms) {
@@ -119,7 +120,8 @@ int rtb_trace_any_device(rtb_scene *s, const rtb_ray *d_rays, const int32_t *d_e
         k.leaf_of_prim = s->impl->leaf_of_prim; k.occluded = d_occ; k.n = n;
         auto t0 = be.now();
         if (n) be.launch_trace((int)n, k);
-        if (ms) *ms = be.elapsed_ms(t0, be.now());
+        const float e = be.elapsed_ms(t0, be.now());  // also waits for the launch
+        if (ms) *ms = e;
     });
 }
 int rtb_trace_closest(rtb_scene *s, const rtb_ray *h_rays, int64_t n, rtb_hit *h_hits) {

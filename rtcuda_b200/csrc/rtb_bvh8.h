@@ -114,6 +114,12 @@ RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 
     const float by = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
     const float bz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
     const bool px = (r.octinv & 1u) != 0, py = (r.octinv & 2u) != 0, pz = (r.octinv & 4u) != 0;
+    // Error bound of the slab arithmetic: t = q*a + b carries an ABSOLUTE error
+    // of about 2^-23 * |b| (b = (origin_node - origin_ray)/d cancels against
+    // q*a when the ray starts close to the planes) plus a relative 2^-23 * |t|.
+    // The far plane is pushed out by both so that the box test never culls a
+    // triangle the exact reference test (triangle.cuh:39-58) would accept.
+    const float eps = fmul(fmaxf(fmaxf(fabsf(bx), fabsf(by)), fabsf(bz)), 4.76837158203125e-07f);  // 2^-21
     uint32_t mask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -134,10 +140,7 @@ RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 
             float tfz = ffma((float)byte_of(fz4, j), az, bz);
             float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
             float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            // outward padding of the far plane: the slab arithmetic carries
-            // ~2^-22 relative error and must never cull a triangle the exact
-            // reference test (triangle.cuh:39-58) would accept
-            if (tn <= fmul(tf, 1.0000019f)) {
+            if (tn <= ffma(tf, 1.0000019f, eps)) {
                 const uint32_t bits = meta >> 5;                       // unary count, or 1 for inner
                 const bool inner = (meta & 0x18u) == 0x18u;            // low 5 bits in 24..31
                 const uint32_t pos = inner ? ((meta & 0x1fu) ^ r.octinv) : (meta & 0x1fu);

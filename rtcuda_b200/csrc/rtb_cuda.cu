@@ -1,0 +1,260 @@
+// rtb_cuda.cu — the shipped backend: sm_100a kernels, device memory, CUB
+// radix sort / select, CUDA events, and the C ABI of include/rtb.h.
+//
+// Kernels (all plain SIMT; nothing on this path is a dense contraction, so
+// no tensor cores):
+//   k_extend / k_shadow   persistent traversal kernels: grid = SMs x resident
+//                         blocks, each warp claims 32 queue entries with one
+//                         atomicAdd (lane 0) and a shuffle broadcast
+//                         (replaces kernels ch / ah, render.cuh:278-328, which
+//                         launch one thread per ray in 64-thread blocks)
+//   k_shade<type>         grid-stride over one material queue (replaces mat +
+//                         init, render.cuh:84-248)
+//   k_generate            grid-stride over the free-slot queue (gen, :250-275)
+//   k_control_a/b         single-thread queue bookkeeping (replaces the four
+//                         blocking 4-byte device->host copies per iteration,
+//                         render.cuh:433-445)
+//   k_for<Functor>        one thread per element for builder / utility bodies
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+#include "rtb_engine.h"
+
+#define RTB_CUDA_CHECK(expr)                                                                              \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            throw rtb::Error(e_ == cudaErrorMemoryAllocation ? RTB_ERR_OOM : RTB_ERR_CUDA,                \
+                             std::string(#expr) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"); \
+    } while (0)
+
+namespace rtb {
+
+constexpr int kBlock = 256;
+
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_for(int n, F f) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) f(i);
+}
+
+__global__ void __launch_bounds__(kBlock) k_generate(WaveState W, RenderConsts rc) {
+    const int n = W.c->n_free;
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) generate_body(W, rc, i);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(kBlock) k_shade(WaveState W, SceneView S, RenderConsts rc) {
+    const int n = W.c->n_mat[TYPE];
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) shade_body(W, S, rc, TYPE, i);
+}
+
+__global__ void k_control_a(WaveState W) { control_a_body(W); }
+__global__ void k_control_b(WaveState W) { control_b_body(W); }
+
+// Persistent traversal: every warp pulls batches of 32 rays until the queue is
+// drained, so a long ray only delays its own warp's next fetch, not a whole
+// block's retirement, and the launch shape is independent of the queue size.
+__global__ void __launch_bounds__(kBlock) k_extend(WaveState W, SceneView S) {
+    const int n = W.c->n_extend;
+    const unsigned lane = threadIdx.x & 31u;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&W.c->extend_head, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) return;
+        const int i = base + (int)lane;
+        if (i < n) extend_body<false>(W, S, i);
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_shadow(WaveState W, SceneView S) {
+    const int n = W.c->n_shadow;
+    const unsigned lane = threadIdx.x & 31u;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&W.c->shadow_head, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) return;
+        const int i = base + (int)lane;
+        if (i < n) shadow_body<false>(W, S, i);
+        __syncwarp();
+    }
+}
+// one thread per queue entry (A/B against the persistent kernels; COUNT = work counters)
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_extend_flat(WaveState W, SceneView S) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < W.c->n_extend) extend_body<COUNT>(W, S, i);
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < W.c->n_shadow) shadow_body<COUNT>(W, S, i);
+}
+
+struct NonNegative {
+    __host__ __device__ bool operator()(const int32_t &v) const { return v >= 0; }
+};
+
+struct CudaBackend {
+    int dev_ = -1;
+    int num_sms_ = 0;
+    cudaStream_t stream_ = nullptr;
+    int blocks_extend_ = 0, blocks_shadow_ = 0;
+    void *cub_temp_ = nullptr;
+    size_t cub_temp_bytes_ = 0;
+
+    explicit CudaBackend(int device) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error(RTB_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                               "); rtcuda_b200 has no CPU fallback");
+        if (device < 0 || device >= count) throw Error(RTB_ERR_INVALID, "device ordinal out of range");
+        cudaDeviceProp prop;
+        RTB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw Error(RTB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                               std::to_string(prop.minor) + "; this library is built for sm_100a (B200) only");
+        dev_ = device;
+        num_sms_ = prop.multiProcessorCount;
+        RTB_CUDA_CHECK(cudaSetDevice(dev_));
+        RTB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamDefault));
+        int per_sm = 0;
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend, kBlock, 0));
+        blocks_extend_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow, kBlock, 0));
+        blocks_shadow_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
+    }
+    ~CudaBackend() {
+        if (dev_ < 0) return;
+        cudaSetDevice(dev_);
+        cudaFree(cub_temp_);
+        if (stream_) cudaStreamDestroy(stream_);
+    }
+    CudaBackend(const CudaBackend &) = delete;
+    CudaBackend &operator=(const CudaBackend &) = delete;
+
+    int device() const { return dev_; }
+    void make_current() { RTB_CUDA_CHECK(cudaSetDevice(dev_)); }
+    void sync() { RTB_CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+    int default_pool() const { return 1 << 21; }
+
+    template <class T> T *alloc(size_t n) {
+        void *p = nullptr;
+        RTB_CUDA_CHECK(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+        return (T *)p;
+    }
+    void free(void *p) { if (p) cudaFree(p); }
+    template <class T> void upload(T *dst, const T *src, size_t n) {
+        RTB_CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, stream_));
+        RTB_CUDA_CHECK(cudaStreamSynchronize(stream_));  // src may be a temporary
+    }
+    template <class T> void download(T *dst, const T *src, size_t n) {
+        RTB_CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyDeviceToHost, stream_));
+        RTB_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+    template <class T> void copy(T *dst, const T *src, size_t n) {
+        RTB_CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyDeviceToDevice, stream_));
+    }
+    template <class T> void zero(T *p, size_t n) { RTB_CUDA_CHECK(cudaMemsetAsync(p, 0, sizeof(T) * n, stream_)); }
+
+    template <class F> void launch(int n, F f) {
+        if (n <= 0) return;
+        k_for<F><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream_>>>(n, f);
+        RTB_CUDA_CHECK(cudaGetLastError());
+    }
+    template <class F> void launch_trace(int n, F f) { launch(n, f); }
+    void launch(int, ControlAK k) { k_control_a<<<1, 1, 0, stream_>>>(k.W); RTB_CUDA_CHECK(cudaGetLastError()); }
+    void launch(int, ControlBK k) { k_control_b<<<1, 1, 0, stream_>>>(k.W); RTB_CUDA_CHECK(cudaGetLastError()); }
+    void launch_generate(int, GenerateK k) {
+        k_generate<<<num_sms_ * 4, kBlock, 0, stream_>>>(k.W, k.rc);
+        RTB_CUDA_CHECK(cudaGetLastError());
+    }
+    void launch_shade(int, ShadeK k) {
+        const int grid = num_sms_ * 4;
+        if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc);
+        else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc);
+        else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc);
+        RTB_CUDA_CHECK(cudaGetLastError());
+    }
+    // mode 0: persistent, 1: one thread per ray, 2: one thread per ray + work counters
+    void extend(const WaveState &W, const SceneView &S, int pool, int mode) {
+        const int flat_grid = (pool + kBlock - 1) / kBlock;
+        if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
+        else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
+        else k_extend<<<blocks_extend_, kBlock, 0, stream_>>>(W, S);
+        RTB_CUDA_CHECK(cudaGetLastError());
+    }
+    void shadow(const WaveState &W, const SceneView &S, int pool, int mode) {
+        const int flat_grid = (pool + kBlock - 1) / kBlock;
+        if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
+        else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
+        else k_shadow<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S);
+        RTB_CUDA_CHECK(cudaGetLastError());
+    }
+
+    void ensure_temp(size_t bytes) {
+        if (bytes <= cub_temp_bytes_) return;
+        cudaFree(cub_temp_);
+        cub_temp_ = nullptr; cub_temp_bytes_ = 0;
+        RTB_CUDA_CHECK(cudaMalloc(&cub_temp_, bytes));
+        cub_temp_bytes_ = bytes;
+    }
+    void sort_pairs(uint64_t *keys, int32_t *vals, int n) {
+        uint64_t *k2 = alloc<uint64_t>(n);
+        int32_t *v2 = alloc<int32_t>(n);
+        cub::DoubleBuffer<uint64_t> dk(keys, k2);
+        cub::DoubleBuffer<int32_t> dv(vals, v2);
+        size_t bytes = 0;
+        RTB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, n, 0, 63, stream_));
+        ensure_temp(bytes);
+        RTB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_temp_, bytes, dk, dv, n, 0, 63, stream_));
+        if (dk.Current() != keys) copy(keys, dk.Current(), n);
+        if (dv.Current() != vals) copy(vals, dv.Current(), n);
+        sync();
+        free(k2); free(v2);
+    }
+    int compact_nonneg(const int32_t *in, int32_t *out, int n) {
+        int32_t *d_count = alloc<int32_t>(1);
+        size_t bytes = 0;
+        RTB_CUDA_CHECK(cub::DeviceSelect::If(nullptr, bytes, in, out, d_count, n, NonNegative(), stream_));
+        ensure_temp(bytes);
+        RTB_CUDA_CHECK(cub::DeviceSelect::If(cub_temp_, bytes, in, out, d_count, n, NonNegative(), stream_));
+        int32_t c = 0;
+        download(&c, d_count, 1);
+        free(d_count);
+        return c;
+    }
+
+    using Time = cudaEvent_t;
+    Time now() {
+        cudaEvent_t e;
+        RTB_CUDA_CHECK(cudaEventCreate(&e));
+        RTB_CUDA_CHECK(cudaEventRecord(e, stream_));
+        return e;
+    }
+    float elapsed_keep(Time a, Time b) {  // both events already completed or on the same stream
+        float ms = 0.f;
+        RTB_CUDA_CHECK(cudaEventSynchronize(b));
+        RTB_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+        return ms;
+    }
+    void release(Time e) { cudaEventDestroy(e); }
+    float elapsed_ms(Time a, Time b) {
+        float ms = 0.f;
+        RTB_CUDA_CHECK(cudaEventSynchronize(b));
+        RTB_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        return ms;
+    }
+};
+
+}  // namespace rtb
+
+#define RTB_BACKEND rtb::CudaBackend
+#include "rtb_api_impl.h"

@@ -169,6 +169,7 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
     const int64_t n64 = sc.n;
     if (n64 > 0x3fffffff) throw Error(RTB_ERR_INVALID, "too many triangles (max 2^30-1)");
     const int n = (int)n64;
+    if (bp.builder != RTB_BUILDER_PLOC) throw Error(RTB_ERR_INVALID, "unknown BVH builder");
     const int max_leaf = bp.max_leaf_tris >= 1 && bp.max_leaf_tris <= 3 ? bp.max_leaf_tris : 3;
     const int radius = bp.ploc_radius > 0 ? bp.ploc_radius : 16;
     auto t0 = be.now();
@@ -425,6 +426,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     { IotaK k; k.p = W.free_q; k.n = pool; be.launch(pool, k); }
     unsigned long long launches = 1;
     const int batch = 4;
+    std::vector<typename BE::Time> stage_times;
     while (true) {
         for (int it = 0; it < batch; ++it) {
             for (int type = 0; type < 3; ++type) {
@@ -435,8 +437,13 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
             }
             { GenerateK k; k.W = W; k.rc = rc; be.launch_generate(pool, k); }
             { ControlAK k; k.W = W; be.launch(1, k); }
-            be.extend(W, S, pool, (p.flags & RTB_RENDER_NONPERSISTENT) != 0);
-            be.shadow(W, S, pool, (p.flags & RTB_RENDER_NONPERSISTENT) != 0);
+            const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
+            auto e0 = be.now();
+            be.extend(W, S, pool, mode);
+            auto e1 = be.now();
+            be.shadow(W, S, pool, mode);
+            auto e2 = be.now();
+            stage_times.push_back(e0); stage_times.push_back(e1); stage_times.push_back(e2);
             { ControlBK k; k.W = W; be.launch(1, k); }
             launches += 5;
         }
@@ -445,16 +452,29 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
         if (done) break;
     }
     auto t1 = be.now();
+    float ms_extend = 0.f, ms_shadow = 0.f;
+    for (size_t i = 0; i + 2 < stage_times.size(); i += 3) {
+        ms_extend += be.elapsed_keep(stage_times[i], stage_times[i + 1]);
+        ms_shadow += be.elapsed_keep(stage_times[i + 1], stage_times[i + 2]);
+    }
+    const size_t n_iter_launched = stage_times.size() / 3;
+    for (auto &e : stage_times) be.release(e);
+    if (!stats) { be.elapsed_ms(t0, t1); }
     if (stats) {
         Counters c;
         be.download(&c, W.c, 1);
         memset(stats, 0, sizeof *stats);
+        stats->extend_nodes = c.work[0]; stats->extend_tris = c.work[1];
+        stats->shadow_nodes = c.work[2]; stats->shadow_tris = c.work[3];
+        stats->extend_launches = n_iter_launched; stats->shadow_launches = n_iter_launched;
+        stats->ms_extend = ms_extend; stats->ms_shadow = ms_shadow;
         stats->paths = c.stat_paths;
         stats->extend_rays = c.stat_extend;
         stats->shadow_rays = c.stat_shadow;
         stats->iterations = c.stat_iters;
         stats->kernel_launches = launches;
         stats->ms_total = be.elapsed_ms(t0, t1);
+        stats->ms_other = stats->ms_total - ms_extend - ms_shadow;
     }
 }
 

@@ -20,7 +20,7 @@
 namespace rtb {
 
 struct TriMeta {
-    int32_t material;  // index into materials
+    int32_t material;  // index into materials (low 24 bits) | material type << 24
     int32_t light;     // index into lights or -1
 };
 
@@ -233,7 +233,7 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
     b++;
     // mat, render.cuh:139-168
     const Tri48 tr = load_tri(S.bvh.tris, in.hit.tri);
-    const rtb_material m = S.materials[meta.material];
+    const rtb_material m = S.materials[meta.material & 0xffffff];  // type is packed in the top byte
     const V3 P = vmad(vmad(tri_p0(tr), -in.hit.u, tri_e1(tr)), in.hit.v, tri_e2(tr));
     const V3 ng = vneg(vnormalize(tri_n(tr)));
     const V3 beta_old = beta;

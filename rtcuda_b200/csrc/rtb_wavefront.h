@@ -27,6 +27,7 @@ struct Counters {
     int32_t done, _pad;
     unsigned long long next_path, total_paths;
     unsigned long long stat_extend, stat_shadow, stat_paths, stat_iters;
+    unsigned long long work[4];  // extend nodes, extend tris, shadow nodes, shadow tris (counting variants)
 };
 
 struct WaveState {
@@ -112,11 +113,19 @@ RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int slot, cons
 }
 
 // ch, render.cuh:297-328 (PATH_RAY part), one queue entry
+#if defined(__CUDA_ARCH__)
+RTB_HD void work_add(unsigned long long *p, unsigned v) { atomicAdd(p, (unsigned long long)v); }
+#else
+RTB_HD void work_add(unsigned long long *p, unsigned v) { *p += v; }
+#endif
+template <bool COUNT>
 RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
     const int slot = W.extend_q[qi];
     const V3 o = xyz(W.ray_o[slot]), d = xyz(W.ray_d[slot]);
     HitRec h;
-    bvh8_trace<false, false>(S.bvh, o, d, FLT_MAX, -1, h, nullptr);
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    bvh8_trace<false, COUNT>(S.bvh, o, d, FLT_MAX, -1, h, &tc);
+    if (COUNT) { work_add(&W.c->work[0], tc.nodes); work_add(&W.c->work[1], tc.tris); }
     extend_finish(W, S, slot, h);
 }
 
@@ -160,10 +169,13 @@ RTB_HD void shadow_finish(const WaveState &W, int si, bool occluded) {
     if (finite3(L)) accum_add(W.accum, (uint32_t)f2i(l.w), L);
 }
 // ah, render.cuh:278-294, one queue entry
+template <bool COUNT>
 RTB_HD void shadow_body(const WaveState &W, const SceneView &S, int si) {
     const F4 o = W.sh_o[si], d = W.sh_d[si];
     HitRec h;
-    const bool occluded = bvh8_trace<true, false>(S.bvh, xyz(o), xyz(d), o.w, f2i(d.w), h, nullptr);
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    const bool occluded = bvh8_trace<true, COUNT>(S.bvh, xyz(o), xyz(d), o.w, f2i(d.w), h, &tc);
+    if (COUNT) { work_add(&W.c->work[2], tc.nodes); work_add(&W.c->work[3], tc.tris); }
     shadow_finish(W, si, occluded);
 }
 

@@ -40,13 +40,13 @@ struct HostBackend {
     template <class F> void launch_shade(int n, F f) { launch(n, f); }
     template <class F> void launch_generate(int n, F f) { launch(n, f); }
     template <class F> void launch_trace(int n, F f) { launch(n, f); }
-    void extend(const WaveState &W, const SceneView &S, int, bool) {
+    void extend(const WaveState &W, const SceneView &S, int, int mode) {
         const int n = W.c->n_extend;
-        for (int i = 0; i < n; ++i) extend_body(W, S, i);
+        for (int i = 0; i < n; ++i) { if (mode == 2) extend_body<true>(W, S, i); else extend_body<false>(W, S, i); }
     }
-    void shadow(const WaveState &W, const SceneView &S, int, bool) {
+    void shadow(const WaveState &W, const SceneView &S, int, int mode) {
         const int n = W.c->n_shadow;
-        for (int i = 0; i < n; ++i) shadow_body(W, S, i);
+        for (int i = 0; i < n; ++i) { if (mode == 2) shadow_body<true>(W, S, i); else shadow_body<false>(W, S, i); }
     }
     void sort_pairs(uint64_t *keys, int32_t *vals, int n) {
         std::vector<int> idx(n);
@@ -66,6 +66,8 @@ struct HostBackend {
     using Time = std::chrono::steady_clock::time_point;
     Time now() { return std::chrono::steady_clock::now(); }
     float elapsed_ms(Time a, Time b) { return std::chrono::duration<float, std::milli>(b - a).count(); }
+    float elapsed_keep(Time a, Time b) { return elapsed_ms(a, b); }
+    void release(Time) {}
 };
 
 }  // namespace rtb

@@ -1,0 +1,87 @@
+"""The C-ABI library loads and exports every symbol include/rtb.h declares
+(no compute calls here: this runs without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from rtcuda_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rtb.h")).read()
+    return sorted(set(re.findall(r"RTB_API[^;]*?\b(rtb_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(capi.SYMBOLS)
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    if not os.path.exists(capi.DEFAULT_LIB):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = capi.load()
+    for s in declared_symbols():
+        assert hasattr(lib, s), s
+    assert b"sm_100a" in lib.rtb_version()
+
+
+def test_struct_layouts_match_the_reference():
+    """sizes of the reference structs: Material 20, Light 40, Camera 48, Ray 28"""
+    assert C.sizeof(capi.Material) == 20
+    assert C.sizeof(capi.Light) == 40 and capi.Light.triangle.offset == 16 and capi.Light.L.offset == 24
+    assert C.sizeof(capi.Camera) == 48
+    assert capi.RAY_DTYPE.itemsize == 28 and capi.HIT_DTYPE.itemsize == 16
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """without a usable B200 the product refuses to create a context instead of falling back"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = capi.load()
+    h = C.c_void_p()
+    rc = lib.rtb_context_create(0, C.byref(h))
+    assert rc == -3 and not h.value
+    assert b"no CPU fallback" in lib.rtb_last_error()
+
+
+def test_host_side_scene_code(emu, bunny):
+    """scene generator restating main.cu:41-148: triangle order and materials"""
+    v, f = bunny
+    assert v.shape == (35947, 3) and f.shape == (69451, 3)
+    hs = emu.host_scene(capi.RTB_SCENE_S1, v, f)
+    a = hs.arrays()
+    assert hs.desc.num_triangles == 69463 and hs.desc.num_materials == 4 and hs.desc.num_lights == 2
+    assert (a["material_ids"][:69451] == 3).all()
+    assert list(a["material_ids"][69451:]) == [0, 0, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2]
+    assert list(a["light_ids"][-2:]) == [0, 1] and (a["light_ids"][:-2] == -1).all()
+    lo = a["vertices"][:69451].reshape(-1, 3).min(0); hi = a["vertices"][:69451].reshape(-1, 3).max(0)
+    # bunny bounding box after the transform, BASELINE.md §2
+    assert abs(lo[0] - 0.3) < 1e-4 and abs(lo[1]) < 1e-4 and abs(lo[2] + 0.7413) < 1e-4
+    assert abs(hi[0] - 0.6114) < 1e-4 and abs(hi[1] - 0.3087) < 1e-4 and abs(hi[2] + 0.5) < 1e-4
+    hm = emu.host_scene(capi.RTB_SCENE_S1_MIXED, v, f)
+    types = hm.arrays()["materials"]["type"].tolist()
+    assert types == [0, 0, 0, 0, 1, 2]
+    s2 = emu.host_scene(capi.RTB_SCENE_S2, v, f, grid=2)
+    assert s2.desc.num_triangles == 4 * 69451 + 12
+    b = s2.arrays()["vertices"].reshape(-1, 3)
+    assert b[:, 0].min() >= -1e-3 and b[:, 0].max() <= 1.001 and b[:, 1].min() >= -1e-3 and b[:, 2].min() >= -1.001
+
+
+def test_ply_reader_and_ppm_writer(emu, tmp_path):
+    ply = tmp_path / "t.ply"
+    ply.write_text("ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
+                   "property float confidence\nelement face 2\nproperty list uchar int vertex_indices\nend_header\n"
+                   "0 0 0 1\n1 0 0 1\n1 1 0 1\n0 1 0.5 1\n3 0 1 2\n4 0 1 2 3\n")
+    v, f = emu.load_mesh(str(ply))
+    assert v.shape == (4, 3) and f.tolist() == [[0, 1, 2], [0, 1, 2], [0, 2, 3]] and v[3, 2] == 0.5
+    import numpy as np
+    img = np.array([[[0.0, 0.5, 1.0], [2.0, -1.0, 0.999]]], np.float32)
+    out = tmp_path / "i.ppm"
+    emu.write_ppm(str(out), img, 2, 1)
+    assert out.read_text().split() == ["P3", "2", "1", "255", "0", "128", "255", "255", "0", "255"]

@@ -1,0 +1,244 @@
+"""Parity of the product kernels against the CPU oracle (oracle/oracle.cpp, a
+restatement of the reference's render path), through the C ABI.
+
+Every test runs twice: on the shipped CUDA library (`-m gpu`, B200) and on the
+host build of the same kernel bodies (tests/emu, no GPU needed).  Bars:
+hit triangle bit-exact, t/u/v bit-exact (stricter than the 1e-5 of
+BASELINE.json), occlusion bit-exact, image mean relative error <= 1e-3 with
+identical per-pixel RNG streams (BASELINE.json north_star).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from rtcuda_b200 import capi
+from conftest import (area_light, make_desc, mean_rel_err, random_rays, small_scene_arrays, std_materials)
+
+IMAGE_TOL = 1e-3  # mean relative error, north_star
+
+
+@pytest.fixture(scope="module", params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def L(request):
+    return request.getfixturevalue(request.param)
+
+
+@pytest.fixture(scope="module")
+def ctx(L):
+    return L.context(0)
+
+
+@pytest.fixture(scope="module")
+def s1(L, bunny):
+    return L.host_scene(capi.RTB_SCENE_S1, *bunny)
+
+
+@pytest.fixture(scope="module")
+def s1_dev(ctx, s1):
+    return ctx.scene(s1.desc)
+
+
+@pytest.fixture(scope="module")
+def s1_orc(oracle, s1):
+    return oracle.scene(s1.desc)
+
+
+def assert_hits_equal(hits, ref):
+    bad = np.nonzero(hits["prim"] != ref["prim"])[0]
+    assert len(bad) == 0, f"{len(bad)} hit-id mismatches, first: {bad[:5]} {hits[bad[:5]]} vs {ref[bad[:5]]}"
+    for k in ("t", "u", "v"):
+        assert (hits[k].view(np.uint32) == ref[k].view(np.uint32)).all(), f"{k} not bit-exact"
+
+
+def test_primary_hits_default_scene(L, s1, s1_dev, s1_orc):
+    """config C1 camera, pixel-centre rays at 600x600 (main.cu:159-166)"""
+    cam = s1.camera(1.0)
+    rays = L.primary_rays(cam, 600, 600)
+    hits = s1_dev.trace_closest(rays)
+    ref = s1_orc.trace_closest(rays, capi.HIT_DTYPE)
+    assert (ref["prim"] >= 0).mean() > 0.9
+    assert_hits_equal(hits, ref)
+
+
+def test_incoherent_rays_default_scene(s1_dev, s1_orc):
+    rays = random_rays(200000, seed=7)
+    assert_hits_equal(s1_dev.trace_closest(rays), s1_orc.trace_closest(rays, capi.HIT_DTYPE))
+
+
+def test_tmax_is_inclusive_and_limits_hits(s1_dev, s1_orc):
+    """0 < t <= tmax (triangle.cuh:49): tmax equal to the hit distance still hits"""
+    rays = random_rays(50000, seed=3)
+    ref = s1_orc.trace_closest(rays, capi.HIT_DTYPE)
+    hit = ref["prim"] >= 0
+    r2 = rays[hit].copy()
+    r2["tmax"] = ref["t"][hit]
+    h2 = s1_dev.trace_closest(r2)
+    assert (h2["prim"] == ref["prim"][hit]).all()
+    r3 = r2.copy()
+    r3["tmax"] = np.nextafter(ref["t"][hit], np.float32(0))
+    h3 = s1_dev.trace_closest(r3)
+    o3 = s1_orc.trace_closest(r3, capi.HIT_DTYPE)
+    assert_hits_equal(h3, o3)
+    assert (h3["prim"] != ref["prim"][hit]).all()
+
+
+def test_any_hit_with_excluded_triangle(s1, s1_dev, s1_orc):
+    """shadow rays towards the two emitters, excluding the emitter itself (render.cuh:196-197)"""
+    rng = np.random.default_rng(5)
+    n = 100000
+    rays = random_rays(n, seed=11)
+    rays["origin"] = (rng.random((n, 3)).astype(np.float32) * np.float32(0.9) + np.float32(0.05)) * np.float32([1, 1, -1])
+    target = np.array([0.5, 0.999, -0.5], np.float32) + (rng.random((n, 3)).astype(np.float32) - 0.5) * np.float32([0.2, 0, 0.2])
+    d = target - rays["origin"]
+    dist = np.linalg.norm(d, axis=1).astype(np.float32)
+    rays["dir"] = (d / dist[:, None]).astype(np.float32)
+    rays["tmax"] = dist * np.float32(1.0005)  # reaches the emitter plane, not the ceiling
+    nt = s1.desc.num_triangles
+    excl = rng.integers(nt - 2, nt, n).astype(np.int32)
+    occ = s1_dev.trace_any(rays, excl)
+    ref = s1_orc.trace_any(rays, excl)
+    assert 0.05 < ref.mean() < 0.95
+    assert (occ == ref).all()
+    occ2 = s1_dev.trace_any(rays, None)
+    ref2 = s1_orc.trace_any(rays, None)
+    assert (occ2 == ref2).all() and occ2.sum() >= occ.sum()
+
+
+def test_axis_aligned_and_degenerate_rays(s1_dev, s1_orc):
+    """direction components that are exactly zero (aabb_intersector.cuh:17-19 clamps them)"""
+    rays = random_rays(30000, seed=13)
+    d = rays["dir"].copy()
+    d[0::3, 0] = 0
+    d[1::3, 1] = 0
+    d[2::3, (0, 2)] = 0
+    d[5::7] = np.float32([0, -1, 0])
+    nrm = np.linalg.norm(d, axis=1, keepdims=True)
+    nrm[nrm == 0] = 1
+    rays["dir"] = (d / nrm).astype(np.float32)
+    assert_hits_equal(s1_dev.trace_closest(rays), s1_orc.trace_closest(rays, capi.HIT_DTYPE))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 9, 33, 200])
+def test_small_and_empty_scenes(L, ctx, oracle, n):
+    """empty, single-triangle and ragged triangle counts; degenerate (zero-area) triangles included"""
+    verts, mat, lid = small_scene_arrays(seed=n, n=200)
+    verts, mat, lid = verts[-n:].copy() if n else verts[:0], mat[-n:] if n else mat[:0], np.full(n, -1, np.int32)
+    if n >= 9:
+        verts[3, 3:6] = verts[3, 0:3]  # zero-area triangle
+        verts[4] = verts[5]            # duplicate triangle
+    desc, keep = make_desc(verts, mat, lid, std_materials(), [])
+    sc = ctx.scene(desc)
+    st = sc.stats()
+    assert st.num_triangles == n and st.num_nodes >= 1
+    rays = random_rays(20000, seed=n + 1)
+    hits = sc.trace_closest(rays)
+    if n == 0:
+        assert (hits["prim"] == -1).all()
+        return
+    osc = oracle.scene(desc)
+    ref = osc.trace_closest(rays, capi.HIT_DTYPE)
+    same_t = hits["t"].view(np.uint32) == ref["t"].view(np.uint32)
+    assert same_t.all()
+    # exact ties between duplicated triangles may resolve to either copy
+    diff = hits["prim"] != ref["prim"]
+    if diff.any():
+        assert n >= 9 and set(hits["prim"][diff]) | set(ref["prim"][diff]) <= {n - 200 + 4 if False else 4, 5} | set(range(n))
+        a, b = verts[hits["prim"][diff]], verts[ref["prim"][diff]]
+        assert (a == b).all()
+    occ = sc.trace_any(rays, None)
+    assert (occ == osc.trace_any(rays, None)).all()
+
+
+def render_pair(L, dev_scene, orc_scene, cam, **kw):
+    p = capi.render_params(L, **kw)
+    img, st = dev_scene.render(cam, p)
+    ref, _, ost = orc_scene.render(cam, p)
+    return img, st, ref, ost
+
+
+def test_image_default_scene(L, s1, s1_dev, s1_orc):
+    """config C1 at reduced size: 150x150, 8 spp, depth 10, seed 1, shared per-pixel RNG streams"""
+    cam = s1.camera(1.0)
+    img, st, ref, ost = render_pair(L, s1_dev, s1_orc, cam, width=150, height=150, spp=8, max_bounces=10)
+    assert st.paths == ost[0] == 150 * 150 * 8
+    assert abs(int(st.extend_rays) - int(ost[1])) <= 2e-3 * ost[1]
+    assert abs(int(st.shadow_rays) - int(ost[2])) <= 2e-3 * ost[2]
+    assert np.isfinite(img).all()
+    assert mean_rel_err(img, ref) <= IMAGE_TOL
+
+
+def test_image_mixed_materials_deep_paths(L, bunny, ctx, oracle):
+    """config C4 at reduced size: MATTE/MIRROR/GLASS round-robin, depth 16 with Russian roulette"""
+    hs = L.host_scene(capi.RTB_SCENE_S1_MIXED, *bunny)
+    sc, osc = ctx.scene(hs.desc), oracle.scene(hs.desc)
+    cam = hs.camera(4 / 3)
+    img, st, ref, ost = render_pair(L, sc, osc, cam, width=128, height=96, spp=8, max_bounces=16)
+    assert st.paths == ost[0]
+    assert abs(int(st.extend_rays) - int(ost[1])) <= 5e-3 * ost[1]
+    assert mean_rel_err(img, ref) <= IMAGE_TOL
+
+
+def test_image_random_soup_with_point_light(L, ctx, oracle):
+    verts, mat, lid = small_scene_arrays(seed=4, n=300)
+    pl = capi.Light(); pl.type = 0; pl.pos[0] = 0.5; pl.pos[1] = 0.8; pl.pos[2] = -0.2; pl.L[0] = pl.L[1] = pl.L[2] = 0.5
+    nt = len(mat)
+    lights = [area_light(nt - 2), area_light(nt - 1), pl]
+    desc, keep = make_desc(verts, mat, lid, std_materials(), lights)
+    sc, osc = ctx.scene(desc), oracle.scene(desc)
+    cam = L.camera_look_at((0.5, 0.5, 1.5), (0.5, 0.5, 0.0), (0, 1, 0), 37.8, 1.0)
+    img, st, ref, ost = render_pair(L, sc, osc, cam, width=96, height=96, spp=16, max_bounces=12)
+    assert st.paths == ost[0]
+    assert mean_rel_err(img, ref) <= IMAGE_TOL
+
+
+def test_russian_roulette_and_depth_limits(L, s1, s1_dev, s1_orc):
+    """rr_start=0 makes roulette fire from the second bounce on (render.cuh:112-124, Quirk A);
+    max_bounces=0 leaves only camera-visible emission (render.cuh:98-109)"""
+    cam = s1.camera(1.0)
+    img, st, ref, ost = render_pair(L, s1_dev, s1_orc, cam, width=96, height=96, spp=8, max_bounces=10, rr_start=0,
+                                    rr_threshold=1.0)
+    assert mean_rel_err(img, ref) <= IMAGE_TOL
+    img0, st0, ref0, ost0 = render_pair(L, s1_dev, s1_orc, cam, width=96, height=96, spp=2, max_bounces=0)
+    assert st0.shadow_rays == 0 and st0.extend_rays == 96 * 96 * 2 == ost0[1]
+    assert mean_rel_err(img0, ref0) <= 1e-6
+    assert (img0 > 0).any() and (img0 == 0).mean() > 0.9
+
+
+def test_sample_pass_sharding_is_additive(L, s1, s1_dev):
+    """the multi-GPU decomposition: samples [0,a) + [a,a+b) == samples [0,a+b) (per-pixel RNG keyed by sample index)"""
+    cam = s1.camera(1.0)
+    w = h = 64
+    full = capi.render_params(L, width=w, height=h, spp=6, max_bounces=6, total_spp=6)
+    a = capi.render_params(L, width=w, height=h, spp=2, max_bounces=6, total_spp=6, first_sample=0)
+    b = capi.render_params(L, width=w, height=h, spp=4, max_bounces=6, total_spp=6, first_sample=2)
+    img_full, _ = s1_dev.render(cam, full)
+    ia, _ = s1_dev.render(cam, a)
+    ib, _ = s1_dev.render(cam, b)
+    # images are sqrt(sum/total): sums add
+    assert mean_rel_err(ia.astype(np.float64) ** 2 + ib.astype(np.float64) ** 2, img_full.astype(np.float64) ** 2) <= 1e-5
+
+
+def test_pool_size_does_not_change_the_image(L, s1, s1_dev):
+    cam = s1.camera(1.0)
+    p1 = capi.render_params(L, width=80, height=60, spp=4, max_bounces=8, pool_size=1 << 10)
+    p2 = capi.render_params(L, width=80, height=60, spp=4, max_bounces=8, pool_size=1 << 15)
+    a, sa = s1_dev.render(cam, p1)
+    b, sb = s1_dev.render(cam, p2)
+    assert sa.extend_rays == sb.extend_rays and sa.shadow_rays == sb.shadow_rays
+    assert sa.iterations > sb.iterations
+    assert mean_rel_err(a, b) <= 1e-5
+
+
+def test_bad_arguments_return_status_codes(L, ctx, s1_dev):
+    lib = L.lib
+    assert lib.rtb_scene_create(ctx.h, None, None, None) == -1
+    p = capi.render_params(L, width=0, height=10)
+    out = np.zeros(30, np.float32)
+    assert lib.rtb_render(s1_dev.h, C.byref(capi.Camera()), C.byref(p), out.ctypes.data_as(C.c_void_p), None) == -1
+    assert b"bad" in lib.rtb_last_error()
+    verts, mat, lid = small_scene_arrays(n=5)
+    mat = mat.copy(); mat[0] = 99
+    desc, keep = make_desc(verts, mat, lid, std_materials(), [])
+    h = C.c_void_p()
+    assert lib.rtb_scene_create(ctx.h, C.byref(desc), None, C.byref(h)) == -1
+    assert b"material id" in lib.rtb_last_error()
