@@ -106,6 +106,7 @@ struct CudaBackend {
     int blocks_extend_ = 0, blocks_shadow_ = 0;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
+    int32_t *d_count_ = nullptr;
 
     explicit CudaBackend(int device) {
         int count = 0;
@@ -133,6 +134,7 @@ struct CudaBackend {
         if (dev_ < 0) return;
         cudaSetDevice(dev_);
         cudaFree(cub_temp_);
+        cudaFree(d_count_);
         if (stream_) cudaStreamDestroy(stream_);
     }
     CudaBackend(const CudaBackend &) = delete;
@@ -219,14 +221,14 @@ struct CudaBackend {
         free(k2); free(v2);
     }
     int compact_nonneg(const int32_t *in, int32_t *out, int n) {
-        int32_t *d_count = alloc<int32_t>(1);
+        if (!d_count_) d_count_ = alloc<int32_t>(1);
+        int32_t *d_count = d_count_;
         size_t bytes = 0;
         RTB_CUDA_CHECK(cub::DeviceSelect::If(nullptr, bytes, in, out, d_count, n, NonNegative(), stream_));
         ensure_temp(bytes);
         RTB_CUDA_CHECK(cub::DeviceSelect::If(cub_temp_, bytes, in, out, d_count, n, NonNegative(), stream_));
         int32_t c = 0;
         download(&c, d_count, 1);
-        free(d_count);
         return c;
     }
 
