@@ -11,8 +11,9 @@
 //   k_shade<type>         grid-stride over one material queue (replaces mat +
 //                         init, render.cuh:84-248)
 //   k_generate            grid-stride over the free-slot queue (gen, :250-275)
-//   k_control_a/b         single-thread queue bookkeeping (replaces the four
-//                         blocking 4-byte device->host copies per iteration,
+//   k_control             single-thread queue bookkeeping; raises `done` in
+//                         mapped host memory (replaces the four blocking
+//                         4-byte device->host copies per iteration,
 //                         render.cuh:433-445)
 //   k_for<Functor>        one thread per element for builder / utility bodies
 #include <cuda_runtime.h>
@@ -40,25 +41,24 @@ __global__ void __launch_bounds__(kBlock) k_for(int n, F f) {
     if (i < n) f(i);
 }
 
-__global__ void __launch_bounds__(kBlock) k_generate(WaveState W, RenderConsts rc) {
-    const int n = W.c->n_free;
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) generate_body(W, rc, i);
+__global__ void __launch_bounds__(kBlock) k_generate(WaveState W, RenderConsts rc, int parity) {
+    const int n = generate_count(W, parity);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) generate_body(W, rc, parity, i);
 }
 
 template <int TYPE>
-__global__ void __launch_bounds__(kBlock) k_shade(WaveState W, SceneView S, RenderConsts rc) {
+__global__ void __launch_bounds__(kBlock) k_shade(WaveState W, SceneView S, RenderConsts rc, int parity) {
     const int n = W.c->n_mat[TYPE];
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) shade_body(W, S, rc, TYPE, i);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) shade_body<TYPE>(W, S, rc, parity, i);
 }
 
-__global__ void k_control_a(WaveState W) { control_a_body(W); }
-__global__ void k_control_b(WaveState W) { control_b_body(W); }
+__global__ void k_control(WaveState W, int parity) { control_body(W, parity); }
 
 // Persistent traversal: every warp pulls batches of 32 rays until the queue is
 // drained, so a long ray only delays its own warp's next fetch, not a whole
 // block's retirement, and the launch shape is independent of the queue size.
-__global__ void __launch_bounds__(kBlock) k_extend(WaveState W, SceneView S) {
-    const int n = W.c->n_extend;
+__global__ void __launch_bounds__(kBlock) k_extend(WaveState W, SceneView S, int parity) {
+    const int n = W.c->n_extend[parity];
     const unsigned lane = threadIdx.x & 31u;
     while (true) {
         int base = 0;
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(kBlock) k_extend(WaveState W, SceneView S) {
         __syncwarp();
     }
 }
-__global__ void __launch_bounds__(kBlock) k_shadow(WaveState W, SceneView S) {
-    const int n = W.c->n_shadow;
+__global__ void __launch_bounds__(kBlock) k_shadow(WaveState W, SceneView S, int parity) {
+    const int n = W.c->n_shadow[parity];
     const unsigned lane = threadIdx.x & 31u;
     while (true) {
         int base = 0;
@@ -85,14 +85,14 @@ __global__ void __launch_bounds__(kBlock) k_shadow(WaveState W, SceneView S) {
 }
 // one thread per queue entry (A/B against the persistent kernels; COUNT = work counters)
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_extend_flat(WaveState W, SceneView S) {
+__global__ void __launch_bounds__(kBlock) k_extend_flat(WaveState W, SceneView S, int parity) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i < W.c->n_extend) extend_body<COUNT>(W, S, i);
+    if (i < W.c->n_extend[parity]) extend_body<COUNT>(W, S, i);
 }
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S) {
+__global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S, int parity) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i < W.c->n_shadow) shadow_body<COUNT>(W, S, i);
+    if (i < W.c->n_shadow[parity]) shadow_body<COUNT>(W, S, i);
 }
 
 struct NonNegative {
@@ -107,6 +107,7 @@ struct CudaBackend {
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
+    int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
 
     explicit CudaBackend(int device) {
         int count = 0;
@@ -124,6 +125,15 @@ struct CudaBackend {
         num_sms_ = prop.multiProcessorCount;
         RTB_CUDA_CHECK(cudaSetDevice(dev_));
         RTB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamDefault));
+        // stream-ordered allocator that keeps freed blocks: scene builds and renders reuse memory
+        // instead of paying cudaMalloc/cudaFree (each an implicit device synchronisation) every call
+        cudaMemPool_t mp;
+        RTB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&mp, dev_));
+        unsigned long long keep = ~0ull;
+        RTB_CUDA_CHECK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+        RTB_CUDA_CHECK(cudaHostAlloc((void **)&h_done_, sizeof(int32_t), cudaHostAllocMapped));
+        RTB_CUDA_CHECK(cudaHostGetDevicePointer((void **)&d_done_, h_done_, 0));
+        *h_done_ = 0;
         int per_sm = 0;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend, kBlock, 0));
         blocks_extend_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
@@ -133,9 +143,11 @@ struct CudaBackend {
     ~CudaBackend() {
         if (dev_ < 0) return;
         cudaSetDevice(dev_);
-        cudaFree(cub_temp_);
-        cudaFree(d_count_);
-        if (stream_) cudaStreamDestroy(stream_);
+        if (stream_) cudaStreamSynchronize(stream_);
+        if (cub_temp_) cudaFreeAsync(cub_temp_, stream_);
+        if (d_count_) cudaFreeAsync(d_count_, stream_);
+        if (h_done_) cudaFreeHost(h_done_);
+        if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
     }
     CudaBackend(const CudaBackend &) = delete;
     CudaBackend &operator=(const CudaBackend &) = delete;
@@ -147,10 +159,10 @@ struct CudaBackend {
 
     template <class T> T *alloc(size_t n) {
         void *p = nullptr;
-        RTB_CUDA_CHECK(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+        RTB_CUDA_CHECK(cudaMallocAsync(&p, sizeof(T) * (n ? n : 1), stream_));
         return (T *)p;
     }
-    void free(void *p) { if (p) cudaFree(p); }
+    void free(void *p) { if (p) cudaFreeAsync(p, stream_); }
     template <class T> void upload(T *dst, const T *src, size_t n) {
         RTB_CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, stream_));
         RTB_CUDA_CHECK(cudaStreamSynchronize(stream_));  // src may be a temporary
@@ -170,40 +182,46 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     template <class F> void launch_trace(int n, F f) { launch(n, f); }
-    void launch(int, ControlAK k) { k_control_a<<<1, 1, 0, stream_>>>(k.W); RTB_CUDA_CHECK(cudaGetLastError()); }
-    void launch(int, ControlBK k) { k_control_b<<<1, 1, 0, stream_>>>(k.W); RTB_CUDA_CHECK(cudaGetLastError()); }
-    void launch_generate(int, GenerateK k) {
-        k_generate<<<num_sms_ * 4, kBlock, 0, stream_>>>(k.W, k.rc);
+    void generate(const GenerateK &k) {
+        k_generate<<<num_sms_ * 4, kBlock, 0, stream_>>>(k.W, k.rc, k.parity);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
-    void launch_shade(int, ShadeK k) {
+    void shade(const ShadeK &k) {
         const int grid = num_sms_ * 4;
-        if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc);
-        else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc);
-        else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc);
+        if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
+        else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
+        else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
+        RTB_CUDA_CHECK(cudaGetLastError());
+    }
+    void control(const WaveState &W, int parity) {
+        k_control<<<1, 1, 0, stream_>>>(W, parity);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     // mode 0: persistent, 1: one thread per ray, 2: one thread per ray + work counters
-    void extend(const WaveState &W, const SceneView &S, int pool, int mode) {
-        const int flat_grid = (pool + kBlock - 1) / kBlock;
-        if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else k_extend<<<blocks_extend_, kBlock, 0, stream_>>>(W, S);
+    void extend(const WaveState &W, const SceneView &S, int parity, int mode) {
+        const int flat_grid = (W.pool + kBlock - 1) / kBlock;
+        if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
+        else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
+        else k_extend<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
-    void shadow(const WaveState &W, const SceneView &S, int pool, int mode) {
-        const int flat_grid = (pool + kBlock - 1) / kBlock;
-        if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else k_shadow<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S);
+    void shadow(const WaveState &W, const SceneView &S, int parity, int mode) {
+        const int flat_grid = (W.pool + kBlock - 1) / kBlock;
+        if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
+        else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
+        else k_shadow<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
+    int32_t *done_flag_device() { return d_done_; }
+    void reset_done() { *(volatile int32_t *)h_done_ = 0; }
+    bool done() const { return *(volatile int32_t *)h_done_ != 0; }
+    void wait(cudaEvent_t e) { RTB_CUDA_CHECK(cudaEventSynchronize(e)); }
 
     void ensure_temp(size_t bytes) {
         if (bytes <= cub_temp_bytes_) return;
-        cudaFree(cub_temp_);
+        if (cub_temp_) cudaFreeAsync(cub_temp_, stream_);
         cub_temp_ = nullptr; cub_temp_bytes_ = 0;
-        RTB_CUDA_CHECK(cudaMalloc(&cub_temp_, bytes));
+        RTB_CUDA_CHECK(cudaMallocAsync(&cub_temp_, bytes, stream_));
         cub_temp_bytes_ = bytes;
     }
     void sort_pairs(uint64_t *keys, int32_t *vals, int n) {

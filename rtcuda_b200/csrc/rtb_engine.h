@@ -60,11 +60,8 @@ struct IngestK {
         if (tm.light >= 0) light_tri[tm.light] = i;
     }
 };
-struct GenerateK { WaveState W; RenderConsts rc; RTB_HD void operator()(int i) const { generate_body(W, rc, i); } };
-struct ShadeK { WaveState W; SceneView S; RenderConsts rc; int type; RTB_HD void operator()(int i) const { shade_body(W, S, rc, type, i); } };
-struct ControlAK { WaveState W; RTB_HD void operator()(int) const { control_a_body(W); } };
-struct ControlBK { WaveState W; RTB_HD void operator()(int) const { control_b_body(W); } };
-struct IotaK { int32_t *p; int n; RTB_HD void operator()(int i) const { if (i < n) p[i] = i; } };
+struct GenerateK { WaveState W; RenderConsts rc; int parity; };
+struct ShadeK { WaveState W; SceneView S; RenderConsts rc; int type, parity; };
 struct TonemapK {  // post_process_framebuffer, render.cuh:330-338
     const float *in; float *out; int64_t n; float inv_spp;
     RTB_HD void operator()(int i) const { if (i < n) out[i] = fsqrt(fmul(in[i], inv_spp)); }
@@ -133,20 +130,16 @@ struct SceneT {
     }
     void free_wave() {
         if (!pool) return;
-        be->free(W.ray_o); be->free(W.ray_d); be->free(W.hit); be->free(W.beta); be->free(W.pixel); be->free(W.sample);
-        be->free(W.sh_o); be->free(W.sh_d); be->free(W.sh_L); be->free(W.extend_q); be->free(W.mat_q); be->free(W.free_q);
-        be->free(W.c);
+        be->free(W.ea); be->free(W.eb); be->free(W.ec); be->free(W.ma); be->free(W.mb); be->free(W.mc);
+        be->free(W.sh_o); be->free(W.sh_d); be->free(W.sh_L); be->free(W.c);
         pool = 0;
     }
     void ensure_wave(int32_t p) {
         if (pool == p) return;
         free_wave();
-        W.ray_o = be->template alloc<F4>(p); W.ray_d = be->template alloc<F4>(p);
-        W.hit = be->template alloc<F4>(p); W.beta = be->template alloc<F4>(p);
-        W.pixel = be->template alloc<uint32_t>(p); W.sample = be->template alloc<uint32_t>(p);
+        W.ea = be->template alloc<F4>(p); W.eb = be->template alloc<F4>(p); W.ec = be->template alloc<F4>(p);
+        W.ma = be->template alloc<F4>(3 * (size_t)p); W.mb = be->template alloc<F4>(3 * (size_t)p); W.mc = be->template alloc<F4>(3 * (size_t)p);
         W.sh_o = be->template alloc<F4>(p); W.sh_d = be->template alloc<F4>(p); W.sh_L = be->template alloc<F4>(p);
-        W.extend_q = be->template alloc<int32_t>(p); W.mat_q = be->template alloc<int32_t>(3 * (size_t)p);
-        W.free_q = be->template alloc<int32_t>(p);
         W.c = be->template alloc<Counters>(1);
         W.pool = p;
         pool = p;
@@ -400,11 +393,17 @@ SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const 
 }
 
 // ---- wavefront loop ----
+// One iteration = shade (one launch per material type present) -> generate ->
+// control -> extend -> shadow, all on one stream.  The host never waits for an
+// iteration: it keeps two batches of launches in flight and watches a `done`
+// word that the control kernel raises in mapped host memory.
 template <class BE>
 void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_render_params &p, float *d_accum,
                        rtb_render_stats *stats) {
     if (p.width <= 0 || p.height <= 0 || p.spp <= 0 || p.max_bounces < 0 || !d_accum)
         throw Error(RTB_ERR_INVALID, "rtb_render: bad parameters");
+    if (p.max_bounces > kMaxBounces) throw Error(RTB_ERR_INVALID, "rtb_render: max_bounces > 255");
+    if (p.first_sample < 0 || (long long)p.first_sample + p.spp > kMaxSampleIndex) throw Error(RTB_ERR_INVALID, "rtb_render: sample index >= 2^24");
     const unsigned long long total = (unsigned long long)p.width * (unsigned long long)p.height * (unsigned long long)p.spp;
     if ((unsigned long long)p.width * (unsigned long long)p.height > 0x7fffffffull) throw Error(RTB_ERR_INVALID, "image too large");
     int pool = p.pool_size > 0 ? p.pool_size : be.default_pool();
@@ -413,68 +412,71 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     sc.ensure_wave(pool);
     WaveState W = sc.W;
     W.accum = d_accum;
+    W.host_done = be.done_flag_device();
     const SceneView S = sc.view();
     RenderConsts rc;
     rc.cam = cam; rc.width = p.width; rc.height = p.height; rc.spp = p.spp; rc.first_sample = p.first_sample;
     rc.max_bounces = p.max_bounces; rc.rr_start = p.rr_start; rc.rr_threshold = p.rr_threshold; rc.seed = p.seed; rc.flags = p.flags;
     Counters c0;
     memset(&c0, 0, sizeof c0);
-    c0.n_free = pool;
     c0.total_paths = total;
+    be.reset_done();
     auto t0 = be.now();
     be.upload(W.c, &c0, 1);
-    { IotaK k; k.p = W.free_q; k.n = pool; be.launch(pool, k); }
-    unsigned long long launches = 1;
+    unsigned long long launches = 0;
     const int batch = 4;
-    std::vector<typename BE::Time> stage_times;
+    const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
+    const bool time_stages = stats != nullptr;
+    std::vector<typename BE::Time> stage_times, fences;
+    size_t fence_head = 0;
+    int it = 0;
     while (true) {
-        for (int it = 0; it < batch; ++it) {
+        for (int k = 0; k < batch; ++k, ++it) {
+            const int parity = it & 1;
             for (int type = 0; type < 3; ++type) {
                 if (!(sc.type_mask >> type & 1u)) continue;
-                ShadeK k; k.W = W; k.S = S; k.rc = rc; k.type = type;
-                be.launch_shade(pool, k);
+                ShadeK ks; ks.W = W; ks.S = S; ks.rc = rc; ks.type = type; ks.parity = parity;
+                be.shade(ks);
                 ++launches;
             }
-            { GenerateK k; k.W = W; k.rc = rc; be.launch_generate(pool, k); }
-            { ControlAK k; k.W = W; be.launch(1, k); }
-            const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
-            auto e0 = be.now();
-            be.extend(W, S, pool, mode);
-            auto e1 = be.now();
-            be.shadow(W, S, pool, mode);
-            auto e2 = be.now();
-            stage_times.push_back(e0); stage_times.push_back(e1); stage_times.push_back(e2);
-            { ControlBK k; k.W = W; be.launch(1, k); }
-            launches += 5;
+            { GenerateK kg; kg.W = W; kg.rc = rc; kg.parity = parity; be.generate(kg); }
+            be.control(W, parity);
+            if (time_stages) stage_times.push_back(be.now());
+            be.extend(W, S, parity, mode);
+            if (time_stages) stage_times.push_back(be.now());
+            be.shadow(W, S, parity, mode);
+            if (time_stages) stage_times.push_back(be.now());
+            launches += 4;
         }
-        int32_t done = 0;
-        be.download(&done, &W.c->done, 1);
-        if (done) break;
+        fences.push_back(be.now());
+        if (fences.size() - fence_head > 2) be.wait(fences[fence_head++]);
+        if (be.done()) break;
     }
     auto t1 = be.now();
+    be.wait(t1);
+    for (auto &e : fences) be.release(e);
     float ms_extend = 0.f, ms_shadow = 0.f;
     for (size_t i = 0; i + 2 < stage_times.size(); i += 3) {
         ms_extend += be.elapsed_keep(stage_times[i], stage_times[i + 1]);
         ms_shadow += be.elapsed_keep(stage_times[i + 1], stage_times[i + 2]);
     }
-    const size_t n_iter_launched = stage_times.size() / 3;
     for (auto &e : stage_times) be.release(e);
-    if (!stats) { be.elapsed_ms(t0, t1); }
+    const float ms_total = be.elapsed_ms(t0, t1);
     if (stats) {
         Counters c;
         be.download(&c, W.c, 1);
         memset(stats, 0, sizeof *stats);
-        stats->extend_nodes = c.work[0]; stats->extend_tris = c.work[1];
-        stats->shadow_nodes = c.work[2]; stats->shadow_tris = c.work[3];
-        stats->extend_launches = n_iter_launched; stats->shadow_launches = n_iter_launched;
-        stats->ms_extend = ms_extend; stats->ms_shadow = ms_shadow;
         stats->paths = c.stat_paths;
         stats->extend_rays = c.stat_extend;
         stats->shadow_rays = c.stat_shadow;
         stats->iterations = c.stat_iters;
         stats->kernel_launches = launches;
-        stats->ms_total = be.elapsed_ms(t0, t1);
-        stats->ms_other = stats->ms_total - ms_extend - ms_shadow;
+        stats->extend_nodes = c.work[0]; stats->extend_tris = c.work[1];
+        stats->shadow_nodes = c.work[2]; stats->shadow_tris = c.work[3];
+        stats->extend_launches = c.stat_iters; stats->shadow_launches = c.stat_iters;
+        stats->ms_extend = ms_extend; stats->ms_shadow = ms_shadow;
+        stats->ms_total = ms_total;
+        stats->ms_other = ms_total - ms_extend - ms_shadow;
     }
 }
 

@@ -202,7 +202,9 @@ struct PathStepOut {
 };
 
 // One visit of a path that HIT something: everything the reference does to it
-// between two closest-hit traversals.
+// between two closest-hit traversals.  MT >= 0 tells the compiler the material
+// type of the hit (the per-type shade kernels), -1 = read it from the material.
+template <int MT>
 RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStepIn &in, PathStepOut &out) {
     out.emit = false; out.extend = false; out.shadow = false;
     const TriMeta meta = S.tri_meta[in.hit.tri];
@@ -233,7 +235,8 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
     b++;
     // mat, render.cuh:139-168
     const Tri48 tr = load_tri(S.bvh.tris, in.hit.tri);
-    const rtb_material m = S.materials[meta.material & 0xffffff];  // type is packed in the top byte
+    rtb_material m = S.materials[meta.material & 0xffffff];  // type is packed in the top byte
+    if (MT >= 0) m.type = MT;
     const V3 P = vmad(vmad(tri_p0(tr), -in.hit.u, tri_e1(tr)), in.hit.v, tri_e2(tr));
     const V3 ng = vneg(vnormalize(tri_n(tr)));
     const V3 beta_old = beta;

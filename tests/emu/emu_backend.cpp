@@ -37,17 +37,32 @@ struct HostBackend {
     template <class T> void zero(T *p, size_t n) { memset(p, 0, sizeof(T) * n); }
 
     template <class F> void launch(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
-    template <class F> void launch_shade(int n, F f) { launch(n, f); }
-    template <class F> void launch_generate(int n, F f) { launch(n, f); }
     template <class F> void launch_trace(int n, F f) { launch(n, f); }
-    void extend(const WaveState &W, const SceneView &S, int, int mode) {
-        const int n = W.c->n_extend;
+    void shade(const ShadeK &k) {
+        const int n = k.W.c->n_mat[k.type];
+        for (int i = 0; i < n; ++i) {
+            if (k.type == 0) shade_body<0>(k.W, k.S, k.rc, k.parity, i);
+            else if (k.type == 1) shade_body<1>(k.W, k.S, k.rc, k.parity, i);
+            else shade_body<2>(k.W, k.S, k.rc, k.parity, i);
+        }
+    }
+    void generate(const GenerateK &k) {
+        const int n = generate_count(k.W, k.parity);
+        for (int i = 0; i < n; ++i) generate_body(k.W, k.rc, k.parity, i);
+    }
+    void control(const WaveState &W, int parity) { control_body(W, parity); }
+    void extend(const WaveState &W, const SceneView &S, int parity, int mode) {
+        const int n = W.c->n_extend[parity];
         for (int i = 0; i < n; ++i) { if (mode == 2) extend_body<true>(W, S, i); else extend_body<false>(W, S, i); }
     }
-    void shadow(const WaveState &W, const SceneView &S, int, int mode) {
-        const int n = W.c->n_shadow;
+    void shadow(const WaveState &W, const SceneView &S, int parity, int mode) {
+        const int n = W.c->n_shadow[parity];
         for (int i = 0; i < n; ++i) { if (mode == 2) shadow_body<true>(W, S, i); else shadow_body<false>(W, S, i); }
     }
+    int32_t done_word_ = 0;
+    int32_t *done_flag_device() { return &done_word_; }
+    void reset_done() { done_word_ = 0; }
+    bool done() const { return done_word_ != 0; }
     void sort_pairs(uint64_t *keys, int32_t *vals, int n) {
         std::vector<int> idx(n);
         std::iota(idx.begin(), idx.end(), 0);
@@ -68,6 +83,7 @@ struct HostBackend {
     float elapsed_ms(Time a, Time b) { return std::chrono::duration<float, std::milli>(b - a).count(); }
     float elapsed_keep(Time a, Time b) { return elapsed_ms(a, b); }
     void release(Time) {}
+    void wait(Time) {}
 };
 
 }  // namespace rtb
