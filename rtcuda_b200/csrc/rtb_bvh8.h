@@ -64,7 +64,7 @@ RTB_HD uint32_t quant_exponent(float extent) {
     uint32_t e = (b >> 23) & 0xffu;
     if (b & 0x7fffffu) e += 1;
     if (e < 40u) e = 40u;
-    if (e > 250u) e = 250u;
+    if (e > 235u) e = 235u;  // the traversal adds 15 to it (node_frame)
     return e;
 }
 RTB_HD uint32_t quant_lo(float lo, float p, uint32_t e) {
@@ -101,25 +101,72 @@ RTB_HD RaySetup ray_setup(V3 o, V3 d) {
 
 RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
+// Byte j of `w` as the float 1 + q * 2^-15, built by ONE byte permute that drops
+// q into mantissa bits 8..15 of 1.0f.  An integer->float conversion (I2F) per
+// plane made the XU pipe the limiter of the traversal kernels (ncu, r1:
+// sm__inst_executed_pipe_xu 74-80 %); PRMT runs on the ALU pipe.
+template <int J>
+RTB_HD float byte_as_unit_float(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (J << 4)));
+#else
+    return u2f(0x3F800000u | (((w >> (8 * J)) & 0xffu) << 8));
+#endif
+}
+
 // Slab-test the 8 quantised child boxes of one node against the ray segment
 // [0, tmax]; returns the hit mask: inner children in bits 24..31 at position
 // 24 + (slot ^ octinv) (so the highest set bit is the nearest child in octant
 // order), triangles of leaf children in bits 0..23.
-RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 &n3, const Q4 &n4,
-                             const RaySetup &r, float tmax) {
-    const float ax = fmul(u2f(byte_of(n0.w, 0) << 23), r.idir.x);
-    const float ay = fmul(u2f(byte_of(n0.w, 1) << 23), r.idir.y);
-    const float az = fmul(u2f(byte_of(n0.w, 2) << 23), r.idir.z);
+//
+// Plane distance: t = (origin_node + q*2^e - origin_ray) / d.  With
+// v = 1 + q*2^-15 (see byte_as_unit_float), a = 2^(e+15)/d and
+// c = (origin_node - origin_ray)/d - a this is t = v*a + c: one FMA per plane.
+struct NodeFrame {
+    float ax, ay, az, cx, cy, cz, eps;
+};
+RTB_HD NodeFrame node_frame(const Q4 &n0, const RaySetup &r) {
+    NodeFrame f;
+    f.ax = fmul(u2f((byte_of(n0.w, 0) + 15u) << 23), r.idir.x);
+    f.ay = fmul(u2f((byte_of(n0.w, 1) + 15u) << 23), r.idir.y);
+    f.az = fmul(u2f((byte_of(n0.w, 2) + 15u) << 23), r.idir.z);
     const float bx = fmul(fsub(u2f(n0.x), r.o.x), r.idir.x);
     const float by = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
     const float bz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
+    f.cx = fsub(bx, f.ax); f.cy = fsub(by, f.ay); f.cz = fsub(bz, f.az);
+    // Error bound of the slab arithmetic: an ABSOLUTE error of about
+    // 2^-23 * max(|b|, |a|) (b cancels against q*a when the ray starts close to
+    // the planes) plus a relative 2^-23 * |t|.  The far plane is pushed out by
+    // both so that the box test never culls a triangle the exact reference
+    // test (triangle.cuh:39-58) would accept.
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(bx), fabsf(by)), fabsf(bz)), fmaxf(fmaxf(fabsf(f.ax), fabsf(f.ay)), fabsf(f.az)));
+    f.eps = fmul(m, 4.76837158203125e-07f);  // 2^-21
+    return f;
+}
+template <int J>
+RTB_HD uint32_t child_hit_bits(const NodeFrame &f, uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4,
+                               uint32_t fy4, uint32_t fz4, float tmax, uint32_t octinv) {
+    const float tnx = ffma(byte_as_unit_float<J>(nx4), f.ax, f.cx);
+    const float tny = ffma(byte_as_unit_float<J>(ny4), f.ay, f.cy);
+    const float tnz = ffma(byte_as_unit_float<J>(nz4), f.az, f.cz);
+    const float tfx = ffma(byte_as_unit_float<J>(fx4), f.ax, f.cx);
+    const float tfy = ffma(byte_as_unit_float<J>(fy4), f.ay, f.cy);
+    const float tfz = ffma(byte_as_unit_float<J>(fz4), f.az, f.cz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    if (tn <= ffma(tf, 1.0000019f, f.eps)) {
+        const uint32_t meta = byte_of(meta4, J);
+        const uint32_t bits = meta >> 5;             // unary triangle count, or 1 for an inner child
+        const bool inner = (meta & 0x18u) == 0x18u;  // low 5 bits in 24..31
+        const uint32_t pos = inner ? ((meta & 0x1fu) ^ octinv) : (meta & 0x1fu);
+        return bits << pos;
+    }
+    return 0u;
+}
+RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 &n3, const Q4 &n4,
+                             const RaySetup &r, float tmax) {
+    const NodeFrame f = node_frame(n0, r);
     const bool px = (r.octinv & 1u) != 0, py = (r.octinv & 2u) != 0, pz = (r.octinv & 4u) != 0;
-    // Error bound of the slab arithmetic: t = q*a + b carries an ABSOLUTE error
-    // of about 2^-23 * |b| (b = (origin_node - origin_ray)/d cancels against
-    // q*a when the ray starts close to the planes) plus a relative 2^-23 * |t|.
-    // The far plane is pushed out by both so that the box test never culls a
-    // triangle the exact reference test (triangle.cuh:39-58) would accept.
-    const float eps = fmul(fmaxf(fmaxf(fabsf(bx), fabsf(by)), fabsf(bz)), 4.76837158203125e-07f);  // 2^-21
     uint32_t mask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -129,45 +176,46 @@ RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 
         const uint32_t nx4 = px ? lox : hix, fx4 = px ? hix : lox;
         const uint32_t ny4 = py ? loy : hiy, fy4 = py ? hiy : loy;
         const uint32_t nz4 = pz ? loz : hiz, fz4 = pz ? hiz : loz;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t meta = byte_of(meta4, j);
-            float tnx = ffma((float)byte_of(nx4, j), ax, bx);
-            float tny = ffma((float)byte_of(ny4, j), ay, by);
-            float tnz = ffma((float)byte_of(nz4, j), az, bz);
-            float tfx = ffma((float)byte_of(fx4, j), ax, bx);
-            float tfy = ffma((float)byte_of(fy4, j), ay, by);
-            float tfz = ffma((float)byte_of(fz4, j), az, bz);
-            float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
-            float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (tn <= ffma(tf, 1.0000019f, eps)) {
-                const uint32_t bits = meta >> 5;                       // unary count, or 1 for inner
-                const bool inner = (meta & 0x18u) == 0x18u;            // low 5 bits in 24..31
-                const uint32_t pos = inner ? ((meta & 0x1fu) ^ r.octinv) : (meta & 0x1fu);
-                mask |= bits << pos;
-            }
-        }
+        mask |= child_hit_bits<0>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+        mask |= child_hit_bits<1>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+        mask |= child_hit_bits<2>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+        mask |= child_hit_bits<3>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
     }
     return mask;
 }
 
 constexpr int kStackSize = 48;
 
-// One ray through the tree.  ANY: stop at the first accepted triangle whose
+// One ray through the tree, as a resumable state machine so that the
+// persistent kernels can swap finished rays for new ones while the rest of
+// the warp keeps going.  ANY: stop at the first accepted triangle whose
 // leaf-order index differs from `excluded` (the light's own triangle,
-// bvh.cuh:239-248) and return true.  Otherwise find the closest hit with the
-// reference's accept rule 0 < t <= tmax, tmax shrinking (bvh.cuh:222-236).
+// bvh.cuh:239-248).  Otherwise find the closest hit with the reference's
+// accept rule 0 < t <= tmax, tmax shrinking (bvh.cuh:222-236).
 template <bool ANY, bool COUNT>
-RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, HitRec &hit,
-                       TraceCounters *cnt) {
-    const RaySetup r = ray_setup(o, d);
-    uint32_t stack_x[kStackSize], stack_y[kStackSize];
-    int sp = 0;
-    uint32_t gx = 0, gy = 0x80000000u;  // node group: child base | hits<<24 | imask
-    uint32_t tx = 0, ty = 0;            // triangle group: tri base | hit bits
-    hit.t = 0.f; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
-    bool found = false;
-    while (true) {
+struct Traversal {
+    RaySetup r;
+    float tmax;
+    uint32_t gx, gy;  // node group: child base | hits<<24 | imask
+    int32_t sp, excluded;
+    HitRec hit;
+    bool found;
+    TraceCounters cnt;
+    // the stack lives OUTSIDE the struct (caller-provided arrays) so that the
+    // scalar state above stays in registers instead of following the
+    // dynamically indexed arrays into local memory
+
+    RTB_HD void init(V3 o, V3 d, float tmax_, int32_t excluded_) {
+        r = ray_setup(o, d);
+        tmax = tmax_; excluded = excluded_;
+        gx = 0; gy = 0x80000000u; sp = 0;
+        hit.t = 0.f; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
+        found = false;
+        cnt.nodes = 0; cnt.tris = 0;
+    }
+    // one node (its 8 child boxes) plus the triangles it exposes; false when the ray is finished
+    RTB_HD bool step(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y) {
+        uint32_t tx = 0, ty = 0;  // triangle group: tri base | hit bits
         if (gy & 0xff000000u) {
             const int bit = bfind(gy);
             gy &= ~(1u << bit);
@@ -177,7 +225,7 @@ RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t exclud
             const uint32_t rel = popc(imask & ~(0xffffffffu << slot));
             const Q4 *np = B.nodes + (size_t)(base + rel) * kNodeWords;
             const Q4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
-            if (COUNT) cnt->nodes++;
+            if (COUNT) cnt.nodes++;
             const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, tmax);
             gx = n1.x; gy = (hm & 0xff000000u) | (n0.w >> 24);
             tx = n1.y; ty = hm & 0x00ffffffu;
@@ -187,22 +235,34 @@ RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t exclud
             ty &= ~(1u << bit);
             const int idx = (int)(tx + (uint32_t)bit);
             const Tri48 tr = load_tri(B.tris, idx);
-            if (COUNT) cnt->tris++;
+            if (COUNT) cnt.tris++;
             float t, u, v;
-            if (tri_intersect(tr, o, d, tmax, t, u, v)) {
+            if (tri_intersect(tr, r.o, r.d, tmax, t, u, v)) {
                 if (ANY) {
-                    if (idx != excluded) return true;
+                    if (idx != excluded) { found = true; return false; }
                 } else {
                     tmax = t; hit.t = t; hit.u = u; hit.v = v; hit.tri = idx; found = true;
                 }
             }
         }
         if ((gy & 0xff000000u) == 0) {
-            if (sp == 0) break;
+            if (sp == 0) return false;
             --sp; gx = stack_x[sp]; gy = stack_y[sp];
         }
+        return true;
     }
-    return found;
+};
+
+template <bool ANY, bool COUNT>
+RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, HitRec &hit,
+                       TraceCounters *cnt) {
+    Traversal<ANY, COUNT> T;
+    uint32_t stack_x[kStackSize], stack_y[kStackSize];
+    T.init(o, d, tmax, excluded);
+    while (T.step(B, stack_x, stack_y)) {}
+    hit = T.hit;
+    if (COUNT) { cnt->nodes = T.cnt.nodes; cnt->tris = T.cnt.tris; }
+    return T.found;
 }
 
 }  // namespace rtb

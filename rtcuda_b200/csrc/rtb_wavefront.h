@@ -109,13 +109,7 @@ RTB_HD void generate_body(const WaveState &W, const RenderConsts &rc, int parity
 // ------------------------------------------------------------ extend
 // ch, render.cuh:297-328 (PATH_RAY part), one queue entry.  A miss ends the
 // path (the reference parks the slot until max_bounces, Quirk B).
-template <bool COUNT>
-RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
-    const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi);
-    HitRec h;
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    bvh8_trace<false, COUNT>(S.bvh, xyz(a), xyz(b), FLT_MAX, -1, h, &tc);
-    if (COUNT) { work_add(&W.c->work[0], tc.nodes); work_add(&W.c->work[1], tc.tris); }
+RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const HitRec &h) {
     if (h.tri < 0) return;
     const int type = S.tri_meta[h.tri].material >> 24;
     int j;
@@ -123,10 +117,19 @@ RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
     else if (type == RTB_MIRROR) j = W.pool + queue_push(&W.c->n_mat[1]);
     else j = 2 * W.pool + queue_push(&W.c->n_mat[2]);
     F4 hr; hr.x = h.t; hr.y = h.u; hr.z = h.v; hr.w = i2f(h.tri);
-    const F4 beta = ldg(W.ec + qi);
+    const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi), beta = ldg(W.ec + qi);
     W.ma[j] = f4(xyz(b), a.w);
     W.mb[j] = f4(xyz(beta), b.w);
     W.mc[j] = hr;
+}
+template <bool COUNT>
+RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
+    const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi);
+    HitRec h;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    bvh8_trace<false, COUNT>(S.bvh, xyz(a), xyz(b), FLT_MAX, -1, h, &tc);
+    if (COUNT) { work_add(&W.c->work[0], tc.nodes); work_add(&W.c->work[1], tc.tris); }
+    extend_finish(W, S, qi, h);
 }
 
 // ------------------------------------------------------------ shade
@@ -163,6 +166,12 @@ RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConst
 
 // ------------------------------------------------------------ shadow
 // ah, render.cuh:278-294, one queue entry
+RTB_HD void shadow_finish(const WaveState &W, int si, bool occluded) {
+    if (occluded) return;
+    const F4 l = ldg(W.sh_L + si);
+    const V3 L = xyz(l);
+    if (finite3(L)) accum_add(W.accum, f2u(l.w), L);
+}
 template <bool COUNT>
 RTB_HD void shadow_body(const WaveState &W, const SceneView &S, int si) {
     const F4 o = ldg(W.sh_o + si), d = ldg(W.sh_d + si);
@@ -170,10 +179,7 @@ RTB_HD void shadow_body(const WaveState &W, const SceneView &S, int si) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     const bool occluded = bvh8_trace<true, COUNT>(S.bvh, xyz(o), xyz(d), o.w, f2i(d.w), h, &tc);
     if (COUNT) { work_add(&W.c->work[2], tc.nodes); work_add(&W.c->work[3], tc.tris); }
-    if (occluded) return;
-    const F4 l = ldg(W.sh_L + si);
-    const V3 L = xyz(l);
-    if (finite3(L)) accum_add(W.accum, f2u(l.w), L);
+    shadow_finish(W, si, occluded);
 }
 
 // ------------------------------------------------------------ control
