@@ -63,8 +63,13 @@ __global__ void k_control(WaveState W, int parity) { control_body(W, parity); }
 // new entries while the others keep their traversal state, so short rays
 // (a wall) do not wait for long ones (the bunny) in the same warp.  ncu r1,
 // before this: 6.9-11 of 32 lanes active per instruction in k_extend.
+struct FetchTuning {
+    int refill;  // refill idle lanes when fewer than this many lanes hold a live ray
+    int steps;   // traversal steps between two warp-wide votes
+    int chunk;   // queue entries a warp claims with one atomicAdd
+};
 template <bool ANY>
-__device__ __forceinline__ void persistent_trace(const WaveState &W, const SceneView &S, int parity, int refill) {
+__device__ __forceinline__ void persistent_trace(const WaveState &W, const SceneView &S, int parity, FetchTuning tune) {
     const int n = ANY ? W.c->n_shadow[parity] : W.c->n_extend[parity];
     int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
     const unsigned lane = threadIdx.x & 31u;
@@ -73,47 +78,59 @@ __device__ __forceinline__ void persistent_trace(const WaveState &W, const Scene
     uint32_t stack_x[kStackSize], stack_y[kStackSize];
     bool has = false, exhausted = false;
     int qi = 0;
+    int chunk_next = 0, chunk_end = 0;  // warp-uniform: the part of the queue this warp has claimed
     while (true) {
-        const unsigned need = __ballot_sync(0xffffffffu, !has);
-        if (need != 0u && !exhausted) {
-            const int cnt = __popc(need), leader = __ffs(need) - 1;
-            int base = 0;
-            if ((int)lane == leader) base = atomicAdd(head, cnt);
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (!has) {
-                const int idx = base + __popc(need & lanes_below);
-                if (idx < n) {
-                    qi = idx;
-                    if (ANY) {
-                        const F4 o = ldg(W.sh_o + qi), d = ldg(W.sh_d + qi);
-                        T.init(xyz(o), xyz(d), o.w, f2i(d.w));
-                    } else {
-                        const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi);
-                        T.init(xyz(a), xyz(b), FLT_MAX, -1);
-                    }
-                    has = true;
-                }
+        // hand queue entries to the idle lanes; a new chunk is claimed (one atomic per warp) when the
+        // current one runs out, so most refills cost no global round trip at all
+        unsigned need = __ballot_sync(0xffffffffu, !has);
+        for (int round = 0; round < 2 && need != 0u && !exhausted; ++round) {
+            if (chunk_next >= chunk_end) {
+                int base = 0;
+                if (lane == 0u) base = atomicAdd(head, tune.chunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                chunk_next = base;
+                chunk_end = min(base + tune.chunk, n);
+                if (base >= n) { exhausted = true; break; }
             }
-            if (base + cnt >= n) exhausted = true;  // warp-uniform
+            const int idx = chunk_next + __popc(need & lanes_below);
+            if (!has && idx < chunk_end) {
+                qi = idx;
+                if (ANY) {
+                    const F4 o = ldg(W.sh_o + qi), d = ldg(W.sh_d + qi);
+                    T.init(xyz(o), xyz(d), o.w, f2i(d.w));
+                } else {
+                    const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi);
+                    T.init(xyz(a), xyz(b), FLT_MAX, -1);
+                }
+                has = true;
+            }
+            chunk_next = min(chunk_next + __popc(need), chunk_end);
+            need = __ballot_sync(0xffffffffu, !has);
         }
         unsigned act = __ballot_sync(0xffffffffu, has);
-        if (act == 0u) return;
-        const int keep_going = exhausted ? 1 : refill;
+        if (act == 0u) {
+            if (exhausted) return;
+            continue;  // chunk boundary: claim the next one
+        }
+        const int keep_going = exhausted ? 1 : tune.refill;
         do {
-            if (has && !T.step(S.bvh, stack_x, stack_y)) {
-                if (ANY) shadow_finish(W, qi, T.found);
-                else extend_finish(W, S, qi, T.hit);
-                has = false;
+#pragma unroll 1
+            for (int k = 0; k < tune.steps && has; ++k) {
+                if (!T.step(S.bvh, stack_x, stack_y)) {
+                    if (ANY) shadow_finish(W, qi, T.found);
+                    else extend_finish(W, S, qi, T.hit);
+                    has = false;
+                }
             }
             act = __ballot_sync(0xffffffffu, has);
         } while (__popc(act) >= keep_going);
     }
 }
-__global__ void __launch_bounds__(kBlock, 4) k_extend(WaveState W, SceneView S, int parity, int refill) {
-    persistent_trace<false>(W, S, parity, refill);
+__global__ void __launch_bounds__(kBlock, 4) k_extend(WaveState W, SceneView S, int parity, FetchTuning tune) {
+    persistent_trace<false>(W, S, parity, tune);
 }
-__global__ void __launch_bounds__(kBlock, 4) k_shadow(WaveState W, SceneView S, int parity, int refill) {
-    persistent_trace<true>(W, S, parity, refill);
+__global__ void __launch_bounds__(kBlock, 4) k_shadow(WaveState W, SceneView S, int parity, FetchTuning tune) {
+    persistent_trace<true>(W, S, parity, tune);
 }
 // one thread per queue entry (A/B against the persistent kernels; COUNT = work counters)
 template <bool COUNT>
@@ -140,7 +157,7 @@ struct CudaBackend {
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
     int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
-    int refill_ = 20;       // dynamic-fetch threshold (lanes), RTB_REFILL overrides (tuning)
+    FetchTuning tune_{16, 4, 128};  // RTB_REFILL / RTB_STEPS / RTB_CHUNK override (tuning runs)
     int pool_ = 1 << 23;    // default path pool, RTB_POOL overrides (tuning)
 
     explicit CudaBackend(int device) {
@@ -168,7 +185,9 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaHostAlloc((void **)&h_done_, sizeof(int32_t), cudaHostAllocMapped));
         RTB_CUDA_CHECK(cudaHostGetDevicePointer((void **)&d_done_, h_done_, 0));
         *h_done_ = 0;
-        if (const char *e = getenv("RTB_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) refill_ = v; }
+        if (const char *e = getenv("RTB_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tune_.refill = v; }
+        if (const char *e = getenv("RTB_STEPS")) { int v = atoi(e); if (v >= 1) tune_.steps = v; }
+        if (const char *e = getenv("RTB_CHUNK")) { int v = atoi(e); if (v >= 32) tune_.chunk = v; }
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
         int per_sm = 0;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend, kBlock, 0));
@@ -238,14 +257,14 @@ struct CudaBackend {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
         else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
-        else k_extend<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity, refill_);
+        else k_extend<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shadow(const WaveState &W, const SceneView &S, int parity, int mode) {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
         else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
-        else k_shadow<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity, refill_);
+        else k_shadow<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     int32_t *done_flag_device() { return d_done_; }

@@ -1,0 +1,48 @@
+"""Tuning sweep over the persistent-kernel knobs (RTB_REFILL / RTB_STEPS / RTB_CHUNK / RTB_POOL are read
+when a context is created), one process, one scene build per setting.
+
+    python tools/sweep.py --workload c2 --refill 8,16,24 --steps 1,4,8 --chunk 128 --pool 8388608
+"""
+import argparse
+import itertools
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rtcuda_b200 import capi  # noqa: E402
+
+W = {"c1": (1, 0, 600, 600, 10, 10), "c2": (1, 0, 1920, 1080, 64, 8), "c2s": (1, 0, 1920, 1080, 8, 8),
+     "c3s": (3, 12, 3840, 2160, 2, 8), "c3": (3, 12, 3840, 2160, 16, 8), "c4": (2, 0, 1920, 1080, 64, 16),
+     "c4s": (2, 0, 1920, 1080, 8, 16)}
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="c2")
+ap.add_argument("--refill", default="16")
+ap.add_argument("--steps", default="4")
+ap.add_argument("--chunk", default="128")
+ap.add_argument("--pool", default="8388608")
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--flags", type=int, default=0)
+a = ap.parse_args()
+kind, grid, w, h, spp, depth = W[a.workload]
+L = capi.Lib()
+hs = L.host_scene(kind, *L.load_mesh(), grid=grid)
+cam = hs.camera(w / h)
+print(f"workload {a.workload}: {hs.desc.num_triangles} triangles, {w}x{h}x{spp}spp depth {depth}")
+for refill, steps, chunk, pool in itertools.product(a.refill.split(","), a.steps.split(","), a.chunk.split(","), a.pool.split(",")):
+    os.environ.update(RTB_REFILL=refill, RTB_STEPS=steps, RTB_CHUNK=chunk, RTB_POOL=pool)
+    ctx = L.context(0)
+    sc = ctx.scene(hs.desc)
+    bs = sc.stats()
+    p = capi.render_params(L, width=w, height=h, spp=spp, max_bounces=depth, flags=a.flags)
+    best = None
+    for _ in range(a.reps):
+        img, st = sc.render(cam, p)
+        if best is None or st.ms_total < best.ms_total:
+            best = st
+    rays = best.extend_rays + best.shadow_rays
+    print(f"refill {refill:>2} steps {steps:>2} chunk {chunk:>4} pool {pool:>9}: {best.ms_total:8.2f} ms  extend {best.ms_extend:7.2f} "
+          f"shadow {best.ms_shadow:7.2f} other {best.ms_other:6.2f}  {rays / best.ms_total * 1e-3:8.1f} Mrays/s  "
+          f"iters {best.iterations}  build {bs.build_ms:.1f} ms nodes {bs.num_nodes} sah {bs.sah_cost:.2f} mean {img.mean():.4f}", flush=True)
+    sc.close()
+    del sc, ctx
