@@ -101,10 +101,10 @@ RTB_HD RaySetup ray_setup(V3 o, V3 d) {
 
 RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
-// Byte j of `w` as the float 1 + q * 2^-15, built by ONE byte permute that drops
-// q into mantissa bits 8..15 of 1.0f.  An integer->float conversion (I2F) per
-// plane made the XU pipe the limiter of the traversal kernels (ncu, r1:
-// sm__inst_executed_pipe_xu 74-80 %); PRMT runs on the ALU pipe.
+// A/B variant kept for measurements (decode 1): byte j of `w` as the float
+// 1 + q * 2^-15, built by one byte permute that drops q into mantissa bits
+// 8..15 of 1.0f, instead of an integer->float conversion (XU pipe, 74-80 % busy
+// in the first ncu capture).  It lost on the B200: see profiles/r1_variants.md.
 template <int J>
 RTB_HD float byte_as_unit_float(uint32_t w) {
 #if defined(__CUDA_ARCH__)
@@ -163,9 +163,44 @@ RTB_HD uint32_t child_hit_bits(const NodeFrame &f, uint32_t meta4, uint32_t nx4,
     }
     return 0u;
 }
+// Default decode (0): plane distance with an integer->float conversion per
+// byte, t = q * (2^e/d) + (origin_node - origin_ray)/d
+template <int J>
+RTB_HD uint32_t child_hit_bits_i2f(const NodeFrame &f, uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4,
+                                   uint32_t fy4, uint32_t fz4, float tmax, uint32_t octinv) {
+    const float tnx = ffma((float)byte_of(nx4, J), f.ax, f.cx);
+    const float tny = ffma((float)byte_of(ny4, J), f.ay, f.cy);
+    const float tnz = ffma((float)byte_of(nz4, J), f.az, f.cz);
+    const float tfx = ffma((float)byte_of(fx4, J), f.ax, f.cx);
+    const float tfy = ffma((float)byte_of(fy4, J), f.ay, f.cy);
+    const float tfz = ffma((float)byte_of(fz4, J), f.az, f.cz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    if (tn <= ffma(tf, 1.0000019f, f.eps)) {
+        const uint32_t meta = byte_of(meta4, J);
+        const uint32_t bits = meta >> 5;
+        const bool inner = (meta & 0x18u) == 0x18u;
+        const uint32_t pos = inner ? ((meta & 0x1fu) ^ octinv) : (meta & 0x1fu);
+        return bits << pos;
+    }
+    return 0u;
+}
+RTB_HD NodeFrame node_frame_i2f(const Q4 &n0, const RaySetup &r) {
+    NodeFrame f;
+    f.ax = fmul(u2f(byte_of(n0.w, 0) << 23), r.idir.x);
+    f.ay = fmul(u2f(byte_of(n0.w, 1) << 23), r.idir.y);
+    f.az = fmul(u2f(byte_of(n0.w, 2) << 23), r.idir.z);
+    f.cx = fmul(fsub(u2f(n0.x), r.o.x), r.idir.x);
+    f.cy = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
+    f.cz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
+    f.eps = fmul(fmaxf(fmaxf(fabsf(f.cx), fabsf(f.cy)), fabsf(f.cz)), 4.76837158203125e-07f);
+    return f;
+}
+
+template <int DEC = RTB_DEFAULT_DECODE>
 RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 &n3, const Q4 &n4,
                              const RaySetup &r, float tmax) {
-    const NodeFrame f = node_frame(n0, r);
+    const NodeFrame f = DEC ? node_frame(n0, r) : node_frame_i2f(n0, r);
     const bool px = (r.octinv & 1u) != 0, py = (r.octinv & 2u) != 0, pz = (r.octinv & 4u) != 0;
     uint32_t mask = 0;
 #pragma unroll
@@ -176,10 +211,17 @@ RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 
         const uint32_t nx4 = px ? lox : hix, fx4 = px ? hix : lox;
         const uint32_t ny4 = py ? loy : hiy, fy4 = py ? hiy : loy;
         const uint32_t nz4 = pz ? loz : hiz, fz4 = pz ? hiz : loz;
-        mask |= child_hit_bits<0>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-        mask |= child_hit_bits<1>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-        mask |= child_hit_bits<2>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-        mask |= child_hit_bits<3>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+        if (DEC) {
+            mask |= child_hit_bits<0>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+            mask |= child_hit_bits<1>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+            mask |= child_hit_bits<2>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+            mask |= child_hit_bits<3>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+        } else {
+            mask |= child_hit_bits_i2f<0>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+            mask |= child_hit_bits_i2f<1>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+            mask |= child_hit_bits_i2f<2>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+            mask |= child_hit_bits_i2f<3>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+        }
     }
     return mask;
 }
@@ -192,7 +234,12 @@ constexpr int kStackSize = 48;
 // leaf-order index differs from `excluded` (the light's own triangle,
 // bvh.cuh:239-248).  Otherwise find the closest hit with the reference's
 // accept rule 0 < t <= tmax, tmax shrinking (bvh.cuh:222-236).
-template <bool ANY, bool COUNT>
+// 0 = integer->float conversion per plane (I2F), 1 = byte permute into the mantissa (PRMT).
+// Measured on B200 (profiles/r1_variants.md): I2F is 1.4-1.6x faster end to end, so it is the default.
+#ifndef RTB_DEFAULT_DECODE
+#define RTB_DEFAULT_DECODE 0
+#endif
+template <bool ANY, bool COUNT, int DEC = RTB_DEFAULT_DECODE>
 struct Traversal {
     RaySetup r;
     float tmax;
@@ -226,7 +273,7 @@ struct Traversal {
             const Q4 *np = B.nodes + (size_t)(base + rel) * kNodeWords;
             const Q4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
             if (COUNT) cnt.nodes++;
-            const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, tmax);
+            const uint32_t hm = node_hitmask<DEC>(n0, n1, n2, n3, n4, r, tmax);
             gx = n1.x; gy = (hm & 0xff000000u) | (n0.w >> 24);
             tx = n1.y; ty = hm & 0x00ffffffu;
         }
@@ -252,6 +299,48 @@ struct Traversal {
         return true;
     }
 };
+
+// A/B variant kept for measurements: the same traversal written as one loop
+template <bool ANY, int DEC>
+RTB_HD bool bvh8_trace_mono(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, HitRec &hit) {
+    const RaySetup r = ray_setup(o, d);
+    uint32_t stack_x[kStackSize], stack_y[kStackSize];
+    int sp = 0;
+    uint32_t gx = 0, gy = 0x80000000u, tx = 0, ty = 0;
+    hit.t = 0.f; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
+    bool found = false;
+    while (true) {
+        if (gy & 0xff000000u) {
+            const int bit = bfind(gy);
+            gy &= ~(1u << bit);
+            const uint32_t base = gx, imask = gy & 0xffu;
+            if (gy & 0xff000000u) { stack_x[sp] = gx; stack_y[sp] = gy; ++sp; }
+            const uint32_t slot = ((uint32_t)bit - 24u) ^ r.octinv;
+            const uint32_t rel = popc(imask & ~(0xffffffffu << slot));
+            const Q4 *np = B.nodes + (size_t)(base + rel) * kNodeWords;
+            const Q4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
+            const uint32_t hm = node_hitmask<DEC>(n0, n1, n2, n3, n4, r, tmax);
+            gx = n1.x; gy = (hm & 0xff000000u) | (n0.w >> 24);
+            tx = n1.y; ty = hm & 0x00ffffffu;
+        }
+        while (ty) {
+            const int bit = bfind(ty);
+            ty &= ~(1u << bit);
+            const int idx = (int)(tx + (uint32_t)bit);
+            const Tri48 tr = load_tri(B.tris, idx);
+            float t, u, v;
+            if (tri_intersect(tr, o, d, tmax, t, u, v)) {
+                if (ANY) { if (idx != excluded) return true; }
+                else { tmax = t; hit.t = t; hit.u = u; hit.v = v; hit.tri = idx; found = true; }
+            }
+        }
+        if ((gy & 0xff000000u) == 0) {
+            if (sp == 0) break;
+            --sp; gx = stack_x[sp]; gy = stack_y[sp];
+        }
+    }
+    return found;
+}
 
 template <bool ANY, bool COUNT>
 RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, HitRec &hit,

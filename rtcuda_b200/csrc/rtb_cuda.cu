@@ -68,13 +68,13 @@ struct FetchTuning {
     int steps;   // traversal steps between two warp-wide votes
     int chunk;   // queue entries a warp claims with one atomicAdd
 };
-template <bool ANY>
+template <bool ANY, int DEC>
 __device__ __forceinline__ void persistent_trace(const WaveState &W, const SceneView &S, int parity, FetchTuning tune) {
     const int n = ANY ? W.c->n_shadow[parity] : W.c->n_extend[parity];
     int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanes_below = (1u << lane) - 1u;
-    Traversal<ANY, false> T;
+    Traversal<ANY, false, DEC> T;
     uint32_t stack_x[kStackSize], stack_y[kStackSize];
     bool has = false, exhausted = false;
     int qi = 0;
@@ -127,11 +127,49 @@ __device__ __forceinline__ void persistent_trace(const WaveState &W, const Scene
     }
 }
 __global__ void __launch_bounds__(kBlock, 4) k_extend(WaveState W, SceneView S, int parity, FetchTuning tune) {
-    persistent_trace<false>(W, S, parity, tune);
+    persistent_trace<false, 0>(W, S, parity, tune);
 }
 __global__ void __launch_bounds__(kBlock, 4) k_shadow(WaveState W, SceneView S, int parity, FetchTuning tune) {
-    persistent_trace<true>(W, S, parity, tune);
+    persistent_trace<true, 0>(W, S, parity, tune);
 }
+// ---- A/B variants (RTB_VARIANT, tuning runs only) ----
+// 1: dynamic fetch with the PRMT decode; 2/3: static batches of 32 rays per warp, one monolithic
+// traversal loop, I2F / PRMT decode
+__global__ void __launch_bounds__(kBlock, 4) k_extend_v1(WaveState W, SceneView S, int parity, FetchTuning tune) {
+    persistent_trace<false, 1>(W, S, parity, tune);
+}
+__global__ void __launch_bounds__(kBlock, 4) k_shadow_v1(WaveState W, SceneView S, int parity, FetchTuning tune) {
+    persistent_trace<true, 1>(W, S, parity, tune);
+}
+template <bool ANY, int DEC>
+__device__ __forceinline__ void static_batches(const WaveState &W, const SceneView &S, int parity) {
+    const int n = ANY ? W.c->n_shadow[parity] : W.c->n_extend[parity];
+    int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
+    const unsigned lane = threadIdx.x & 31u;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(head, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) return;
+        const int i = base + (int)lane;
+        if (i < n) {
+            HitRec h;
+            if (ANY) {
+                const F4 o = ldg(W.sh_o + i), d = ldg(W.sh_d + i);
+                shadow_finish(W, i, bvh8_trace_mono<true, DEC>(S.bvh, xyz(o), xyz(d), o.w, f2i(d.w), h));
+            } else {
+                const F4 a = ldg(W.ea + i), b = ldg(W.eb + i);
+                bvh8_trace_mono<false, DEC>(S.bvh, xyz(a), xyz(b), FLT_MAX, -1, h);
+                extend_finish(W, S, i, h);
+            }
+        }
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(kBlock, 4) k_extend_v2(WaveState W, SceneView S, int parity) { static_batches<false, 0>(W, S, parity); }
+__global__ void __launch_bounds__(kBlock, 4) k_shadow_v2(WaveState W, SceneView S, int parity) { static_batches<true, 0>(W, S, parity); }
+__global__ void __launch_bounds__(kBlock, 4) k_extend_v3(WaveState W, SceneView S, int parity) { static_batches<false, 1>(W, S, parity); }
+__global__ void __launch_bounds__(kBlock, 4) k_shadow_v3(WaveState W, SceneView S, int parity) { static_batches<true, 1>(W, S, parity); }
 // one thread per queue entry (A/B against the persistent kernels; COUNT = work counters)
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_extend_flat(WaveState W, SceneView S, int parity) {
@@ -157,7 +195,8 @@ struct CudaBackend {
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
     int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
-    FetchTuning tune_{16, 4, 128};  // RTB_REFILL / RTB_STEPS / RTB_CHUNK override (tuning runs)
+    FetchTuning tune_{24, 1, 128};  // RTB_REFILL / RTB_STEPS / RTB_CHUNK override (tuning runs)
+    int variant_e_ = 0, variant_s_ = 0;  // RTB_VARIANT_E / RTB_VARIANT_S: A/B kernels (tuning runs)
     int pool_ = 1 << 23;    // default path pool, RTB_POOL overrides (tuning)
 
     explicit CudaBackend(int device) {
@@ -188,6 +227,8 @@ struct CudaBackend {
         if (const char *e = getenv("RTB_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tune_.refill = v; }
         if (const char *e = getenv("RTB_STEPS")) { int v = atoi(e); if (v >= 1) tune_.steps = v; }
         if (const char *e = getenv("RTB_CHUNK")) { int v = atoi(e); if (v >= 32) tune_.chunk = v; }
+        if (const char *e = getenv("RTB_VARIANT_E")) variant_e_ = atoi(e);
+        if (const char *e = getenv("RTB_VARIANT_S")) variant_s_ = atoi(e);
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
         int per_sm = 0;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend, kBlock, 0));
@@ -257,6 +298,9 @@ struct CudaBackend {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
         else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
+        else if (variant_e_ == 1) k_extend_v1<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity, tune_);
+        else if (variant_e_ == 2) k_extend_v2<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity);
+        else if (variant_e_ == 3) k_extend_v3<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity);
         else k_extend<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
@@ -264,6 +308,9 @@ struct CudaBackend {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
         else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
+        else if (variant_s_ == 1) k_shadow_v1<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity, tune_);
+        else if (variant_s_ == 2) k_shadow_v2<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity);
+        else if (variant_s_ == 3) k_shadow_v3<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity);
         else k_shadow<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
