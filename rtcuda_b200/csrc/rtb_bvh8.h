@@ -101,6 +101,12 @@ RTB_HD RaySetup ray_setup(V3 o, V3 d) {
 
 RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
+// 0 = integer->float conversion per plane (I2F), 1 = byte permute into the mantissa (PRMT).
+// Measured on B200 (profiles/r1_variants.md): I2F is 1.4-1.6x faster end to end, so it is the default.
+#ifndef RTB_DEFAULT_DECODE
+#define RTB_DEFAULT_DECODE 0
+#endif
+
 // A/B variant kept for measurements (decode 1): byte j of `w` as the float
 // 1 + q * 2^-15, built by one byte permute that drops q into mantissa bits
 // 8..15 of 1.0f, instead of an integer->float conversion (XU pipe, 74-80 % busy
@@ -234,11 +240,6 @@ constexpr int kStackSize = 48;
 // leaf-order index differs from `excluded` (the light's own triangle,
 // bvh.cuh:239-248).  Otherwise find the closest hit with the reference's
 // accept rule 0 < t <= tmax, tmax shrinking (bvh.cuh:222-236).
-// 0 = integer->float conversion per plane (I2F), 1 = byte permute into the mantissa (PRMT).
-// Measured on B200 (profiles/r1_variants.md): I2F is 1.4-1.6x faster end to end, so it is the default.
-#ifndef RTB_DEFAULT_DECODE
-#define RTB_DEFAULT_DECODE 0
-#endif
 template <bool ANY, bool COUNT, int DEC = RTB_DEFAULT_DECODE>
 struct Traversal {
     RaySetup r;
