@@ -190,7 +190,7 @@ struct CudaBackend {
     int dev_ = -1;
     int num_sms_ = 0;
     cudaStream_t stream_ = nullptr;
-    int blocks_extend_ = 0, blocks_shadow_ = 0;
+    int blocks_extend_ = 0, blocks_shadow_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_generate_ = 0;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
@@ -235,6 +235,14 @@ struct CudaBackend {
         blocks_extend_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow, kBlock, 0));
         blocks_shadow_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<0>, kBlock, 0));
+        blocks_shade_[0] = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<1>, kBlock, 0));
+        blocks_shade_[1] = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<2>, kBlock, 0));
+        blocks_shade_[2] = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate, kBlock, 0));
+        blocks_generate_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
     }
     ~CudaBackend() {
         if (dev_ < 0) return;
@@ -279,11 +287,11 @@ struct CudaBackend {
     }
     template <class F> void launch_trace(int n, F f) { launch(n, f); }
     void generate(const GenerateK &k) {
-        k_generate<<<num_sms_ * 4, kBlock, 0, stream_>>>(k.W, k.rc, k.parity);
+        k_generate<<<blocks_generate_, kBlock, 0, stream_>>>(k.W, k.rc, k.parity);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shade(const ShadeK &k) {
-        const int grid = num_sms_ * 4;
+        const int grid = blocks_shade_[k.type];  // exactly one resident wave: the kernels are grid-stride loops
         if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
         else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
         else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);

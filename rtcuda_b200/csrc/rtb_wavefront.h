@@ -66,6 +66,23 @@ RTB_HD int queue_push(int32_t *counter) {
     base = __shfl_sync(m, base, leader);
     return base + __popc(m & ((1u << lane) - 1u));
 }
+// two appends at once: both atomics are in flight together (one round trip instead of two)
+RTB_HD void queue_push2(int32_t *c1, bool f1, int &i1, int32_t *c2, bool f2, int &i2) {
+    const unsigned m = __activemask();
+    const unsigned m1 = __ballot_sync(m, f1), m2 = __ballot_sync(m, f2);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int b1 = 0, b2 = 0;
+    if (lane == leader) {
+        if (m1) b1 = atomicAdd(c1, __popc(m1));
+        if (m2) b2 = atomicAdd(c2, __popc(m2));
+    }
+    b1 = __shfl_sync(m, b1, leader);
+    b2 = __shfl_sync(m, b2, leader);
+    const unsigned below = (1u << lane) - 1u;
+    i1 = b1 + __popc(m1 & below);
+    i2 = b2 + __popc(m2 & below);
+}
 RTB_HD void accum_add(float *accum, uint32_t pixel, V3 L) {
     float *p = accum + 3 * (size_t)pixel;
     atomicAdd(p, L.x); atomicAdd(p + 1, L.y); atomicAdd(p + 2, L.z);
@@ -73,6 +90,10 @@ RTB_HD void accum_add(float *accum, uint32_t pixel, V3 L) {
 RTB_HD void work_add(unsigned long long *p, unsigned v) { atomicAdd(p, (unsigned long long)v); }
 #else
 RTB_HD int queue_push(int32_t *counter) { return (*counter)++; }
+RTB_HD void queue_push2(int32_t *c1, bool f1, int &i1, int32_t *c2, bool f2, int &i2) {
+    i1 = f1 ? (*c1)++ : 0;
+    i2 = f2 ? (*c2)++ : 0;
+}
 RTB_HD void accum_add(float *accum, uint32_t pixel, V3 L) {
     float *p = accum + 3 * (size_t)pixel;
     p[0] += L.x; p[1] += L.y; p[2] += L.z;
@@ -150,14 +171,14 @@ RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConst
     PathStepOut out;
     path_step<TYPE>(S, rc, in, out);
     if (out.emit) accum_add(W.accum, in.pixel, out.emission);
+    int j, si;
+    queue_push2(&W.c->n_extend[parity], out.extend, j, &W.c->n_shadow[parity], out.shadow, si);
     if (out.extend) {
-        const int j = queue_push(&W.c->n_extend[parity]);
         W.ea[j] = f4(out.o, a.w);
         W.eb[j] = f4(out.d, u2f((in.sample << 8) | (uint32_t)out.bounces));
         W.ec[j] = f4(out.beta, 0.f);
     }
     if (out.shadow) {
-        const int si = queue_push(&W.c->n_shadow[parity]);
         W.sh_o[si] = f4(out.so, out.stmax);
         W.sh_d[si] = f4(out.sd, i2f(out.sexcl));
         W.sh_L[si] = f4(out.sL, a.w);
