@@ -323,7 +323,10 @@ def main():
         cst = scene.render_accumulate(cam, pc, accum.data_ptr())
         nodes_per_ray = cst.extend_nodes / max(cst.extend_rays, 1)
         tris_per_ray = cst.extend_tris / max(cst.extend_rays, 1)
-        bytes_per_ray = nodes_per_ray * 80 + tris_per_ray * 48 + 32 + 16
+        hit_frac = cst.hits / max(cst.extend_rays, 1)
+        # algorithmic bytes per extend ray: 80 B per node fetched, 48 B per triangle tested,
+        # 48 B queue record read (origin|pixel, dir|sample, beta), 48 B hit record written when it hits
+        bytes_per_ray = nodes_per_ray * 80 + tris_per_ray * 48 + 48 + 48 * hit_frac
         avg_launch_ms = ext_ms / max(ext_launches, 1)
         bytes_per_launch = bytes_per_ray * ext_rays / max(ext_launches, 1)
         achieved = bytes_per_launch / (avg_launch_ms * 1e-3) * 1e-9 if avg_launch_ms > 0 else 0.0
@@ -336,7 +339,7 @@ def main():
             pass
         roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                    "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "hit_fraction": hit_frac,
                     "avg_launch_ms": avg_launch_ms, "launches": int(ext_launches),
                     "kernel_share_of_step": ext_ms / tot_ms if tot_ms else None,
                     "shadow_share_of_step": sh_ms / tot_ms if tot_ms else None,
@@ -349,8 +352,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": desc_txt, "spp_per_gpu": spp, "total_spp": total_spp,
                            "sharding": "sample pass per rank, scene replicated, NCCL all-reduce of the accumulation buffer" if world > 1 else "single GPU",
-                           "pool_size": int(p.pool_size) or (1 << 21),
-                           "l2": "256 MB device memset between timed steps (L2 flush); path-pool state (>300 MB) is streamed every iteration"},
+                           "pool_size": int(p.pool_size) or int(os.environ.get("RTB_POOL", 1 << 23)),
+                           "l2": "256 MB device memset between timed steps (L2 flush); ray queues (2 GB) are streamed every iteration"},
                 "ms_per_spp": ms_per_step / total_spp * world, "paths_per_step": int(stats[0].paths) * world,
                 "rays_per_step": rays_total.item() / args.steps,
                 "iterations_per_step": int(stats[0].iterations), "bvh_build_ms": bst.build_ms, "bvh_nodes": int(bst.num_nodes),

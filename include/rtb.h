@@ -155,6 +155,7 @@ typedef struct rtb_render_stats {
     uint64_t extend_nodes, extend_tris; /* 80-byte nodes fetched / triangles tested by extend rays */
     uint64_t shadow_nodes, shadow_tris; /* same for shadow rays (only with RTB_RENDER_COUNT_WORK) */
     uint64_t extend_launches, shadow_launches; /* launches of the two traversal kernels */
+    uint64_t hits;         /* extend rays that hit something (= paths shaded) */
     float ms_total;        /* generate..accumulate, CUDA events on the render stream */
     float ms_extend;       /* summed duration of the extend launches (CUDA events) */
     float ms_shadow;       /* summed duration of the shadow launches */

@@ -61,7 +61,7 @@ class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("extend_nodes", C.c_uint64), ("extend_tris", C.c_uint64), ("shadow_nodes", C.c_uint64),
-                ("shadow_tris", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
+                ("shadow_tris", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64), ("hits", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_extend", C.c_float), ("ms_shadow", C.c_float), ("ms_other", C.c_float)]
 
 

@@ -474,6 +474,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
         stats->extend_nodes = c.work[0]; stats->extend_tris = c.work[1];
         stats->shadow_nodes = c.work[2]; stats->shadow_tris = c.work[3];
         stats->extend_launches = c.stat_iters; stats->shadow_launches = c.stat_iters;
+        stats->hits = c.stat_hits;
         stats->ms_extend = ms_extend; stats->ms_shadow = ms_shadow;
         stats->ms_total = ms_total;
         stats->ms_other = ms_total - ms_extend - ms_shadow;

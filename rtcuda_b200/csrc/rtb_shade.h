@@ -207,7 +207,12 @@ struct PathStepOut {
 template <int MT>
 RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStepIn &in, PathStepOut &out) {
     out.emit = false; out.extend = false; out.shadow = false;
+    // issue every load that only depends on the hit before the roulette logic: the shade kernel is
+    // bound by memory latency (ncu r1: long-scoreboard stalls dominate), not by instruction count
     const TriMeta meta = S.tri_meta[in.hit.tri];
+    const Tri48 tr = load_tri(S.bvh.tris, in.hit.tri);
+    rtb_material m = S.materials[meta.material & 0xffffff];  // type is packed in the top byte
+    if (MT >= 0) m.type = MT;
     int b = in.bounces;
     V3 beta = in.beta;
     // init, render.cuh:98-107: only camera rays see emitters
@@ -234,9 +239,6 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
     const Rand4 xi = rand4(rc.seed, in.pixel, in.sample, 2u * (uint32_t)b + 2u);
     b++;
     // mat, render.cuh:139-168
-    const Tri48 tr = load_tri(S.bvh.tris, in.hit.tri);
-    rtb_material m = S.materials[meta.material & 0xffffff];  // type is packed in the top byte
-    if (MT >= 0) m.type = MT;
     const V3 P = vmad(vmad(tri_p0(tr), -in.hit.u, tri_e1(tr)), in.hit.v, tri_e2(tr));
     const V3 ng = vneg(vnormalize(tri_n(tr)));
     const V3 beta_old = beta;

@@ -33,7 +33,7 @@ struct Counters {
     int32_t extend_head, shadow_head;  // fetch cursors of the persistent kernels
     int32_t done, n_new, _pad;
     unsigned long long next_path, total_paths;
-    unsigned long long stat_extend, stat_shadow, stat_paths, stat_iters;
+    unsigned long long stat_extend, stat_shadow, stat_paths, stat_iters, stat_hits;
     unsigned long long work[4];  // extend nodes, extend tris, shadow nodes, shadow tris (counting variants)
 };
 
@@ -213,6 +213,7 @@ RTB_HD void control_body(const WaveState &W, int parity) {
     c.next_path += (unsigned long long)started;
     c.stat_paths += (unsigned long long)started;
     c.n_extend[parity] += started;
+    c.stat_hits += (unsigned long long)(c.n_mat[0] + c.n_mat[1] + c.n_mat[2]);
     c.n_mat[0] = c.n_mat[1] = c.n_mat[2] = 0;
     c.n_extend[parity ^ 1] = 0;
     c.n_shadow[parity ^ 1] = 0;

@@ -17,8 +17,8 @@ W = {"c1": (1, 0, 600, 600, 10, 10), "c2": (1, 0, 1920, 1080, 64, 8), "c2s": (1,
      "c4s": (2, 0, 1920, 1080, 8, 16)}
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2")
-ap.add_argument("--refill", default="16")
-ap.add_argument("--steps", default="4")
+ap.add_argument("--refill", default="24")
+ap.add_argument("--steps", default="1")
 ap.add_argument("--chunk", default="128")
 ap.add_argument("--pool", default="8388608")
 ap.add_argument("--ve", default="0")
