@@ -30,7 +30,7 @@ RTB_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
 RTB_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
 RTB_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 RTB_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
-RTB_HD float frcp(float a) { return __fdiv_rn(1.0f, a); }
+RTB_HD float frcp(float a) { return __frcp_rn(a); }  // IEEE 1/x: the sequence nvcc emits for the reference's `1.f / x`
 RTB_HD float fsqrt(float a) { return __fsqrt_rn(a); }
 RTB_HD int f2i(float a) { return __float_as_int(a); }
 RTB_HD float i2f(int a) { return __int_as_float(a); }

@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(kBlock) k_generate(WaveState W, RenderConsts r
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) generate_body(W, rc, parity, i);
 }
 
-template <int TYPE>
-__global__ void __launch_bounds__(kBlock, 3) k_shade(WaveState W, SceneView S, RenderConsts rc, int parity) {
+template <int TYPE, int MINB = 3>
+__global__ void __launch_bounds__(kBlock, MINB) k_shade(WaveState W, SceneView S, RenderConsts rc, int parity) {
     const int n = W.c->n_mat[TYPE];
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) shade_body<TYPE>(W, S, rc, parity, i);
 }
@@ -76,10 +76,17 @@ __device__ __forceinline__ void persistent_trace(const WaveState &W, const Scene
     const unsigned lanes_below = (1u << lane) - 1u;
     Traversal<ANY, false, DEC> T;
     uint32_t stack_x[kStackSize], stack_y[kStackSize];
-    bool has = false, exhausted = false;
+    bool has = false, exhausted = false, pending = false;
     int qi = 0;
     int chunk_next = 0, chunk_end = 0;  // warp-uniform: the part of the queue this warp has claimed
     while (true) {
+        // results of the rays that finished since the last refill are written here, together, so
+        // that the hit-record / atomic code runs with many lanes instead of one at a time
+        if (pending) {
+            if (ANY) shadow_finish(W, qi, T.found);
+            else extend_finish(W, S, qi, T.hit);
+            pending = false;
+        }
         // hand queue entries to the idle lanes; a new chunk is claimed (one atomic per warp) when the
         // current one runs out, so most refills cost no global round trip at all
         unsigned need = __ballot_sync(0xffffffffu, !has);
@@ -116,11 +123,7 @@ __device__ __forceinline__ void persistent_trace(const WaveState &W, const Scene
         do {
 #pragma unroll 1
             for (int k = 0; k < tune.steps && has; ++k) {
-                if (!T.step(S.bvh, stack_x, stack_y)) {
-                    if (ANY) shadow_finish(W, qi, T.found);
-                    else extend_finish(W, S, qi, T.hit);
-                    has = false;
-                }
+                if (!T.step(S.bvh, stack_x, stack_y)) { has = false; pending = true; }
             }
             act = __ballot_sync(0xffffffffu, has);
         } while (__popc(act) >= keep_going);
@@ -190,7 +193,7 @@ struct CudaBackend {
     int dev_ = -1;
     int num_sms_ = 0;
     cudaStream_t stream_ = nullptr;
-    int blocks_extend_ = 0, blocks_shadow_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_generate_ = 0;
+    int blocks_extend_ = 0, blocks_shadow_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_shade4_[3] = {0, 0, 0}, blocks_generate_ = 0, shade_occ_ = 3;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
@@ -241,6 +244,13 @@ struct CudaBackend {
         blocks_shade_[1] = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<2>, kBlock, 0));
         blocks_shade_[2] = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<0, 4>, kBlock, 0));
+        blocks_shade4_[0] = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<1, 4>, kBlock, 0));
+        blocks_shade4_[1] = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<2, 4>, kBlock, 0));
+        blocks_shade4_[2] = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        if (const char *e = getenv("RTB_SHADE_OCC")) shade_occ_ = atoi(e);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate, kBlock, 0));
         blocks_generate_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
     }
@@ -291,6 +301,14 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shade(const ShadeK &k) {
+        if (shade_occ_ == 4) {  // tuning: 64 registers (small spills), 4 blocks per SM
+            const int g4 = blocks_shade4_[k.type];
+            if (k.type == 0) k_shade<0, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
+            else if (k.type == 1) k_shade<1, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
+            else k_shade<2, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
+            RTB_CUDA_CHECK(cudaGetLastError());
+            return;
+        }
         const int grid = blocks_shade_[k.type];  // exactly one resident wave: the kernels are grid-stride loops
         if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
         else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);

@@ -1,0 +1,125 @@
+"""Full-size checks on the 10-million-triangle scene (configs C3/C5) through
+size-independent properties, plus an exact comparison with the oracle on a
+625k-triangle cut of the same generator (the oracle's host SAH build is the
+reference's O(n log n) single-thread build and takes minutes at 10 M)."""
+import numpy as np
+import pytest
+
+from rtcuda_b200 import capi
+from conftest import mean_rel_err, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def field_small(gpu, bunny):
+    hs = gpu.host_scene(capi.RTB_SCENE_S2, *bunny, grid=3)
+    return hs, gpu.context(0).scene(hs.desc)
+
+
+@pytest.fixture(scope="module")
+def field_full(gpu, bunny):
+    hs = gpu.host_scene(capi.RTB_SCENE_S2, *bunny, grid=12)
+    sc = gpu.context(0).scene(hs.desc)
+    return hs, sc
+
+
+def test_bunny_field_625k_matches_oracle(gpu, oracle, field_small):
+    hs, sc = field_small
+    assert hs.desc.num_triangles == 9 * 69451 + 12
+    osc = oracle.scene(hs.desc)
+    cam = hs.camera(16 / 9)
+    rays = np.concatenate([gpu.primary_rays(cam, 640, 360), random_rays(200000, seed=31)])
+    hits, ref = sc.trace_closest(rays), osc.trace_closest(rays, capi.HIT_DTYPE)
+    assert (hits["prim"] == ref["prim"]).all()
+    for k in ("t", "u", "v"):
+        assert (hits[k].view(np.uint32) == ref[k].view(np.uint32)).all()
+    p = capi.render_params(gpu, width=160, height=90, spp=4, max_bounces=8)
+    img, st = sc.render(cam, p)
+    rimg, _, ost = osc.render(cam, p)
+    assert st.paths == ost[0]
+    assert mean_rel_err(img, rimg) <= 1e-3
+
+
+def test_full_scene_build(field_full):
+    hs, sc = field_full
+    st = sc.stats()
+    n = 144 * 69451 + 12
+    assert st.num_triangles == n == hs.desc.num_triangles
+    assert st.num_bvh2_nodes == 2 * n - 1
+    assert n / 24 <= st.num_nodes <= n  # at most 24 triangles per 8-wide node
+    assert st.collapse_levels < 48
+    b = list(st.scene_bounds)
+    assert b[0] >= -1e-3 and b[1] <= 1.001 and b[2] >= -1e-3 and b[3] <= 1.001 and b[4] >= -1.001 and b[5] <= 0.05  # the open front: instances of the first row may lean out a little
+
+
+def brute_force(verts, o, d):
+    """closest strictly-interior hit by testing EVERY triangle in float64"""
+    p0, p1, p2 = verts[:, 0:3], verts[:, 3:6], verts[:, 6:9]
+    e1, e2 = p0 - p1, p2 - p0
+    n = np.cross(e1, e2)
+    c = p0 - o
+    r = np.cross(np.broadcast_to(d, c.shape), c)
+    det = n @ d
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / det
+        u = inv * np.einsum("ij,ij->i", e2, r)
+        v = inv * np.einsum("ij,ij->i", e1, r)
+        t = inv * np.einsum("ij,ij->i", c, n)
+    inside = (u > 1e-6) & (v > 1e-6) & (u + v < 1 - 1e-6) & (t > 1e-9)
+    if not inside.any():
+        return -1, np.inf
+    idx = np.nonzero(inside)[0]
+    k = idx[np.argmin(t[idx])]
+    return int(k), float(t[k])
+
+
+def test_full_scene_hits_agree_with_exhaustive_search(gpu, field_full):
+    """closest hit == minimum over ALL 10 M triangles (float64 exhaustive test) for sampled rays"""
+    hs, sc = field_full
+    verts = hs.arrays()["vertices"].astype(np.float64)
+    cam = hs.camera(16 / 9)
+    prim = gpu.primary_rays(cam, 3840, 2160)
+    rng = np.random.default_rng(3)
+    rays = np.concatenate([prim[rng.integers(0, len(prim), 16)], random_rays(8, seed=77)])
+    hits = sc.trace_closest(rays)
+    for r, h in zip(rays, hits):
+        k, t = brute_force(verts, r["origin"].astype(np.float64), r["dir"].astype(np.float64))
+        if k < 0:
+            assert h["prim"] == -1 or h["t"] > 0  # only edge-grazing hits may be missed by the strict test
+            continue
+        assert h["prim"] >= 0
+        assert abs(h["t"] - t) <= 1e-5 * t or h["t"] < t, (h, k, t)
+        if abs(h["t"] - t) <= 1e-5 * t and h["prim"] != k:
+            continue  # two triangles at the same distance (shared edge)
+        assert h["prim"] == k or h["t"] < t * (1 - 1e-5), (h, k, t)
+
+
+def test_full_scene_any_hit_consistent_with_closest_hit(field_full):
+    hs, sc = field_full
+    rays = random_rays(300000, seed=5)
+    hits = sc.trace_closest(rays)
+    hit = hits["prim"] >= 0
+    assert 0.3 < hit.mean() <= 1.0
+    r = rays[hit].copy()
+    r["tmax"] = hits["t"][hit]
+    assert sc.trace_any(r).all()          # 0 < t <= tmax is inclusive (triangle.cuh:49)
+    r["tmax"] = np.nextafter(hits["t"][hit], np.float32(0))
+    assert not sc.trace_any(r).any()      # nothing closer than the closest hit
+    assert not sc.trace_any(rays[~hit]).any()
+    # excluding the hit triangle itself: still unoccluded up to just below t, regardless of exclusion
+    assert not sc.trace_any(r, hits["prim"][hit]).any()
+
+
+def test_full_scene_4k_sample_passes_add_up(gpu, field_full):
+    """C5's sharding at C3's size: samples [0,1) + [1,2) == samples [0,2) at 3840x2160"""
+    hs, sc = field_full
+    cam = hs.camera(16 / 9)
+    w, h = 3840, 2160
+    full, sf = sc.render(cam, capi.render_params(gpu, width=w, height=h, spp=2, max_bounces=8, total_spp=2))
+    a, sa = sc.render(cam, capi.render_params(gpu, width=w, height=h, spp=1, max_bounces=8, total_spp=2, first_sample=0))
+    b, sb = sc.render(cam, capi.render_params(gpu, width=w, height=h, spp=1, max_bounces=8, total_spp=2, first_sample=1))
+    assert sa.paths + sb.paths == sf.paths == 2 * w * h
+    assert sa.extend_rays + sb.extend_rays == sf.extend_rays and sa.shadow_rays + sb.shadow_rays == sf.shadow_rays
+    assert np.isfinite(full).all()
+    assert mean_rel_err(a.astype(np.float64) ** 2 + b.astype(np.float64) ** 2, full.astype(np.float64) ** 2) <= 1e-5
