@@ -160,6 +160,9 @@ typedef struct rtb_render_stats {
     float ms_extend;       /* summed duration of the extend launches (CUDA events) */
     float ms_shadow;       /* summed duration of the shadow launches */
     float ms_other;        /* ms_total - ms_extend - ms_shadow: shade, generate, control, host gaps */
+    float ms_shade;        /* summed duration of shade + generate + control (part of ms_other) */
+    int32_t fused_trace;   /* 1: extend and shadow rays ran in ONE launch per iteration; then ms_extend
+                              is the duration of that launch and ms_shadow is 0 */
 } rtb_render_stats;
 
 typedef struct rtb_context rtb_context; /* one per GPU */

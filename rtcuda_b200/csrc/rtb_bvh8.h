@@ -94,7 +94,9 @@ RTB_HD RaySetup ray_setup(V3 o, V3 d) {
     float dx = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
     float dy = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
     float dz = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
-    r.idir = v3(frcp(dx), frcp(dy), frcp(dz));
+    // 1/d only feeds the conservative slab test, whose interval is padded by 16 ulp: the 1-ulp
+    // MUFU.RCP result is enough (an IEEE 1/x costs ~10 instructions per axis)
+    r.idir = v3(frcp_fast(dx), frcp_fast(dy), frcp_fast(dz));
     r.octinv = (dx >= 0.f ? 1u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 4u : 0u);
     return r;
 }
@@ -170,10 +172,14 @@ RTB_HD uint32_t child_hit_bits(const NodeFrame &f, uint32_t meta4, uint32_t nx4,
     return 0u;
 }
 // Default decode (0): plane distance with an integer->float conversion per
-// byte, t = q * (2^e/d) + (origin_node - origin_ray)/d
+// byte, t = q * (2^e/d) + (origin_node - origin_ray)/d.  The per-child meta
+// decode is done four children at a time in packed bytes (bits4 = unary
+// triangle count or 1 for an inner child, pos4 = bit position in the hit mask
+// with the octant permutation already applied to inner children), after
+// Ylitie et al. 2017, so a hit child costs two byte extracts, a shift and an OR.
 template <int J>
-RTB_HD uint32_t child_hit_bits_i2f(const NodeFrame &f, uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4,
-                                   uint32_t fy4, uint32_t fz4, float tmax, uint32_t octinv) {
+RTB_HD uint32_t child_hit_bits_i2f(const NodeFrame &f, uint32_t bits4, uint32_t pos4, uint32_t nx4, uint32_t ny4, uint32_t nz4,
+                                   uint32_t fx4, uint32_t fy4, uint32_t fz4, float tmax) {
     const float tnx = ffma((float)byte_of(nx4, J), f.ax, f.cx);
     const float tny = ffma((float)byte_of(ny4, J), f.ay, f.cy);
     const float tnz = ffma((float)byte_of(nz4, J), f.az, f.cz);
@@ -182,14 +188,15 @@ RTB_HD uint32_t child_hit_bits_i2f(const NodeFrame &f, uint32_t meta4, uint32_t 
     const float tfz = ffma((float)byte_of(fz4, J), f.az, f.cz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-    if (tn <= ffma(tf, 1.0000019f, f.eps)) {
-        const uint32_t meta = byte_of(meta4, J);
-        const uint32_t bits = meta >> 5;
-        const bool inner = (meta & 0x18u) == 0x18u;
-        const uint32_t pos = inner ? ((meta & 0x1fu) ^ octinv) : (meta & 0x1fu);
-        return bits << pos;
-    }
+    if (tn <= ffma(tf, 1.0000019f, f.eps)) return byte_of(bits4, J) << byte_of(pos4, J);
     return 0u;
+}
+// meta4 -> (bits4, pos4) for four children at once
+RTB_HD void meta_decode4(uint32_t meta4, uint32_t oct4, uint32_t &bits4, uint32_t &pos4) {
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;  // low five bits in 24..31
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;            // 0xff in the bytes of inner children
+    pos4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1f1f1f1fu;
+    bits4 = (meta4 >> 5) & 0x07070707u;
 }
 RTB_HD NodeFrame node_frame_i2f(const Q4 &n0, const RaySetup &r) {
     NodeFrame f;
@@ -223,10 +230,12 @@ RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 
             mask |= child_hit_bits<2>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
             mask |= child_hit_bits<3>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
         } else {
-            mask |= child_hit_bits_i2f<0>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-            mask |= child_hit_bits_i2f<1>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-            mask |= child_hit_bits_i2f<2>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-            mask |= child_hit_bits_i2f<3>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
+            uint32_t bits4, pos4;
+            meta_decode4(meta4, r.octinv * 0x01010101u, bits4, pos4);
+            mask |= child_hit_bits_i2f<0>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
+            mask |= child_hit_bits_i2f<1>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
+            mask |= child_hit_bits_i2f<2>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
+            mask |= child_hit_bits_i2f<3>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
         }
     }
     return mask;
@@ -261,9 +270,13 @@ struct Traversal {
         found = false;
         cnt.nodes = 0; cnt.tris = 0;
     }
-    // one node (its 8 child boxes) plus the triangles it exposes; false when the ray is finished
-    RTB_HD bool step(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y) {
-        uint32_t tx = 0, ty = 0;  // triangle group: tri base | hit bits
+    // The three parts of one traversal step.  The persistent kernels call them separately so that
+    // the triangle tests of a whole warp can be pooled (rtb_cuda.cu, coop_triangles); step() below
+    // is the plain per-ray composition.
+    // (1) pop the nearest pending child, fetch its node, slab-test the 8 child boxes;
+    //     (tx, ty) = triangle base | hit triangle bits of that node
+    RTB_HD void node_part(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y, uint32_t &tx, uint32_t &ty) {
+        tx = 0; ty = 0;
         if (gy & 0xff000000u) {
             const int bit = bfind(gy);
             gy &= ~(1u << bit);
@@ -278,6 +291,31 @@ struct Traversal {
             gx = n1.x; gy = (hm & 0xff000000u) | (n0.w >> 24);
             tx = n1.y; ty = hm & 0x00ffffffu;
         }
+    }
+    // (2) the accept rule of Triangle::intersect / intersect_leaf (triangle.cuh:49, bvh.cuh:222-248)
+    //     for a candidate whose barycentric test passed; true when an any-hit ray is finished
+    RTB_HD bool accept(int idx, float t, float u, float v) {
+        if (0.0f < t && t <= tmax) {
+            if (ANY) {
+                if (idx != excluded) { found = true; return true; }
+            } else {
+                tmax = t; hit.t = t; hit.u = u; hit.v = v; hit.tri = idx; found = true;
+            }
+        }
+        return false;
+    }
+    // (3) next pending node group; false when the ray is finished
+    RTB_HD bool advance(const uint32_t *stack_x, const uint32_t *stack_y) {
+        if ((gy & 0xff000000u) == 0) {
+            if (sp == 0) return false;
+            --sp; gx = stack_x[sp]; gy = stack_y[sp];
+        }
+        return true;
+    }
+    // one node (its 8 child boxes) plus the triangles it exposes; false when the ray is finished
+    RTB_HD bool step(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y) {
+        uint32_t tx, ty;  // triangle group: tri base | hit bits
+        node_part(B, stack_x, stack_y, tx, ty);
         while (ty) {
             const int bit = bfind(ty);
             ty &= ~(1u << bit);
@@ -293,11 +331,7 @@ struct Traversal {
                 }
             }
         }
-        if ((gy & 0xff000000u) == 0) {
-            if (sp == 0) return false;
-            --sp; gx = stack_x[sp]; gy = stack_y[sp];
-        }
-        return true;
+        return advance(stack_x, stack_y);
     }
 };
 

@@ -32,6 +32,9 @@ RTB_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 RTB_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 RTB_HD float frcp(float a) { return __frcp_rn(a); }  // IEEE 1/x: the sequence nvcc emits for the reference's `1.f / x`
 RTB_HD float fsqrt(float a) { return __fsqrt_rn(a); }
+// approximate 1/x (MUFU.RCP, <= 1 ulp): only for quantities that feed CONSERVATIVE tests (the slab
+// test pads its interval by 16 ulp), never for anything that decides a hit
+RTB_HD float frcp_fast(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
 RTB_HD int f2i(float a) { return __float_as_int(a); }
 RTB_HD float i2f(int a) { return __int_as_float(a); }
 RTB_HD uint32_t f2u(float a) { return __float_as_uint(a); }
@@ -47,6 +50,7 @@ RTB_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
 RTB_HD float fdiv(float a, float b) { return a / b; }
 RTB_HD float frcp(float a) { return 1.0f / a; }
 RTB_HD float fsqrt(float a) { return sqrtf(a); }
+RTB_HD float frcp_fast(float a) { return 1.0f / a; }
 RTB_HD int f2i(float a) { int r; memcpy(&r, &a, 4); return r; }
 RTB_HD float i2f(int a) { float r; memcpy(&r, &a, 4); return r; }
 RTB_HD uint32_t f2u(float a) { uint32_t r; memcpy(&r, &a, 4); return r; }
@@ -167,20 +171,28 @@ RTB_HD Tri48 tri_from_vertices(V3 p0, V3 p1, V3 p2) {
 
 // Triangle::intersect, triangle.cuh:39-58, operation for operation as nvcc
 // compiles it for sm_100a.  Accepts iff u>=0, v>=0, u+v<=1 and 0 < t <= tmax.
-RTB_HD bool tri_intersect(const Tri48 &tr, V3 o, V3 d, float tmax, float &t_out, float &u_out,
-                          float &v_out) {
+// tri_candidate is the part that does not depend on tmax (the barycentric
+// test and t); it returns t, or -1 when the barycentric test rejects, so that
+// a warp can pool the candidates of all its rays and leave the order-dependent
+// accept rule `0 < t <= tmax` to the ray's own lane.
+RTB_HD float tri_candidate(const Tri48 &tr, V3 o, V3 d, float &u_out, float &v_out) {
     V3 c = vsub(tri_p0(tr), o);
     V3 r = vcross(d, c);
     V3 n = tri_n(tr);
     float inv_det = frcp(vdot(d, n));
     float u = fmul(inv_det, vdot(tri_e2(tr), r));
     float v = fmul(inv_det, vdot(tri_e1(tr), r));
-    if (u >= 0.0f && v >= 0.0f && fadd(u, v) <= 1.0f) {
-        float t = fmul(inv_det, vdot(c, n));
-        if (0.0f < t && t <= tmax) {
-            t_out = t; u_out = u; v_out = v;
-            return true;
-        }
+    u_out = u; v_out = v;
+    if (u >= 0.0f && v >= 0.0f && fadd(u, v) <= 1.0f) return fmul(inv_det, vdot(c, n));
+    return -1.0f;
+}
+RTB_HD bool tri_intersect(const Tri48 &tr, V3 o, V3 d, float tmax, float &t_out, float &u_out,
+                          float &v_out) {
+    float u, v;
+    const float t = tri_candidate(tr, o, d, u, v);
+    if (0.0f < t && t <= tmax) {
+        t_out = t; u_out = u; v_out = v;
+        return true;
     }
     return false;
 }

@@ -67,6 +67,7 @@ struct FetchTuning {
     int refill;  // refill idle lanes when fewer than this many lanes hold a live ray
     int steps;   // traversal steps between two warp-wide votes
     int chunk;   // queue entries a warp claims with one atomicAdd
+    int prefetch;  // v2 kernels: prefetch a claimed chunk's rays into L2
 };
 template <bool ANY, int DEC>
 __device__ __forceinline__ void persistent_trace(const WaveState &W, const SceneView &S, int parity, FetchTuning tune) {
@@ -135,6 +136,158 @@ __global__ void __launch_bounds__(kBlock, 4) k_extend(WaveState W, SceneView S, 
 __global__ void __launch_bounds__(kBlock, 4) k_shadow(WaveState W, SceneView S, int parity, FetchTuning tune) {
     persistent_trace<true, 0>(W, S, parity, tune);
 }
+// ---- v2: pooled triangle tests ----
+// ncu r1 (profiles/r1_ncu_full_big_launches_session6.txt and the source page of the same capture):
+// the node step ran with 24 of 32 lanes but the per-ray triangle loop with 5-8, and took 31 % of
+// the issue slots of k_extend for ~1 triangle per ray and step.  Here the hit triangles of all the
+// rays of a warp are pooled in shared memory after every node step and tested 32 at a time, one
+// candidate per lane whatever ray it belongs to; the order-dependent accept rule (0 < t <= tmax,
+// tmax shrinking, last tie wins: triangle.cuh:49, bvh.cuh:231) stays with the ray's own lane, which
+// walks its candidates in the same order as the per-ray loop, so results are bit-identical.
+struct alignas(16) WarpScratch {
+    float4 ro[32];   // per lane: ray origin | pixel (extend)
+    float4 rd[32];   // per lane: ray direction | sample<<8|bounces (extend)
+    float4 res[32];  // per candidate: t (or -1), u, v, leaf-order triangle index
+    uint2 item[32];  // per candidate: leaf-order triangle index, owner lane
+};
+template <bool ANY, int DEC>
+__device__ __forceinline__ void coop_triangles(WarpScratch &ws, const Bvh8View &B, Traversal<ANY, false, DEC> &T, uint32_t tx,
+                                               uint32_t ty, bool &has, bool &pending, const unsigned lane) {
+    while (__any_sync(0xffffffffu, ty != 0u)) {
+        const int cnt = __popc(ty);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int first = incl - cnt;
+        const int take = max(0, min(cnt, 32 - first));  // candidates beyond 32 wait for the next round
+        for (int k = 0; k < take; ++k) {
+            const int bit = 31 - __clz(ty);
+            ty &= ~(1u << bit);
+            ws.item[first + k] = make_uint2(tx + (uint32_t)bit, lane);
+        }
+        __syncwarp();
+        if ((int)lane < min(total, 32)) {
+            const uint2 it = ws.item[lane];
+            const float4 o = ws.ro[it.y], d = ws.rd[it.y];
+            const Tri48 tr = load_tri(B.tris, (int)it.x);
+            float u, v;
+            const float t = tri_candidate(tr, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), u, v);
+            ws.res[lane] = make_float4(t, u, v, __int_as_float((int)it.x));
+        }
+        __syncwarp();
+        for (int k = 0; k < take; ++k) {
+            const float4 c = ws.res[first + k];
+            if (T.accept(__float_as_int(c.w), c.x, c.y, c.z)) {  // any-hit ray occluded: finished
+                ty = 0u; has = false; pending = true;
+                break;
+            }
+        }
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <bool ANY, int DEC>
+__device__ __forceinline__ void persistent_trace2(WarpScratch &ws, const WaveState &W, const SceneView &S, int parity, FetchTuning tune) {
+    const int n = ANY ? W.c->n_shadow[parity] : W.c->n_extend[parity];
+    int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lanes_below = (1u << lane) - 1u;
+    Traversal<ANY, false, DEC> T;
+    uint32_t stack_x[kStackSize], stack_y[kStackSize];
+    bool has = false, exhausted = false, pending = false;
+    int qi = 0;
+    int chunk_next = 0, chunk_end = 0;
+    while (true) {
+        if (pending) {  // results of the rays that finished since the last refill, written together
+            if (ANY) {
+                shadow_finish(W, qi, T.found);
+            } else if (T.hit.tri >= 0) {
+                const int mat = S.tri_meta[T.hit.tri].material;
+                const int type = mat >> 24;
+                int j;
+                if (type == RTB_MATTE) j = queue_push(&W.c->n_mat[0]);
+                else if (type == RTB_MIRROR) j = W.pool + queue_push(&W.c->n_mat[1]);
+                else j = 2 * W.pool + queue_push(&W.c->n_mat[2]);
+                const F4 beta = ldg(W.ec + qi);
+                const float4 o = ws.ro[lane], d = ws.rd[lane];
+                F4 ma; ma.x = d.x; ma.y = d.y; ma.z = d.z; ma.w = o.w;
+                F4 mb; mb.x = beta.x; mb.y = beta.y; mb.z = beta.z; mb.w = d.w;
+                F4 mc; mc.x = i2f(mat); mc.y = T.hit.u; mc.z = T.hit.v; mc.w = i2f(T.hit.tri);
+                W.ma[j] = ma; W.mb[j] = mb; W.mc[j] = mc;
+            }
+            pending = false;
+        }
+        unsigned need = __ballot_sync(0xffffffffu, !has);
+        for (int round = 0; round < 2 && need != 0u && !exhausted; ++round) {
+            if (chunk_next >= chunk_end) {
+                int base = 0;
+                if (lane == 0u) base = atomicAdd(head, tune.chunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                chunk_next = base;
+                chunk_end = min(base + tune.chunk, n);
+                if (base >= n) { exhausted = true; break; }
+                if (tune.prefetch) {  // pull the chunk's rays towards L2 while the warp still traverses
+                    for (int i = base + (int)lane; i < chunk_end; i += 32) {
+                        if (ANY) { prefetch_l2(W.sh_o + i); prefetch_l2(W.sh_d + i); }
+                        else { prefetch_l2(W.ea + i); prefetch_l2(W.eb + i); prefetch_l2(W.ec + i); }
+                    }
+                }
+            }
+            const int idx = chunk_next + __popc(need & lanes_below);
+            if (!has && idx < chunk_end) {
+                qi = idx;
+                if (ANY) {
+                    const F4 o = ldg(W.sh_o + qi), d = ldg(W.sh_d + qi);
+                    ws.ro[lane] = make_float4(o.x, o.y, o.z, 0.f);
+                    ws.rd[lane] = make_float4(d.x, d.y, d.z, 0.f);
+                    T.init(xyz(o), xyz(d), o.w, f2i(d.w));
+                } else {
+                    const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi);
+                    ws.ro[lane] = make_float4(a.x, a.y, a.z, a.w);
+                    ws.rd[lane] = make_float4(b.x, b.y, b.z, b.w);
+                    T.init(xyz(a), xyz(b), FLT_MAX, -1);
+                }
+                has = true;
+            }
+            chunk_next = min(chunk_next + __popc(need), chunk_end);
+            need = __ballot_sync(0xffffffffu, !has);
+        }
+        unsigned act = __ballot_sync(0xffffffffu, has);
+        if (act == 0u) {
+            if (exhausted) return;
+            continue;
+        }
+        const int keep_going = exhausted ? 1 : tune.refill;
+        do {
+            uint32_t tx = 0u, ty = 0u;
+            if (has) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+            coop_triangles<ANY, DEC>(ws, S.bvh, T, tx, ty, has, pending, lane);
+            if (has && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
+            act = __ballot_sync(0xffffffffu, has);
+        } while (__popc(act) >= keep_going);
+    }
+}
+__global__ void __launch_bounds__(kBlock, 4) k_extend2(WaveState W, SceneView S, int parity, FetchTuning tune) {
+    __shared__ WarpScratch scratch[kBlock / 32];
+    persistent_trace2<false, 0>(scratch[threadIdx.x >> 5], W, S, parity, tune);
+}
+__global__ void __launch_bounds__(kBlock, 4) k_shadow2(WaveState W, SceneView S, int parity, FetchTuning tune) {
+    __shared__ WarpScratch scratch[kBlock / 32];
+    persistent_trace2<true, 0>(scratch[threadIdx.x >> 5], W, S, parity, tune);
+}
+// extend and shadow rays of one iteration in ONE launch: a warp that runs out of extend rays goes
+// on with shadow rays, so the tail of the first queue overlaps the start of the second
+__global__ void __launch_bounds__(kBlock, 4) k_trace2(WaveState W, SceneView S, int parity, FetchTuning tune) {
+    __shared__ WarpScratch scratch[kBlock / 32];
+    persistent_trace2<false, 0>(scratch[threadIdx.x >> 5], W, S, parity, tune);
+    __syncwarp();
+    persistent_trace2<true, 0>(scratch[threadIdx.x >> 5], W, S, parity, tune);
+}
 // ---- A/B variants (RTB_VARIANT, tuning runs only) ----
 // 1: dynamic fetch with the PRMT decode; 2/3: static batches of 32 rays per warp, one monolithic
 // traversal loop, I2F / PRMT decode
@@ -193,13 +346,15 @@ struct CudaBackend {
     int dev_ = -1;
     int num_sms_ = 0;
     cudaStream_t stream_ = nullptr;
+    int blocks_extend2_ = 0, blocks_shadow2_ = 0, blocks_trace2_ = 0;
     int blocks_extend_ = 0, blocks_shadow_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_shade4_[3] = {0, 0, 0}, blocks_generate_ = 0, shade_occ_ = 3;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
     int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
-    FetchTuning tune_{24, 1, 128};  // RTB_REFILL / RTB_STEPS / RTB_CHUNK override (tuning runs)
-    int variant_e_ = 0, variant_s_ = 0;  // RTB_VARIANT_E / RTB_VARIANT_S: A/B kernels (tuning runs)
+    FetchTuning tune_{24, 1, 128, 1};  // RTB_REFILL / RTB_STEPS / RTB_CHUNK override (tuning runs)
+    int variant_e_ = 4, variant_s_ = 4;  // RTB_VARIANT_E / RTB_VARIANT_S: 4 = pooled triangle tests (default), 0-3 = A/B kernels (tuning runs)
+    int fused_ = 1;  // RTB_FUSED: extend + shadow of one iteration in one launch (needs variants 4/4)
     int pool_ = 1 << 23;    // default path pool, RTB_POOL overrides (tuning)
 
     explicit CudaBackend(int device) {
@@ -230,6 +385,8 @@ struct CudaBackend {
         if (const char *e = getenv("RTB_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tune_.refill = v; }
         if (const char *e = getenv("RTB_STEPS")) { int v = atoi(e); if (v >= 1) tune_.steps = v; }
         if (const char *e = getenv("RTB_CHUNK")) { int v = atoi(e); if (v >= 32) tune_.chunk = v; }
+        if (const char *e = getenv("RTB_PREFETCH")) tune_.prefetch = atoi(e);
+        if (const char *e = getenv("RTB_FUSED")) fused_ = atoi(e);
         if (const char *e = getenv("RTB_VARIANT_E")) variant_e_ = atoi(e);
         if (const char *e = getenv("RTB_VARIANT_S")) variant_s_ = atoi(e);
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
@@ -238,6 +395,12 @@ struct CudaBackend {
         blocks_extend_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow, kBlock, 0));
         blocks_shadow_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend2, kBlock, 0));
+        blocks_extend2_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow2, kBlock, 0));
+        blocks_shadow2_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace2, kBlock, 0));
+        blocks_trace2_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<0>, kBlock, 0));
         blocks_shade_[0] = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<1>, kBlock, 0));
@@ -327,6 +490,7 @@ struct CudaBackend {
         else if (variant_e_ == 1) k_extend_v1<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         else if (variant_e_ == 2) k_extend_v2<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity);
         else if (variant_e_ == 3) k_extend_v3<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity);
+        else if (variant_e_ == 4) k_extend2<<<blocks_extend2_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         else k_extend<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
@@ -337,8 +501,16 @@ struct CudaBackend {
         else if (variant_s_ == 1) k_shadow_v1<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         else if (variant_s_ == 2) k_shadow_v2<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity);
         else if (variant_s_ == 3) k_shadow_v3<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity);
+        else if (variant_s_ == 4) k_shadow2<<<blocks_shadow2_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         else k_shadow<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
+    }
+    // both ray types in one launch; false = not available with the selected variants
+    bool trace_fused(const WaveState &W, const SceneView &S, int parity, int mode) {
+        if (mode != 0 || !fused_ || variant_e_ != 4 || variant_s_ != 4) return false;
+        k_trace2<<<blocks_trace2_, kBlock, 0, stream_>>>(W, S, parity, tune_);
+        RTB_CUDA_CHECK(cudaGetLastError());
+        return true;
     }
     int32_t *done_flag_device() { return d_done_; }
     void reset_done() { *(volatile int32_t *)h_done_ = 0; }

@@ -427,12 +427,16 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     const int batch = 4;
     const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
     const bool time_stages = stats != nullptr;
+    // per iteration: [0] before shade, [1] before the traversal kernels, [2] after extend (or after the
+    // fused extend+shadow launch), [3] after shadow
     std::vector<typename BE::Time> stage_times, fences;
     size_t fence_head = 0;
     int it = 0;
+    bool fused = false;
     while (true) {
         for (int k = 0; k < batch; ++k, ++it) {
             const int parity = it & 1;
+            if (time_stages) stage_times.push_back(be.now());
             for (int type = 0; type < 3; ++type) {
                 if (!(sc.type_mask >> type & 1u)) continue;
                 ShadeK ks; ks.W = W; ks.S = S; ks.rc = rc; ks.type = type; ks.parity = parity;
@@ -442,11 +446,17 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
             { GenerateK kg; kg.W = W; kg.rc = rc; kg.parity = parity; be.generate(kg); }
             be.control(W, parity);
             if (time_stages) stage_times.push_back(be.now());
-            be.extend(W, S, parity, mode);
-            if (time_stages) stage_times.push_back(be.now());
-            be.shadow(W, S, parity, mode);
-            if (time_stages) stage_times.push_back(be.now());
-            launches += 4;
+            if (be.trace_fused(W, S, parity, mode)) {
+                fused = true;
+                if (time_stages) { stage_times.push_back(be.now()); stage_times.push_back(be.now()); }
+                launches += 3;
+            } else {
+                be.extend(W, S, parity, mode);
+                if (time_stages) stage_times.push_back(be.now());
+                be.shadow(W, S, parity, mode);
+                if (time_stages) stage_times.push_back(be.now());
+                launches += 4;
+            }
         }
         fences.push_back(be.now());
         if (fences.size() - fence_head > 2) be.wait(fences[fence_head++]);
@@ -455,10 +465,11 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     auto t1 = be.now();
     be.wait(t1);
     for (auto &e : fences) be.release(e);
-    float ms_extend = 0.f, ms_shadow = 0.f;
-    for (size_t i = 0; i + 2 < stage_times.size(); i += 3) {
-        ms_extend += be.elapsed_keep(stage_times[i], stage_times[i + 1]);
-        ms_shadow += be.elapsed_keep(stage_times[i + 1], stage_times[i + 2]);
+    float ms_extend = 0.f, ms_shadow = 0.f, ms_shade = 0.f;
+    for (size_t i = 0; i + 3 < stage_times.size(); i += 4) {
+        ms_shade += be.elapsed_keep(stage_times[i], stage_times[i + 1]);
+        ms_extend += be.elapsed_keep(stage_times[i + 1], stage_times[i + 2]);
+        ms_shadow += be.elapsed_keep(stage_times[i + 2], stage_times[i + 3]);
     }
     for (auto &e : stage_times) be.release(e);
     const float ms_total = be.elapsed_ms(t0, t1);
@@ -478,6 +489,8 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
         stats->ms_extend = ms_extend; stats->ms_shadow = ms_shadow;
         stats->ms_total = ms_total;
         stats->ms_other = ms_total - ms_extend - ms_shadow;
+        stats->ms_shade = ms_shade;
+        stats->fused_trace = fused ? 1 : 0;
     }
 }
 

@@ -194,6 +194,7 @@ struct PathStepIn {
     V3 beta;
     uint32_t pixel, sample;
     int32_t bounces;
+    int32_t material;  // TriMeta::material of the hit triangle (index | type << 24)
 };
 struct PathStepOut {
     bool emit; V3 emission;
@@ -209,17 +210,19 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
     out.emit = false; out.extend = false; out.shadow = false;
     // issue every load that only depends on the hit before the roulette logic: the shade kernel is
     // bound by memory latency (ncu r1: long-scoreboard stalls dominate), not by instruction count
-    const TriMeta meta = S.tri_meta[in.hit.tri];
     const Tri48 tr = load_tri(S.bvh.tris, in.hit.tri);
-    rtb_material m = S.materials[meta.material & 0xffffff];  // type is packed in the top byte
+    rtb_material m = S.materials[in.material & 0xffffff];  // type is packed in the top byte
     if (MT >= 0) m.type = MT;
     int b = in.bounces;
     V3 beta = in.beta;
     // init, render.cuh:98-107: only camera rays see emitters
-    if (b == 0 && meta.light >= 0) {
-        const LightDev &l = S.lights[meta.light];
-        out.emit = true;
-        out.emission = v3(l.Lx, l.Ly, l.Lz);
+    if (b == 0) {
+        const int light = S.tri_meta[in.hit.tri].light;
+        if (light >= 0) {
+            const LightDev &l = S.lights[light];
+            out.emit = true;
+            out.emission = v3(l.Lx, l.Ly, l.Lz);
+        }
     }
     // init, render.cuh:109-126: depth cut + Russian roulette (Quirk A: a kill
     // costs one depth level and the roulette is rolled again on the same hit)

@@ -39,7 +39,7 @@ struct Counters {
 
 // Record layouts (each field array has `pool` entries, 16 bytes per entry):
 //   extend queue   ea = origin.xyz | pixel      eb = dir.xyz | sample<<8|bounces   ec = beta.xyz | -
-//   hit queue[t]   ma = dir.xyz    | pixel      mb = beta.xyz | sample<<8|bounces  mc = t,u,v | leaf-order triangle
+//   hit queue[t]   ma = dir.xyz    | pixel      mb = beta.xyz | sample<<8|bounces  mc = material word,u,v | leaf-order triangle
 //   shadow queue   sh_o = origin.xyz | tmax     sh_d = dir.xyz | excluded triangle sh_L = radiance | pixel
 struct WaveState {
     F4 *ea, *eb, *ec;
@@ -132,12 +132,15 @@ RTB_HD void generate_body(const WaveState &W, const RenderConsts &rc, int parity
 // path (the reference parks the slot until max_bounces, Quirk B).
 RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const HitRec &h) {
     if (h.tri < 0) return;
-    const int type = S.tri_meta[h.tri].material >> 24;
+    const int mat = S.tri_meta[h.tri].material;
+    const int type = mat >> 24;
     int j;
     if (type == RTB_MATTE) j = queue_push(&W.c->n_mat[0]);
     else if (type == RTB_MIRROR) j = W.pool + queue_push(&W.c->n_mat[1]);
     else j = 2 * W.pool + queue_push(&W.c->n_mat[2]);
-    F4 hr; hr.x = h.t; hr.y = h.u; hr.z = h.v; hr.w = i2f(h.tri);
+    // the shade kernel needs u, v and the triangle, not t: the slot carries the material word
+    // (index | type << 24) instead, which saves shade one dependent load per hit
+    F4 hr; hr.x = i2f(mat); hr.y = h.u; hr.z = h.v; hr.w = i2f(h.tri);
     const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi), beta = ldg(W.ec + qi);
     W.ma[j] = f4(xyz(b), a.w);
     W.mb[j] = f4(xyz(beta), b.w);
@@ -162,7 +165,8 @@ RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConst
     const F4 a = ldg(W.ma + q), b = ldg(W.mb + q), hr = ldg(W.mc + q);
     PathStepIn in;
     in.wo = xyz(a);
-    in.hit.t = hr.x; in.hit.u = hr.y; in.hit.v = hr.z; in.hit.tri = f2i(hr.w);
+    in.hit.t = 0.f; in.hit.u = hr.y; in.hit.v = hr.z; in.hit.tri = f2i(hr.w);
+    in.material = f2i(hr.x);
     in.beta = xyz(b);
     const uint32_t packed = f2u(b.w);
     in.bounces = (int)(packed & 0xffu);

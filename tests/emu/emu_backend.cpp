@@ -51,6 +51,7 @@ struct HostBackend {
         for (int i = 0; i < n; ++i) generate_body(k.W, k.rc, k.parity, i);
     }
     void control(const WaveState &W, int parity) { control_body(W, parity); }
+    bool trace_fused(const WaveState &, const SceneView &, int, int) { return false; }
     void extend(const WaveState &W, const SceneView &S, int parity, int mode) {
         const int n = W.c->n_extend[parity];
         for (int i = 0; i < n; ++i) { if (mode == 2) extend_body<true>(W, S, i); else extend_body<false>(W, S, i); }

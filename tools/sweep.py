@@ -21,8 +21,10 @@ ap.add_argument("--refill", default="24")
 ap.add_argument("--steps", default="1")
 ap.add_argument("--chunk", default="128")
 ap.add_argument("--pool", default="8388608")
-ap.add_argument("--ve", default="0")
-ap.add_argument("--vs", default="0")
+ap.add_argument("--ve", default="4")
+ap.add_argument("--vs", default="4")
+ap.add_argument("--fused", default="1")
+ap.add_argument("--prefetch", default="1")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--flags", type=int, default=0)
 a = ap.parse_args()
@@ -31,8 +33,10 @@ L = capi.Lib()
 hs = L.host_scene(kind, *L.load_mesh(), grid=grid)
 cam = hs.camera(w / h)
 print(f"workload {a.workload}: {hs.desc.num_triangles} triangles, {w}x{h}x{spp}spp depth {depth}")
-for refill, steps, chunk, pool, ve, vs in itertools.product(a.refill.split(","), a.steps.split(","), a.chunk.split(","), a.pool.split(","), a.ve.split(","), a.vs.split(",")):
-    os.environ.update(RTB_REFILL=refill, RTB_STEPS=steps, RTB_CHUNK=chunk, RTB_POOL=pool, RTB_VARIANT_E=ve, RTB_VARIANT_S=vs)
+for refill, steps, chunk, pool, ve, vs, fused, pf in itertools.product(a.refill.split(","), a.steps.split(","), a.chunk.split(","), a.pool.split(","), a.ve.split(","), a.vs.split(","), a.fused.split(","), a.prefetch.split(",")):
+    if len(a.ve.split(",")) > 1 and a.ve == a.vs and ve != vs:
+        continue  # same list for both: sweep them together
+    os.environ.update(RTB_REFILL=refill, RTB_STEPS=steps, RTB_CHUNK=chunk, RTB_POOL=pool, RTB_VARIANT_E=ve, RTB_VARIANT_S=vs, RTB_FUSED=fused, RTB_PREFETCH=pf)
     ctx = L.context(0)
     sc = ctx.scene(hs.desc)
     bs = sc.stats()
@@ -43,8 +47,8 @@ for refill, steps, chunk, pool, ve, vs in itertools.product(a.refill.split(","),
         if best is None or st.ms_total < best.ms_total:
             best = st
     rays = best.extend_rays + best.shadow_rays
-    print(f"ve {ve} vs {vs} refill {refill:>2} steps {steps:>2} chunk {chunk:>4} pool {pool:>9}: {best.ms_total:8.2f} ms  extend {best.ms_extend:7.2f} "
-          f"shadow {best.ms_shadow:7.2f} other {best.ms_other:6.2f}  {rays / best.ms_total * 1e-3:8.1f} Mrays/s  "
+    print(f"ve {ve} vs {vs} fused {best.fused_trace} pf {pf} refill {refill:>2} steps {steps:>2} chunk {chunk:>4} pool {pool:>9}: {best.ms_total:8.2f} ms  extend {best.ms_extend:7.2f} "
+          f"shadow {best.ms_shadow:7.2f} shade {best.ms_shade:6.2f} other {best.ms_other:6.2f}  {rays / best.ms_total * 1e-3:8.1f} Mrays/s  "
           f"iters {best.iterations}  build {bs.build_ms:.1f} ms nodes {bs.num_nodes} sah {bs.sah_cost:.2f} mean {img.mean():.4f}", flush=True)
     sc.close()
     del sc, ctx
