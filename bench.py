@@ -313,40 +313,48 @@ def main():
         dist.all_reduce(e2e_r, op=dist.ReduceOp.SUM)
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (k_extend), measured live ----
+        # ---- roofline of the dominant kernel, measured live ----
+        # k_trace<3>: the extend AND shadow rays of one iteration in one persistent launch (stats.fused_trace);
+        # its duration is ms_extend (CUDA events on the render stream inside rtb_render_accumulate).
         s0 = stats
-        ext_ms = sum(s.ms_extend for s in s0); sh_ms = sum(s.ms_shadow for s in s0); tot_ms = sum(s.ms_total for s in s0)
-        ext_launches = sum(s.extend_launches for s in s0)
-        ext_rays = sum(s.extend_rays for s in s0)
+        fused = all(s.fused_trace for s in s0)
+        tr_ms = sum(s.ms_extend + s.ms_shadow for s in s0); sh_ms = sum(s.ms_shade for s in s0); tot_ms = sum(s.ms_total for s in s0)
+        tr_launches = sum(s.extend_launches for s in s0)
+        ext_rays = sum(s.extend_rays for s in s0); shd_rays = sum(s.shadow_rays for s in s0)
         pc = capi.render_params(L, width=W, height=H, spp=max(1, min(2, spp)), max_bounces=depth, first_sample=rank * spp,
                                 total_spp=total_spp, flags=capi.RTB_RENDER_COUNT_WORK)
         accum.zero_()
         cst = scene.render_accumulate(cam, pc, accum.data_ptr())
-        nodes_per_ray = cst.extend_nodes / max(cst.extend_rays, 1)
-        tris_per_ray = cst.extend_tris / max(cst.extend_rays, 1)
+        e_nodes = cst.extend_nodes / max(cst.extend_rays, 1); e_tris = cst.extend_tris / max(cst.extend_rays, 1)
+        s_nodes = cst.shadow_nodes / max(cst.shadow_rays, 1); s_tris = cst.shadow_tris / max(cst.shadow_rays, 1)
         hit_frac = cst.hits / max(cst.extend_rays, 1)
-        # algorithmic bytes per extend ray: 80 B per node fetched, 48 B per triangle tested,
-        # 48 B queue record read (origin|pixel, dir|sample, beta), 48 B hit record written when it hits
-        bytes_per_ray = nodes_per_ray * 80 + tris_per_ray * 48 + 48 + 48 * hit_frac
-        avg_launch_ms = ext_ms / max(ext_launches, 1)
-        bytes_per_launch = bytes_per_ray * ext_rays / max(ext_launches, 1)
+        # algorithmic bytes: 80 B per node fetched, 48 B per triangle tested; an extend ray reads its
+        # 32 B record (origin|pixel, dir|sample) and, when it hits, 16 B (beta) and writes the 48 B hit record; a
+        # shadow ray reads 32 B (origin|tmax, dir|excluded) and, unoccluded, 16 B (radiance|pixel) + 12 B splat
+        bytes_extend = e_nodes * 80 + e_tris * 48 + 32 + 64 * hit_frac
+        bytes_shadow = s_nodes * 80 + s_tris * 48 + 32 + 28
+        bytes_per_launch = (bytes_extend * ext_rays + bytes_shadow * shd_rays) / max(tr_launches, 1)
+        avg_launch_ms = tr_ms / max(tr_launches, 1)
         achieved = bytes_per_launch / (avg_launch_ms * 1e-3) * 1e-9 if avg_launch_ms > 0 else 0.0
         peak, peak_src = hbm_peak()
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("k_extend_dram_bytes_per_launch")
+                traffic = json.load(f).get(args.workload, {}).get("k_trace_dram_bytes_per_launch")
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "k_trace<3> (extend + shadow rays, one persistent launch per iteration)" if fused else "k_trace<1> + k_trace<2>",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "hit_fraction": hit_frac,
-                    "avg_launch_ms": avg_launch_ms, "launches": int(ext_launches),
-                    "kernel_share_of_step": ext_ms / tot_ms if tot_ms else None,
-                    "shadow_share_of_step": sh_ms / tot_ms if tot_ms else None,
-                    "note": "scene (%.1f MB nodes+triangles) %s; algorithmic bytes counted by a counting kernel variant"
+                    "algorithmic_bytes_per_extend_ray": bytes_extend, "algorithmic_bytes_per_shadow_ray": bytes_shadow,
+                    "extend_nodes_per_ray": e_nodes, "extend_tris_per_ray": e_tris, "shadow_nodes_per_ray": s_nodes,
+                    "shadow_tris_per_ray": s_tris, "hit_fraction": hit_frac,
+                    "avg_launch_ms": avg_launch_ms, "launches": int(tr_launches),
+                    "kernel_share_of_step": tr_ms / tot_ms if tot_ms else None,
+                    "shade_share_of_step": sh_ms / tot_ms if tot_ms else None,
+                    "note": "scene (%.1f MB nodes+triangles) %s; node/triangle counts from the counting kernel variant"
                             % ((bst.node_bytes + bst.triangle_bytes) / 1e6,
-                               "is L2-resident, so achieved can exceed the HBM peak" if bst.node_bytes + bst.triangle_bytes < 100e6
+                               "is L2-resident: the kernel is bound by instruction issue, not by HBM (see profiles/)" if bst.node_bytes + bst.triangle_bytes < 100e6
                                else "exceeds L2")}
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -43,131 +43,69 @@ __global__ void __launch_bounds__(kBlock) k_for(int n, F f) {
     if (i < n) f(i);
 }
 
-__global__ void __launch_bounds__(kBlock) k_generate(WaveState W, RenderConsts rc, int parity) {
-    const int n = generate_count(W, parity);
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) generate_body(W, rc, parity, i);
+__global__ void __launch_bounds__(kBlock) k_generate(WaveState W, RenderConsts rc) {
+    const int n = generate_count(W);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) generate_body(W, rc, i);
 }
 
 template <int TYPE, int MINB = 3>
-__global__ void __launch_bounds__(kBlock, MINB) k_shade(WaveState W, SceneView S, RenderConsts rc, int parity) {
+__global__ void __launch_bounds__(kBlock, MINB) k_shade(WaveState W, SceneView S, RenderConsts rc, bool shadows) {
     const int n = W.c->n_mat[TYPE];
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) shade_body<TYPE>(W, S, rc, parity, i);
+    ShadeTally tally; tally.extend = 0u; tally.shadow = 0u;
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) shade_body<TYPE>(W, S, rc, shadows, i, tally);
+    tally_flush(W.c, tally);
 }
 
-__global__ void k_control(WaveState W, int parity) { control_body(W, parity); }
+__global__ void k_control(WaveState W, bool shadows) { control_body(W, shadows); }
 
 // Persistent traversal with dynamic ray fetch (after Aila & Laine 2009): the
-// grid is SMs x resident blocks whatever the queue size; a warp claims queue
-// entries with one atomicAdd (elected lane) + shuffle broadcast, and whenever
-// fewer than `refill` of its lanes still hold a live ray the idle lanes claim
-// new entries while the others keep their traversal state, so short rays
-// (a wall) do not wait for long ones (the bunny) in the same warp.  ncu r1,
+// grid is SMs x resident blocks whatever the queue size; a warp claims `chunk`
+// queue entries with one atomicAdd (elected lane) + shuffle broadcast, and
+// whenever fewer than `refill` of its lanes still hold a live ray the idle
+// lanes take new entries while the others keep their traversal state, so short
+// rays (a wall) do not wait for long ones (the bunny) in the same warp.  ncu r1
 // before this: 6.9-11 of 32 lanes active per instruction in k_extend.
 struct FetchTuning {
-    int refill;  // refill idle lanes when fewer than this many lanes hold a live ray
-    int steps;   // traversal steps between two warp-wide votes
-    int chunk;   // queue entries a warp claims with one atomicAdd
-    int prefetch;  // v2 kernels: prefetch a claimed chunk's rays into L2
+    int refill;    // refill idle lanes when fewer than this many lanes hold a live ray
+    int chunk;     // queue entries a warp claims with one atomicAdd
+    int prefetch;  // prefetch a claimed chunk's rays into L2
 };
-template <bool ANY, int DEC>
-__device__ __forceinline__ void persistent_trace(const WaveState &W, const SceneView &S, int parity, FetchTuning tune) {
-    const int n = ANY ? W.c->n_shadow[parity] : W.c->n_extend[parity];
-    int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lanes_below = (1u << lane) - 1u;
-    Traversal<ANY, false, DEC> T;
-    uint32_t stack_x[kStackSize], stack_y[kStackSize];
-    bool has = false, exhausted = false, pending = false;
-    int qi = 0;
-    int chunk_next = 0, chunk_end = 0;  // warp-uniform: the part of the queue this warp has claimed
-    while (true) {
-        // results of the rays that finished since the last refill are written here, together, so
-        // that the hit-record / atomic code runs with many lanes instead of one at a time
-        if (pending) {
-            if (ANY) shadow_finish(W, qi, T.found);
-            else extend_finish(W, S, qi, T.hit);
-            pending = false;
-        }
-        // hand queue entries to the idle lanes; a new chunk is claimed (one atomic per warp) when the
-        // current one runs out, so most refills cost no global round trip at all
-        unsigned need = __ballot_sync(0xffffffffu, !has);
-        for (int round = 0; round < 2 && need != 0u && !exhausted; ++round) {
-            if (chunk_next >= chunk_end) {
-                int base = 0;
-                if (lane == 0u) base = atomicAdd(head, tune.chunk);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                chunk_next = base;
-                chunk_end = min(base + tune.chunk, n);
-                if (base >= n) { exhausted = true; break; }
-            }
-            const int idx = chunk_next + __popc(need & lanes_below);
-            if (!has && idx < chunk_end) {
-                qi = idx;
-                if (ANY) {
-                    const F4 o = ldg(W.sh_o + qi), d = ldg(W.sh_d + qi);
-                    T.init(xyz(o), xyz(d), o.w, f2i(d.w));
-                } else {
-                    const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi);
-                    T.init(xyz(a), xyz(b), FLT_MAX, -1);
-                }
-                has = true;
-            }
-            chunk_next = min(chunk_next + __popc(need), chunk_end);
-            need = __ballot_sync(0xffffffffu, !has);
-        }
-        unsigned act = __ballot_sync(0xffffffffu, has);
-        if (act == 0u) {
-            if (exhausted) return;
-            continue;  // chunk boundary: claim the next one
-        }
-        const int keep_going = exhausted ? 1 : tune.refill;
-        do {
-#pragma unroll 1
-            for (int k = 0; k < tune.steps && has; ++k) {
-                if (!T.step(S.bvh, stack_x, stack_y)) { has = false; pending = true; }
-            }
-            act = __ballot_sync(0xffffffffu, has);
-        } while (__popc(act) >= keep_going);
-    }
-}
-__global__ void __launch_bounds__(kBlock, 4) k_extend(WaveState W, SceneView S, int parity, FetchTuning tune) {
-    persistent_trace<false, 0>(W, S, parity, tune);
-}
-__global__ void __launch_bounds__(kBlock, 4) k_shadow(WaveState W, SceneView S, int parity, FetchTuning tune) {
-    persistent_trace<true, 0>(W, S, parity, tune);
-}
-// ---- v2: pooled triangle tests ----
-// ncu r1 (profiles/r1_ncu_full_big_launches_session6.txt and the source page of the same capture):
-// the node step ran with 24 of 32 lanes but the per-ray triangle loop with 5-8, and took 31 % of
-// the issue slots of k_extend for ~1 triangle per ray and step.  Here the hit triangles of all the
-// rays of a warp are pooled in shared memory after every node step and tested 32 at a time, one
-// candidate per lane whatever ray it belongs to; the order-dependent accept rule (0 < t <= tmax,
-// tmax shrinking, last tie wins: triangle.cuh:49, bvh.cuh:231) stays with the ray's own lane, which
-// walks its candidates in the same order as the per-ray loop, so results are bit-identical.
+
+// Pooled triangle tests (POOL).  ncu r1 (profiles/r1_ncu_full_big_launches_session6.txt and the
+// source page of the same capture): the node step ran with 24 of 32 lanes but the per-ray triangle
+// loop with 5-8, and took 31 % of the issue slots of k_extend for ~1 triangle per ray and step.
+// With POOL the hit triangles of all the rays of a warp are gathered in shared memory after every
+// node step and tested 32 at a time, one candidate per lane whatever ray it belongs to; the
+// order-dependent accept rule (0 < t <= tmax, tmax shrinking, last tie wins: triangle.cuh:49,
+// bvh.cuh:231) stays with the ray's own lane, which walks its candidates in the same order as the
+// per-ray loop, so results are bit-identical.
 struct alignas(16) WarpScratch {
     float4 ro[32];   // per lane: ray origin | pixel (extend)
     float4 rd[32];   // per lane: ray direction | sample<<8|bounces (extend)
     float4 res[32];  // per candidate: t (or -1), u, v, leaf-order triangle index
     uint2 item[32];  // per candidate: leaf-order triangle index, owner lane
 };
-template <bool ANY, int DEC>
-__device__ __forceinline__ void coop_triangles(WarpScratch &ws, const Bvh8View &B, Traversal<ANY, false, DEC> &T, uint32_t tx,
-                                               uint32_t ty, bool &has, bool &pending, const unsigned lane) {
+template <bool ANY>
+__device__ __forceinline__ void pooled_triangles(WarpScratch &ws, const Bvh8View &B, Traversal<ANY, false> &T, uint32_t tx,
+                                                 uint32_t ty, bool &has, bool &pending, const unsigned lane,
+                                                 const unsigned lanes_below) {
+    // A lane submits at most 3 candidates per round (one leaf child holds <= 3 triangles), so the
+    // positions come from two ballots instead of a 5-step shuffle scan and the per-lane loops are
+    // three predicated steps; a lane's surplus, and whatever does not fit in 32 slots, waits for the
+    // next round.
     while (__any_sync(0xffffffffu, ty != 0u)) {
-        const int cnt = __popc(ty);
-        int incl = cnt;
+        const int cnt = min(__popc(ty), 3);
+        const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2);
+        const int first = __popc(b0 & lanes_below) + 2 * __popc(b1 & lanes_below);
+        const int total = __popc(b0) + 2 * __popc(b1);
+        const int take = max(0, min(cnt, 32 - first));
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((int)lane >= d) incl += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int first = incl - cnt;
-        const int take = max(0, min(cnt, 32 - first));  // candidates beyond 32 wait for the next round
-        for (int k = 0; k < take; ++k) {
-            const int bit = 31 - __clz(ty);
-            ty &= ~(1u << bit);
-            ws.item[first + k] = make_uint2(tx + (uint32_t)bit, lane);
+        for (int k = 0; k < 3; ++k) {
+            if (k < take) {
+                const int bit = 31 - __clz(ty);
+                ty &= ~(1u << bit);
+                ws.item[first + k] = make_uint2(tx + (uint32_t)bit, lane);
+            }
         }
         __syncwarp();
         if ((int)lane < min(total, 32)) {
@@ -179,31 +117,49 @@ __device__ __forceinline__ void coop_triangles(WarpScratch &ws, const Bvh8View &
             ws.res[lane] = make_float4(t, u, v, __int_as_float((int)it.x));
         }
         __syncwarp();
-        for (int k = 0; k < take; ++k) {
-            const float4 c = ws.res[first + k];
-            if (T.accept(__float_as_int(c.w), c.x, c.y, c.z)) {  // any-hit ray occluded: finished
-                ty = 0u; has = false; pending = true;
-                break;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < take && has) {
+                const float4 c = ws.res[first + k];
+                if (T.accept(__float_as_int(c.w), c.x, c.y, c.z)) {  // any-hit ray occluded: finished
+                    ty = 0u; has = false; pending = true;
+                }
             }
         }
         __syncwarp();
     }
 }
+// the same triangles, each ray's lane on its own (A/B, and the better choice when rays meet ~1 triangle per step)
+template <bool ANY>
+__device__ __forceinline__ void own_triangles(const Bvh8View &B, Traversal<ANY, false> &T, uint32_t tx, uint32_t ty, bool &has,
+                                              bool &pending) {
+    while (ty) {
+        const int bit = 31 - __clz(ty);
+        ty &= ~(1u << bit);
+        const int idx = (int)(tx + (uint32_t)bit);
+        const Tri48 tr = load_tri(B.tris, idx);
+        float u, v;
+        const float t = tri_candidate(tr, T.r.o, T.r.d, u, v);
+        if (T.accept(idx, t, u, v)) { has = false; pending = true; break; }
+    }
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <bool ANY, int DEC>
-__device__ __forceinline__ void persistent_trace2(WarpScratch &ws, const WaveState &W, const SceneView &S, int parity, FetchTuning tune) {
-    const int n = ANY ? W.c->n_shadow[parity] : W.c->n_extend[parity];
+template <bool ANY, bool POOL>
+__device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveState &W, const SceneView &S, FetchTuning tune) {
+    const int n = ANY ? W.c->n_shadow : W.c->n_extend;
     int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanes_below = (1u << lane) - 1u;
-    Traversal<ANY, false, DEC> T;
+    Traversal<ANY, false> T;
     uint32_t stack_x[kStackSize], stack_y[kStackSize];
     bool has = false, exhausted = false, pending = false;
     int qi = 0;
-    int chunk_next = 0, chunk_end = 0;
+    int chunk_next = 0, chunk_end = 0;  // warp-uniform: the part of the queue this warp has claimed
     while (true) {
-        if (pending) {  // results of the rays that finished since the last refill, written together
+        // results of the rays that finished since the last refill are written here, together, so
+        // that the hit-record / atomic code runs with many lanes instead of one at a time
+        if (pending) {
             if (ANY) {
                 shadow_finish(W, qi, T.found);
             } else if (T.hit.tri >= 0) {
@@ -222,6 +178,9 @@ __device__ __forceinline__ void persistent_trace2(WarpScratch &ws, const WaveSta
             }
             pending = false;
         }
+        // hand queue entries to the idle lanes; a new chunk is claimed (one atomic per warp) when the
+        // current one runs out, so most refills cost no global round trip at all.  Holes (slots whose
+        // path cast no ray) leave their lane idle for this round.
         unsigned need = __ballot_sync(0xffffffffu, !has);
         for (int round = 0; round < 2 && need != 0u && !exhausted; ++round) {
             if (chunk_next >= chunk_end) {
@@ -240,19 +199,25 @@ __device__ __forceinline__ void persistent_trace2(WarpScratch &ws, const WaveSta
             }
             const int idx = chunk_next + __popc(need & lanes_below);
             if (!has && idx < chunk_end) {
-                qi = idx;
                 if (ANY) {
-                    const F4 o = ldg(W.sh_o + qi), d = ldg(W.sh_d + qi);
-                    ws.ro[lane] = make_float4(o.x, o.y, o.z, 0.f);
-                    ws.rd[lane] = make_float4(d.x, d.y, d.z, 0.f);
-                    T.init(xyz(o), xyz(d), o.w, f2i(d.w));
+                    const F4 o = ldg(W.sh_o + idx);
+                    if (o.w > 0.f) {
+                        const F4 d = ldg(W.sh_d + idx);
+                        ws.ro[lane] = make_float4(o.x, o.y, o.z, 0.f);
+                        ws.rd[lane] = make_float4(d.x, d.y, d.z, 0.f);
+                        T.init(xyz(o), xyz(d), o.w, f2i(d.w));
+                        qi = idx; has = true;
+                    }
                 } else {
-                    const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi);
-                    ws.ro[lane] = make_float4(a.x, a.y, a.z, a.w);
-                    ws.rd[lane] = make_float4(b.x, b.y, b.z, b.w);
-                    T.init(xyz(a), xyz(b), FLT_MAX, -1);
+                    const F4 a = ldg(W.ea + idx);
+                    if (f2u(a.w) != kHolePixel) {
+                        const F4 b = ldg(W.eb + idx);
+                        ws.ro[lane] = make_float4(a.x, a.y, a.z, a.w);
+                        ws.rd[lane] = make_float4(b.x, b.y, b.z, b.w);
+                        T.init(xyz(a), xyz(b), FLT_MAX, -1);
+                        qi = idx; has = true;
+                    }
                 }
-                has = true;
             }
             chunk_next = min(chunk_next + __popc(need), chunk_end);
             need = __ballot_sync(0xffffffffu, !has);
@@ -260,82 +225,40 @@ __device__ __forceinline__ void persistent_trace2(WarpScratch &ws, const WaveSta
         unsigned act = __ballot_sync(0xffffffffu, has);
         if (act == 0u) {
             if (exhausted) return;
-            continue;
+            continue;  // chunk boundary (or a run of holes): claim more
         }
         const int keep_going = exhausted ? 1 : tune.refill;
         do {
             uint32_t tx = 0u, ty = 0u;
             if (has) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
-            coop_triangles<ANY, DEC>(ws, S.bvh, T, tx, ty, has, pending, lane);
+            if (POOL) pooled_triangles<ANY>(ws, S.bvh, T, tx, ty, has, pending, lane, lanes_below);
+            else own_triangles<ANY>(S.bvh, T, tx, ty, has, pending);
             if (has && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
             act = __ballot_sync(0xffffffffu, has);
         } while (__popc(act) >= keep_going);
     }
 }
-__global__ void __launch_bounds__(kBlock, 4) k_extend2(WaveState W, SceneView S, int parity, FetchTuning tune) {
+// extend and shadow rays of one iteration in ONE launch (WHICH = 3): a warp that runs out of extend
+// rays goes on with shadow rays, so the tail of the first queue overlaps the start of the second.
+// WHICH = 1 / 2: extend / shadow only (A/B, and per-stage timing).
+template <int WHICH, bool POOL>
+__global__ void __launch_bounds__(kBlock, 4) k_trace(WaveState W, SceneView S, FetchTuning tune) {
     __shared__ WarpScratch scratch[kBlock / 32];
-    persistent_trace2<false, 0>(scratch[threadIdx.x >> 5], W, S, parity, tune);
+    WarpScratch &ws = scratch[threadIdx.x >> 5];
+    if (WHICH & 1) persistent_trace<false, POOL>(ws, W, S, tune);
+    if (WHICH == 3) __syncwarp();
+    if (WHICH & 2) persistent_trace<true, POOL>(ws, W, S, tune);
 }
-__global__ void __launch_bounds__(kBlock, 4) k_shadow2(WaveState W, SceneView S, int parity, FetchTuning tune) {
-    __shared__ WarpScratch scratch[kBlock / 32];
-    persistent_trace2<true, 0>(scratch[threadIdx.x >> 5], W, S, parity, tune);
-}
-// extend and shadow rays of one iteration in ONE launch: a warp that runs out of extend rays goes
-// on with shadow rays, so the tail of the first queue overlaps the start of the second
-__global__ void __launch_bounds__(kBlock, 4) k_trace2(WaveState W, SceneView S, int parity, FetchTuning tune) {
-    __shared__ WarpScratch scratch[kBlock / 32];
-    persistent_trace2<false, 0>(scratch[threadIdx.x >> 5], W, S, parity, tune);
-    __syncwarp();
-    persistent_trace2<true, 0>(scratch[threadIdx.x >> 5], W, S, parity, tune);
-}
-// ---- A/B variants (RTB_VARIANT, tuning runs only) ----
-// 1: dynamic fetch with the PRMT decode; 2/3: static batches of 32 rays per warp, one monolithic
-// traversal loop, I2F / PRMT decode
-__global__ void __launch_bounds__(kBlock, 4) k_extend_v1(WaveState W, SceneView S, int parity, FetchTuning tune) {
-    persistent_trace<false, 1>(W, S, parity, tune);
-}
-__global__ void __launch_bounds__(kBlock, 4) k_shadow_v1(WaveState W, SceneView S, int parity, FetchTuning tune) {
-    persistent_trace<true, 1>(W, S, parity, tune);
-}
-template <bool ANY, int DEC>
-__device__ __forceinline__ void static_batches(const WaveState &W, const SceneView &S, int parity) {
-    const int n = ANY ? W.c->n_shadow[parity] : W.c->n_extend[parity];
-    int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
-    const unsigned lane = threadIdx.x & 31u;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(head, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) return;
-        const int i = base + (int)lane;
-        if (i < n) {
-            HitRec h;
-            if (ANY) {
-                const F4 o = ldg(W.sh_o + i), d = ldg(W.sh_d + i);
-                shadow_finish(W, i, bvh8_trace_mono<true, DEC>(S.bvh, xyz(o), xyz(d), o.w, f2i(d.w), h));
-            } else {
-                const F4 a = ldg(W.ea + i), b = ldg(W.eb + i);
-                bvh8_trace_mono<false, DEC>(S.bvh, xyz(a), xyz(b), FLT_MAX, -1, h);
-                extend_finish(W, S, i, h);
-            }
-        }
-        __syncwarp();
-    }
-}
-__global__ void __launch_bounds__(kBlock, 4) k_extend_v2(WaveState W, SceneView S, int parity) { static_batches<false, 0>(W, S, parity); }
-__global__ void __launch_bounds__(kBlock, 4) k_shadow_v2(WaveState W, SceneView S, int parity) { static_batches<true, 0>(W, S, parity); }
-__global__ void __launch_bounds__(kBlock, 4) k_extend_v3(WaveState W, SceneView S, int parity) { static_batches<false, 1>(W, S, parity); }
-__global__ void __launch_bounds__(kBlock, 4) k_shadow_v3(WaveState W, SceneView S, int parity) { static_batches<true, 1>(W, S, parity); }
 // one thread per queue entry (A/B against the persistent kernels; COUNT = work counters)
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_extend_flat(WaveState W, SceneView S, int parity) {
+__global__ void __launch_bounds__(kBlock) k_extend_flat(WaveState W, SceneView S) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i < W.c->n_extend[parity]) extend_body<COUNT>(W, S, i);
+    if (i < W.c->n_extend) extend_body<COUNT>(W, S, i);
 }
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S, int parity) {
+__global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i < W.c->n_shadow[parity]) shadow_body<COUNT>(W, S, i);
+    if (i < W.c->n_shadow) shadow_body<COUNT>(W, S, i);
 }
 
 struct NonNegative {
@@ -346,15 +269,14 @@ struct CudaBackend {
     int dev_ = -1;
     int num_sms_ = 0;
     cudaStream_t stream_ = nullptr;
-    int blocks_extend2_ = 0, blocks_shadow2_ = 0, blocks_trace2_ = 0;
-    int blocks_extend_ = 0, blocks_shadow_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_shade4_[3] = {0, 0, 0}, blocks_generate_ = 0, shade_occ_ = 3;
+    int blocks_trace_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_shade4_[3] = {0, 0, 0}, blocks_generate_ = 0, shade_occ_ = 3;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
     int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
-    FetchTuning tune_{24, 1, 128, 1};  // RTB_REFILL / RTB_STEPS / RTB_CHUNK override (tuning runs)
-    int variant_e_ = 4, variant_s_ = 4;  // RTB_VARIANT_E / RTB_VARIANT_S: 4 = pooled triangle tests (default), 0-3 = A/B kernels (tuning runs)
-    int fused_ = 1;  // RTB_FUSED: extend + shadow of one iteration in one launch (needs variants 4/4)
+    FetchTuning tune_{24, 128, 1};  // RTB_REFILL / RTB_CHUNK / RTB_PREFETCH override (tuning runs)
+    int pooled_ = 1;  // RTB_POOLED: pooled triangle tests (1) or each ray's lane on its own (0)
+    int fused_ = 1;   // RTB_FUSED: extend + shadow rays of one iteration in one launch
     int pool_ = 1 << 23;    // default path pool, RTB_POOL overrides (tuning)
 
     explicit CudaBackend(int device) {
@@ -383,24 +305,14 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaHostGetDevicePointer((void **)&d_done_, h_done_, 0));
         *h_done_ = 0;
         if (const char *e = getenv("RTB_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tune_.refill = v; }
-        if (const char *e = getenv("RTB_STEPS")) { int v = atoi(e); if (v >= 1) tune_.steps = v; }
         if (const char *e = getenv("RTB_CHUNK")) { int v = atoi(e); if (v >= 32) tune_.chunk = v; }
         if (const char *e = getenv("RTB_PREFETCH")) tune_.prefetch = atoi(e);
+        if (const char *e = getenv("RTB_POOLED")) pooled_ = atoi(e);
         if (const char *e = getenv("RTB_FUSED")) fused_ = atoi(e);
-        if (const char *e = getenv("RTB_VARIANT_E")) variant_e_ = atoi(e);
-        if (const char *e = getenv("RTB_VARIANT_S")) variant_s_ = atoi(e);
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
         int per_sm = 0;
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend, kBlock, 0));
-        blocks_extend_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow, kBlock, 0));
-        blocks_shadow_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_extend2, kBlock, 0));
-        blocks_extend2_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shadow2, kBlock, 0));
-        blocks_shadow2_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace2, kBlock, 0));
-        blocks_trace2_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<3, true>, kBlock, 0));
+        blocks_trace_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<0>, kBlock, 0));
         blocks_shade_[0] = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<1>, kBlock, 0));
@@ -460,55 +372,50 @@ struct CudaBackend {
     }
     template <class F> void launch_trace(int n, F f) { launch(n, f); }
     void generate(const GenerateK &k) {
-        k_generate<<<blocks_generate_, kBlock, 0, stream_>>>(k.W, k.rc, k.parity);
+        k_generate<<<blocks_generate_, kBlock, 0, stream_>>>(k.W, k.rc);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shade(const ShadeK &k) {
         if (shade_occ_ == 4) {  // tuning: 64 registers (small spills), 4 blocks per SM
             const int g4 = blocks_shade4_[k.type];
-            if (k.type == 0) k_shade<0, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
-            else if (k.type == 1) k_shade<1, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
-            else k_shade<2, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
+            if (k.type == 0) k_shade<0, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 1) k_shade<1, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else k_shade<2, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             RTB_CUDA_CHECK(cudaGetLastError());
             return;
         }
         const int grid = blocks_shade_[k.type];  // exactly one resident wave: the kernels are grid-stride loops
-        if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
-        else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
-        else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.parity);
+        if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+        else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+        else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
-    void control(const WaveState &W, int parity) {
-        k_control<<<1, 1, 0, stream_>>>(W, parity);
+    void control(const WaveState &W, bool shadows) {
+        k_control<<<1, 1, 0, stream_>>>(W, shadows);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     // mode 0: persistent, 1: one thread per ray, 2: one thread per ray + work counters
-    void extend(const WaveState &W, const SceneView &S, int parity, int mode) {
+    void extend(const WaveState &W, const SceneView &S, int mode) {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
-        if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
-        else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
-        else if (variant_e_ == 1) k_extend_v1<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity, tune_);
-        else if (variant_e_ == 2) k_extend_v2<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity);
-        else if (variant_e_ == 3) k_extend_v3<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity);
-        else if (variant_e_ == 4) k_extend2<<<blocks_extend2_, kBlock, 0, stream_>>>(W, S, parity, tune_);
-        else k_extend<<<blocks_extend_, kBlock, 0, stream_>>>(W, S, parity, tune_);
+        if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
+        else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
+        else if (pooled_) k_trace<1, true><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
+        else k_trace<1, false><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
-    void shadow(const WaveState &W, const SceneView &S, int parity, int mode) {
+    void shadow(const WaveState &W, const SceneView &S, int mode) {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
-        if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
-        else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S, parity);
-        else if (variant_s_ == 1) k_shadow_v1<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity, tune_);
-        else if (variant_s_ == 2) k_shadow_v2<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity);
-        else if (variant_s_ == 3) k_shadow_v3<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity);
-        else if (variant_s_ == 4) k_shadow2<<<blocks_shadow2_, kBlock, 0, stream_>>>(W, S, parity, tune_);
-        else k_shadow<<<blocks_shadow_, kBlock, 0, stream_>>>(W, S, parity, tune_);
+        if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
+        else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
+        else if (pooled_) k_trace<2, true><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
+        else k_trace<2, false><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
-    // both ray types in one launch; false = not available with the selected variants
-    bool trace_fused(const WaveState &W, const SceneView &S, int parity, int mode) {
-        if (mode != 0 || !fused_ || variant_e_ != 4 || variant_s_ != 4) return false;
-        k_trace2<<<blocks_trace2_, kBlock, 0, stream_>>>(W, S, parity, tune_);
+    // both ray types in one launch; false = not available in this mode
+    bool trace_fused(const WaveState &W, const SceneView &S, int mode) {
+        if (mode != 0 || !fused_) return false;
+        if (pooled_) k_trace<3, true><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
+        else k_trace<3, false><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
         return true;
     }

@@ -8,8 +8,8 @@
 // library never contains it (no CPU fallback).
 //
 // Host loop being replaced: render(), render.cuh:366-457 (13 launches and 4
-// blocking 4-byte device->host copies per iteration); here an iteration is 7
-// launches, and the host looks at one `done` word every few iterations.
+// blocking 4-byte device->host copies per iteration); here an iteration is 4
+// launches (shade, generate, control, trace), and the host looks at one `done` word every few iterations.
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -60,8 +60,8 @@ struct IngestK {
         if (tm.light >= 0) light_tri[tm.light] = i;
     }
 };
-struct GenerateK { WaveState W; RenderConsts rc; int parity; };
-struct ShadeK { WaveState W; SceneView S; RenderConsts rc; int type, parity; };
+struct GenerateK { WaveState W; RenderConsts rc; };
+struct ShadeK { WaveState W; SceneView S; RenderConsts rc; int type; bool shadows; };
 struct TonemapK {  // post_process_framebuffer, render.cuh:330-338
     const float *in; float *out; int64_t n; float inv_spp;
     RTB_HD void operator()(int i) const { if (i < n) out[i] = fsqrt(fmul(in[i], inv_spp)); }
@@ -427,6 +427,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     const int batch = 4;
     const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
     const bool time_stages = stats != nullptr;
+    const bool shadows = sc.num_lights > 0 && !(p.flags & RTB_RENDER_NO_SHADOW);
     // per iteration: [0] before shade, [1] before the traversal kernels, [2] after extend (or after the
     // fused extend+shadow launch), [3] after shadow
     std::vector<typename BE::Time> stage_times, fences;
@@ -435,25 +436,24 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     bool fused = false;
     while (true) {
         for (int k = 0; k < batch; ++k, ++it) {
-            const int parity = it & 1;
             if (time_stages) stage_times.push_back(be.now());
             for (int type = 0; type < 3; ++type) {
                 if (!(sc.type_mask >> type & 1u)) continue;
-                ShadeK ks; ks.W = W; ks.S = S; ks.rc = rc; ks.type = type; ks.parity = parity;
+                ShadeK ks; ks.W = W; ks.S = S; ks.rc = rc; ks.type = type; ks.shadows = shadows;
                 be.shade(ks);
                 ++launches;
             }
-            { GenerateK kg; kg.W = W; kg.rc = rc; kg.parity = parity; be.generate(kg); }
-            be.control(W, parity);
+            { GenerateK kg; kg.W = W; kg.rc = rc; be.generate(kg); }
+            be.control(W, shadows);
             if (time_stages) stage_times.push_back(be.now());
-            if (be.trace_fused(W, S, parity, mode)) {
+            if (be.trace_fused(W, S, mode)) {
                 fused = true;
                 if (time_stages) { stage_times.push_back(be.now()); stage_times.push_back(be.now()); }
                 launches += 3;
             } else {
-                be.extend(W, S, parity, mode);
+                be.extend(W, S, mode);
                 if (time_stages) stage_times.push_back(be.now());
-                be.shadow(W, S, parity, mode);
+                be.shadow(W, S, mode);
                 if (time_stages) stage_times.push_back(be.now());
                 launches += 4;
             }

@@ -9,17 +9,18 @@
 //     compacted at its queue position as three 16-byte words, so every stage
 //     reads and writes whole 128-bit words at consecutive addresses
 //     (the reference gathers 7 scalars per ray through an id indirection);
-//   - queues are filled by the producing kernel through warp-aggregated
-//     atomics (ballot + prefix popcount): no compaction pass, no flag arrays,
-//     no per-iteration device->host copy of queue sizes;
+//   - the hit queues are filled by the extend kernel through warp-aggregated
+//     atomics (ballot + prefix popcount); the ray queues are written by shade
+//     at the path's own hit-queue position (holes where a path casts no ray):
+//     no compaction pass, no flag arrays, no per-iteration device->host copy
+//     of queue sizes;
 //   - a finished path frees queue capacity at once and `generate` tops the
 //     extend queue up with new camera paths every iteration (no lock-step
 //     generations, SURVEY §3.3 Quirk B);
 //   - hits are written into one queue per material type, so each shade launch
 //     runs a single BSDF (material sort without a sort);
 //   - per-path RNG is a counter hash (no 48-byte XORWOW state traffic).
-// Queue counters are double-buffered by iteration parity so that one
-// single-thread control kernel per iteration is enough.
+// One single-thread control kernel per iteration does the queue bookkeeping.
 // Bodies are RTB_HD: kernels in rtb_cuda.cu are thin wrappers, and tests/emu
 // runs the same bodies sequentially on the CPU.
 #pragma once
@@ -28,10 +29,10 @@
 namespace rtb {
 
 struct Counters {
-    int32_t n_extend[2], n_shadow[2];  // by iteration parity
-    int32_t n_mat[3];
+    int32_t n_extend, n_shadow;        // entries of this iteration's ray queues (holes included), set by control
+    int32_t n_mat[3];                  // hit queue sizes: pushed by extend, consumed by shade, reset by control
     int32_t extend_head, shadow_head;  // fetch cursors of the persistent kernels
-    int32_t done, n_new, _pad;
+    int32_t done, _pad[2];
     unsigned long long next_path, total_paths;
     unsigned long long stat_extend, stat_shadow, stat_paths, stat_iters, stat_hits;
     unsigned long long work[4];  // extend nodes, extend tris, shadow nodes, shadow tris (counting variants)
@@ -41,6 +42,11 @@ struct Counters {
 //   extend queue   ea = origin.xyz | pixel      eb = dir.xyz | sample<<8|bounces   ec = beta.xyz | -
 //   hit queue[t]   ma = dir.xyz    | pixel      mb = beta.xyz | sample<<8|bounces  mc = material word,u,v | leaf-order triangle
 //   shadow queue   sh_o = origin.xyz | tmax     sh_d = dir.xyz | excluded triangle sh_L = radiance | pixel
+// Hit queues are dense (extend appends to them with warp-aggregated atomics).  The two ray queues
+// are NOT compacted: the path in slot i of the concatenated hit queues writes its next ray and its
+// shadow ray to slot i of the ray queues, or a hole marker (pixel = kHolePixel / tmax = 0) when it
+// casts none; `generate` appends new camera paths behind them.  ncu r1 on the compacting version:
+// 52 % of the shade kernel's stall samples sat on the return of the two queue-append atomics.
 struct WaveState {
     F4 *ea, *eb, *ec;
     F4 *ma, *mb, *mc;  // [3][pool]
@@ -53,6 +59,7 @@ struct WaveState {
 
 constexpr int kMaxBounces = 255;       // bounces share a word with the sample index
 constexpr int kMaxSampleIndex = 1 << 24;
+constexpr uint32_t kHolePixel = 0xffffffffu;
 
 // ------------------------------------------------------------ queue pushes
 #if defined(__CUDA_ARCH__)
@@ -66,22 +73,15 @@ RTB_HD int queue_push(int32_t *counter) {
     base = __shfl_sync(m, base, leader);
     return base + __popc(m & ((1u << lane) - 1u));
 }
-// two appends at once: both atomics are in flight together (one round trip instead of two)
-RTB_HD void queue_push2(int32_t *c1, bool f1, int &i1, int32_t *c2, bool f2, int &i2) {
-    const unsigned m = __activemask();
-    const unsigned m1 = __ballot_sync(m, f1), m2 = __ballot_sync(m, f2);
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    int b1 = 0, b2 = 0;
-    if (lane == leader) {
-        if (m1) b1 = atomicAdd(c1, __popc(m1));
-        if (m2) b2 = atomicAdd(c2, __popc(m2));
+// ray statistics of a shade launch: tallied per thread over its grid-stride loop, then one
+// reduction per warp without a return value (RED: nothing waits for it)
+struct ShadeTally { uint32_t extend, shadow; };
+RTB_HD void tally_flush(Counters *c, const ShadeTally &t) {
+    const unsigned e = __reduce_add_sync(0xffffffffu, t.extend), s = __reduce_add_sync(0xffffffffu, t.shadow);
+    if ((threadIdx.x & 31) == 0) {
+        if (e) atomicAdd(&c->stat_extend, (unsigned long long)e);
+        if (s) atomicAdd(&c->stat_shadow, (unsigned long long)s);
     }
-    b1 = __shfl_sync(m, b1, leader);
-    b2 = __shfl_sync(m, b2, leader);
-    const unsigned below = (1u << lane) - 1u;
-    i1 = b1 + __popc(m1 & below);
-    i2 = b2 + __popc(m2 & below);
 }
 RTB_HD void accum_add(float *accum, uint32_t pixel, V3 L) {
     float *p = accum + 3 * (size_t)pixel;
@@ -90,10 +90,8 @@ RTB_HD void accum_add(float *accum, uint32_t pixel, V3 L) {
 RTB_HD void work_add(unsigned long long *p, unsigned v) { atomicAdd(p, (unsigned long long)v); }
 #else
 RTB_HD int queue_push(int32_t *counter) { return (*counter)++; }
-RTB_HD void queue_push2(int32_t *c1, bool f1, int &i1, int32_t *c2, bool f2, int &i2) {
-    i1 = f1 ? (*c1)++ : 0;
-    i2 = f2 ? (*c2)++ : 0;
-}
+struct ShadeTally { uint32_t extend, shadow; };
+RTB_HD void tally_flush(Counters *c, const ShadeTally &t) { c->stat_extend += t.extend; c->stat_shadow += t.shadow; }
 RTB_HD void accum_add(float *accum, uint32_t pixel, V3 L) {
     float *p = accum + 3 * (size_t)pixel;
     p[0] += L.x; p[1] += L.y; p[2] += L.z;
@@ -108,20 +106,21 @@ RTB_HD V3 xyz(F4 a) { return v3(a.x, a.y, a.z); }
 // gen, render.cuh:250-275.  Tops the extend queue up to `pool` entries with
 // new camera paths; pixel = path / spp (the samples of one pixel are
 // consecutive ids, so one warp's primary rays are coherent).
-RTB_HD int generate_count(const WaveState &W, int parity) {
+RTB_HD int hit_total(const Counters &c) { return c.n_mat[0] + c.n_mat[1] + c.n_mat[2]; }
+RTB_HD int generate_count(const WaveState &W) {
     const Counters &c = *W.c;
     const unsigned long long remaining = c.total_paths - c.next_path;
-    const unsigned long long room = (unsigned long long)(W.pool - c.n_extend[parity]);
+    const unsigned long long room = (unsigned long long)(W.pool - hit_total(c));
     return (int)(room < remaining ? room : remaining);
 }
-RTB_HD void generate_body(const WaveState &W, const RenderConsts &rc, int parity, int tid) {
+RTB_HD void generate_body(const WaveState &W, const RenderConsts &rc, int tid) {
     const Counters &c = *W.c;
     const unsigned long long path = c.next_path + (unsigned long long)tid;
     const uint32_t pixel = (uint32_t)(path / (unsigned long long)rc.spp);
     const uint32_t sample = (uint32_t)rc.first_sample + (uint32_t)(path % (unsigned long long)rc.spp);
     V3 o, d;
     generate_camera_ray(rc, pixel, sample, o, d);
-    const int q = c.n_extend[parity] + tid;  // n_extend is advanced by control
+    const int q = hit_total(c) + tid;  // behind the slots of the paths that were shaded this iteration
     W.ea[q] = f4(o, u2f(pixel));
     W.eb[q] = f4(d, u2f(sample << 8));
     W.ec[q] = f4(v3(1.f), 0.f);
@@ -148,7 +147,9 @@ RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const 
 }
 template <bool COUNT>
 RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
-    const F4 a = ldg(W.ea + qi), b = ldg(W.eb + qi);
+    const F4 a = ldg(W.ea + qi);
+    if (f2u(a.w) == kHolePixel) return;
+    const F4 b = ldg(W.eb + qi);
     HitRec h;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     bvh8_trace<false, COUNT>(S.bvh, xyz(a), xyz(b), FLT_MAX, -1, h, &tc);
@@ -159,7 +160,7 @@ RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
 // ------------------------------------------------------------ shade
 // init + mat (render.cuh:84-248) for entry `tid` of hit queue `type`
 template <int TYPE>
-RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConsts &rc, int parity, int tid) {
+RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConsts &rc, bool shadows, int tid, ShadeTally &tally) {
     const int type = TYPE;
     const int q = type * W.pool + tid;
     const F4 a = ldg(W.ma + q), b = ldg(W.mb + q), hr = ldg(W.mc + q);
@@ -175,18 +176,27 @@ RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConst
     PathStepOut out;
     path_step<TYPE>(S, rc, in, out);
     if (out.emit) accum_add(W.accum, in.pixel, out.emission);
-    int j, si;
-    queue_push2(&W.c->n_extend[parity], out.extend, j, &W.c->n_shadow[parity], out.shadow, si);
+    // slot of this path in the ray queues = its position in the concatenated hit queues
+    const Counters &c = *W.c;
+    const int j = tid + (TYPE > 0 ? c.n_mat[0] : 0) + (TYPE > 1 ? c.n_mat[1] : 0);
     if (out.extend) {
         W.ea[j] = f4(out.o, a.w);
         W.eb[j] = f4(out.d, u2f((in.sample << 8) | (uint32_t)out.bounces));
         W.ec[j] = f4(out.beta, 0.f);
+    } else {
+        W.ea[j] = f4(v3(0.f), u2f(kHolePixel));
     }
-    if (out.shadow) {
-        W.sh_o[si] = f4(out.so, out.stmax);
-        W.sh_d[si] = f4(out.sd, i2f(out.sexcl));
-        W.sh_L[si] = f4(out.sL, a.w);
+    if (shadows) {
+        if (out.shadow) {
+            W.sh_o[j] = f4(out.so, out.stmax);
+            W.sh_d[j] = f4(out.sd, i2f(out.sexcl));
+            W.sh_L[j] = f4(out.sL, a.w);
+        } else {
+            W.sh_o[j] = f4(v3(0.f), 0.f);  // tmax = 0: hole
+        }
     }
+    tally.extend += out.extend ? 1u : 0u;
+    tally.shadow += out.shadow ? 1u : 0u;
 }
 
 // ------------------------------------------------------------ shadow
@@ -199,7 +209,9 @@ RTB_HD void shadow_finish(const WaveState &W, int si, bool occluded) {
 }
 template <bool COUNT>
 RTB_HD void shadow_body(const WaveState &W, const SceneView &S, int si) {
-    const F4 o = ldg(W.sh_o + si), d = ldg(W.sh_d + si);
+    const F4 o = ldg(W.sh_o + si);
+    if (!(o.w > 0.f)) return;  // hole (a ray with tmax <= 0 can hit nothing and would splat unoccluded)
+    const F4 d = ldg(W.sh_d + si);
     HitRec h;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
     const bool occluded = bvh8_trace<true, COUNT>(S.bvh, xyz(o), xyz(d), o.w, f2i(d.w), h, &tc);
@@ -208,25 +220,22 @@ RTB_HD void shadow_body(const WaveState &W, const SceneView &S, int si) {
 }
 
 // ------------------------------------------------------------ control
-// one thread, between (shade, generate) and (extend, shadow) of iteration
-// `parity`: account the new camera paths, reset what shade consumed and the
-// other parity's counters, arm the fetch cursors, raise `done`
-RTB_HD void control_body(const WaveState &W, int parity) {
+// one thread, between (shade, generate) and the traversal kernels: size the ray queues of this
+// iteration, account the new camera paths, reset what shade consumed, arm the fetch cursors, raise `done`
+RTB_HD void control_body(const WaveState &W, bool shadows) {
     Counters &c = *W.c;
-    const int started = generate_count(W, parity);
+    const int nh = hit_total(c);
+    const int started = generate_count(W);
     c.next_path += (unsigned long long)started;
     c.stat_paths += (unsigned long long)started;
-    c.n_extend[parity] += started;
-    c.stat_hits += (unsigned long long)(c.n_mat[0] + c.n_mat[1] + c.n_mat[2]);
+    c.stat_extend += (unsigned long long)started;
+    c.stat_hits += (unsigned long long)nh;
+    c.n_extend = nh + started;
+    c.n_shadow = shadows ? nh : 0;
     c.n_mat[0] = c.n_mat[1] = c.n_mat[2] = 0;
-    c.n_extend[parity ^ 1] = 0;
-    c.n_shadow[parity ^ 1] = 0;
     c.extend_head = 0;
     c.shadow_head = 0;
-    c.stat_extend += (unsigned long long)c.n_extend[parity];
-    c.stat_shadow += (unsigned long long)c.n_shadow[parity];
-    if (c.n_extend[parity] == 0 && c.n_shadow[parity] == 0) {
-        if (!c.done) c.stat_iters += 0;
+    if (c.n_extend == 0) {
         c.done = 1;
         if (W.host_done) *W.host_done = 1;
     } else {

@@ -40,26 +40,28 @@ struct HostBackend {
     template <class F> void launch_trace(int n, F f) { launch(n, f); }
     void shade(const ShadeK &k) {
         const int n = k.W.c->n_mat[k.type];
+        ShadeTally tally; tally.extend = 0; tally.shadow = 0;
         for (int i = 0; i < n; ++i) {
-            if (k.type == 0) shade_body<0>(k.W, k.S, k.rc, k.parity, i);
-            else if (k.type == 1) shade_body<1>(k.W, k.S, k.rc, k.parity, i);
-            else shade_body<2>(k.W, k.S, k.rc, k.parity, i);
+            if (k.type == 0) shade_body<0>(k.W, k.S, k.rc, k.shadows, i, tally);
+            else if (k.type == 1) shade_body<1>(k.W, k.S, k.rc, k.shadows, i, tally);
+            else shade_body<2>(k.W, k.S, k.rc, k.shadows, i, tally);
         }
+        tally_flush(k.W.c, tally);
     }
     void generate(const GenerateK &k) {
-        const int n = generate_count(k.W, k.parity);
-        for (int i = 0; i < n; ++i) generate_body(k.W, k.rc, k.parity, i);
+        const int n = generate_count(k.W);
+        for (int i = 0; i < n; ++i) generate_body(k.W, k.rc, i);
     }
-    void control(const WaveState &W, int parity) { control_body(W, parity); }
-    bool trace_fused(const WaveState &, const SceneView &, int, int) { return false; }
-    void extend(const WaveState &W, const SceneView &S, int parity, int mode) {
-        const int n = W.c->n_extend[parity];
+    void control(const WaveState &W, bool shadows) { control_body(W, shadows); }
+    void extend(const WaveState &W, const SceneView &S, int mode) {
+        const int n = W.c->n_extend;
         for (int i = 0; i < n; ++i) { if (mode == 2) extend_body<true>(W, S, i); else extend_body<false>(W, S, i); }
     }
-    void shadow(const WaveState &W, const SceneView &S, int parity, int mode) {
-        const int n = W.c->n_shadow[parity];
+    void shadow(const WaveState &W, const SceneView &S, int mode) {
+        const int n = W.c->n_shadow;
         for (int i = 0; i < n; ++i) { if (mode == 2) shadow_body<true>(W, S, i); else shadow_body<false>(W, S, i); }
     }
+    bool trace_fused(const WaveState &, const SceneView &, int) { return false; }
     int32_t done_word_ = 0;
     int32_t *done_flag_device() { return &done_word_; }
     void reset_done() { done_word_ = 0; }

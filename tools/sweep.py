@@ -1,7 +1,7 @@
-"""Tuning sweep over the persistent-kernel knobs (RTB_REFILL / RTB_STEPS / RTB_CHUNK / RTB_POOL are read
+"""Tuning sweep over the persistent-kernel knobs (RTB_REFILL / RTB_CHUNK / RTB_POOL / RTB_POOLED / RTB_FUSED / RTB_PREFETCH / RTB_SHADE_OCC are read
 when a context is created), one process, one scene build per setting.
 
-    python tools/sweep.py --workload c2 --refill 8,16,24 --steps 1,4,8 --chunk 128 --pool 8388608
+    python tools/sweep.py --workload c2 --refill 8,16,24 --pooled 0,1 --fused 0,1 --chunk 128 --pool 8388608
 """
 import argparse
 import itertools
@@ -18,13 +18,12 @@ W = {"c1": (1, 0, 600, 600, 10, 10), "c2": (1, 0, 1920, 1080, 64, 8), "c2s": (1,
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2")
 ap.add_argument("--refill", default="24")
-ap.add_argument("--steps", default="1")
 ap.add_argument("--chunk", default="128")
 ap.add_argument("--pool", default="8388608")
-ap.add_argument("--ve", default="4")
-ap.add_argument("--vs", default="4")
+ap.add_argument("--pooled", default="1")
 ap.add_argument("--fused", default="1")
 ap.add_argument("--prefetch", default="1")
+ap.add_argument("--shade-occ", default="3")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--flags", type=int, default=0)
 a = ap.parse_args()
@@ -33,10 +32,9 @@ L = capi.Lib()
 hs = L.host_scene(kind, *L.load_mesh(), grid=grid)
 cam = hs.camera(w / h)
 print(f"workload {a.workload}: {hs.desc.num_triangles} triangles, {w}x{h}x{spp}spp depth {depth}")
-for refill, steps, chunk, pool, ve, vs, fused, pf in itertools.product(a.refill.split(","), a.steps.split(","), a.chunk.split(","), a.pool.split(","), a.ve.split(","), a.vs.split(","), a.fused.split(","), a.prefetch.split(",")):
-    if len(a.ve.split(",")) > 1 and a.ve == a.vs and ve != vs:
-        continue  # same list for both: sweep them together
-    os.environ.update(RTB_REFILL=refill, RTB_STEPS=steps, RTB_CHUNK=chunk, RTB_POOL=pool, RTB_VARIANT_E=ve, RTB_VARIANT_S=vs, RTB_FUSED=fused, RTB_PREFETCH=pf)
+for refill, chunk, pool, pooled, fused, pf, occ in itertools.product(a.refill.split(","), a.chunk.split(","), a.pool.split(","), a.pooled.split(","),
+                                                                 a.fused.split(","), a.prefetch.split(","), a.shade_occ.split(",")):
+    os.environ.update(RTB_REFILL=refill, RTB_CHUNK=chunk, RTB_POOL=pool, RTB_POOLED=pooled, RTB_FUSED=fused, RTB_PREFETCH=pf, RTB_SHADE_OCC=occ)
     ctx = L.context(0)
     sc = ctx.scene(hs.desc)
     bs = sc.stats()
@@ -47,7 +45,7 @@ for refill, steps, chunk, pool, ve, vs, fused, pf in itertools.product(a.refill.
         if best is None or st.ms_total < best.ms_total:
             best = st
     rays = best.extend_rays + best.shadow_rays
-    print(f"ve {ve} vs {vs} fused {best.fused_trace} pf {pf} refill {refill:>2} steps {steps:>2} chunk {chunk:>4} pool {pool:>9}: {best.ms_total:8.2f} ms  extend {best.ms_extend:7.2f} "
+    print(f"pooled {pooled} fused {best.fused_trace} pf {pf} occ {occ} refill {refill:>2} chunk {chunk:>4} pool {pool:>9}: {best.ms_total:8.2f} ms  trace/extend {best.ms_extend:7.2f} "
           f"shadow {best.ms_shadow:7.2f} shade {best.ms_shade:6.2f} other {best.ms_other:6.2f}  {rays / best.ms_total * 1e-3:8.1f} Mrays/s  "
           f"iters {best.iterations}  build {bs.build_ms:.1f} ms nodes {bs.num_nodes} sah {bs.sah_cost:.2f} mean {img.mean():.4f}", flush=True)
     sc.close()
