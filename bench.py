@@ -316,7 +316,15 @@ def main():
         # ---- roofline of the dominant kernel, measured live ----
         # k_trace<3>: the extend AND shadow rays of one iteration in one persistent launch (stats.fused_trace);
         # its duration is ms_extend (CUDA events on the render stream inside rtb_render_accumulate).
-        s0 = stats
+        # The timed steps run two concurrent wavefronts (streams), whose kernels overlap; the per-kernel durations
+        # come from extra steps with RTB_RENDER_SINGLE_PIPELINE (one stream, the kernel timed alone).
+        ps = capi.render_params(L, width=W, height=H, spp=spp, max_bounces=depth, first_sample=rank * spp,
+                                total_spp=total_spp, pool_size=args.pool, flags=args.flags | capi.RTB_RENDER_SINGLE_PIPELINE)
+        s0 = []
+        for _ in range(max(1, min(args.steps, 3))):
+            flush.zero_()
+            accum.zero_()
+            s0.append(scene.render_accumulate(cam, ps, accum.data_ptr()))
         fused = all(s.fused_trace for s in s0)
         tr_ms = sum(s.ms_extend + s.ms_shadow for s in s0); sh_ms = sum(s.ms_shade for s in s0); tot_ms = sum(s.ms_total for s in s0)
         tr_launches = sum(s.extend_launches for s in s0)
@@ -349,7 +357,8 @@ def main():
                     "algorithmic_bytes_per_extend_ray": bytes_extend, "algorithmic_bytes_per_shadow_ray": bytes_shadow,
                     "extend_nodes_per_ray": e_nodes, "extend_tris_per_ray": e_tris, "shadow_nodes_per_ray": s_nodes,
                     "shadow_tris_per_ray": s_tris, "hit_fraction": hit_frac,
-                    "avg_launch_ms": avg_launch_ms, "launches": int(tr_launches),
+                    "avg_launch_ms": avg_launch_ms, "launches": int(tr_launches), "timed_with": "single pipeline (kernel alone on one stream), %d steps" % len(s0),
+                    "single_pipeline_ms_per_step": tot_ms / len(s0),
                     "kernel_share_of_step": tr_ms / tot_ms if tot_ms else None,
                     "shade_share_of_step": sh_ms / tot_ms if tot_ms else None,
                     "note": "scene (%.1f MB nodes+triangles) %s; node/triangle counts from the counting kernel variant"
@@ -365,7 +374,7 @@ def main():
                            "l2": "256 MB device memset between timed steps (L2 flush); ray queues (2 GB) are streamed every iteration"},
                 "ms_per_spp": ms_per_step / total_spp * world, "paths_per_step": int(stats[0].paths) * world,
                 "rays_per_step": rays_total.item() / args.steps,
-                "iterations_per_step": int(stats[0].iterations), "bvh_build_ms": bst.build_ms, "bvh_nodes": int(bst.num_nodes),
+                "iterations_per_step": int(stats[0].iterations), "pipelines": int(stats[0].pipelines), "bvh_build_ms": bst.build_ms, "bvh_nodes": int(bst.num_nodes),
                 "bvh_sah": bst.sah_cost,
                 "e2e": {"value": e2e_r.item() / e2e_t.item() * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(nfl * 4), "steps": n_e2e, "ms_per_step": e2e_t.item() / n_e2e * 1e3,

@@ -143,7 +143,8 @@ enum {
     RTB_RENDER_PIXEL_CENTRE = 1, /* no sub-pixel jitter: camera rays through pixel centres */
     RTB_RENDER_NO_SHADOW = 2,    /* skip next-event estimation (debug) */
     RTB_RENDER_NONPERSISTENT = 4, /* one-thread-per-ray traversal launch (A/B for the persistent kernel) */
-    RTB_RENDER_COUNT_WORK = 8     /* counting kernel variants: fill the *_nodes / *_tris statistics (slower) */
+    RTB_RENDER_COUNT_WORK = 8,    /* counting kernel variants: fill the *_nodes / *_tris statistics (slower) */
+    RTB_RENDER_SINGLE_PIPELINE = 16 /* one wavefront on one stream (per-stage timing; default is two concurrent ones) */
 };
 
 typedef struct rtb_render_stats {
@@ -163,6 +164,9 @@ typedef struct rtb_render_stats {
     float ms_shade;        /* summed duration of shade + generate + control (part of ms_other) */
     int32_t fused_trace;   /* 1: extend and shadow rays ran in ONE launch per iteration; then ms_extend
                               is the duration of that launch and ms_shadow is 0 */
+    int32_t pipelines;     /* independent wavefronts run on concurrent streams (1 or 2); the per-stage
+                              times above are only measured with 1 (RTB_RENDER_SINGLE_PIPELINE) */
+    int32_t _pad;
 } rtb_render_stats;
 
 typedef struct rtb_context rtb_context; /* one per GPU */

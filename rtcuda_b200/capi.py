@@ -16,6 +16,7 @@ BUNNY_BIN = os.path.join(HERE, "data", "bunny.rtbm")
 
 RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2 = 1, 2, 3
 RTB_RENDER_PIXEL_CENTRE, RTB_RENDER_NO_SHADOW, RTB_RENDER_NONPERSISTENT, RTB_RENDER_COUNT_WORK = 1, 2, 4, 8
+RTB_RENDER_SINGLE_PIPELINE = 16
 
 
 class Material(C.Structure):
@@ -63,7 +64,7 @@ class RenderStats(C.Structure):
                 ("extend_nodes", C.c_uint64), ("extend_tris", C.c_uint64), ("shadow_nodes", C.c_uint64),
                 ("shadow_tris", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64), ("hits", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_extend", C.c_float), ("ms_shadow", C.c_float), ("ms_other", C.c_float),
-                ("ms_shade", C.c_float), ("fused_trace", C.c_int32)]
+                ("ms_shade", C.c_float), ("fused_trace", C.c_int32), ("pipelines", C.c_int32), ("_pad", C.c_int32)]
 
 
 RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("dir", np.float32, 3), ("tmax", np.float32)])

@@ -241,6 +241,9 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
 // extend and shadow rays of one iteration in ONE launch (WHICH = 3): a warp that runs out of extend
 // rays goes on with shadow rays, so the tail of the first queue overlaps the start of the second.
 // WHICH = 1 / 2: extend / shadow only (A/B, and per-stage timing).
+// POOL is chosen by scene size (CudaBackend::use_pooled): pooled triangle tests win when triangle fetches
+// miss L2 (10 M triangles: 116 vs 123 ms), each lane on its own wins when everything hits in cache (C2: 46.2 vs 47.9 ms).
+// Tried and dropped: prefetching the next node into L2 during the triangle tests (C3 116 -> 140 ms, C2 40 -> 49 ms).
 template <int WHICH, bool POOL>
 __global__ void __launch_bounds__(kBlock, 4) k_trace(WaveState W, SceneView S, FetchTuning tune) {
     __shared__ WarpScratch scratch[kBlock / 32];
@@ -248,6 +251,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_trace(WaveState W, SceneView S, F
     if (WHICH & 1) persistent_trace<false, POOL>(ws, W, S, tune);
     if (WHICH == 3) __syncwarp();
     if (WHICH & 2) persistent_trace<true, POOL>(ws, W, S, tune);
+}
+template <int WHICH>
+static void launch_trace_kernel(int grid, cudaStream_t st, bool pooled, const WaveState &W, const SceneView &S, const FetchTuning &tune) {
+    if (pooled) k_trace<WHICH, true><<<grid, kBlock, 0, st>>>(W, S, tune);
+    else k_trace<WHICH, false><<<grid, kBlock, 0, st>>>(W, S, tune);
 }
 // one thread per queue entry (A/B against the persistent kernels; COUNT = work counters)
 template <bool COUNT>
@@ -268,16 +276,19 @@ struct NonNegative {
 struct CudaBackend {
     int dev_ = -1;
     int num_sms_ = 0;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr;  // the stream launches go to: streams_[0] unless use_stream(k) says otherwise
+    cudaStream_t streams_[kMaxPipelines] = {nullptr, nullptr};
+    cudaEvent_t sync_ev_ = nullptr;
+    int pipelines_ = 2;  // RTB_PIPELINES: concurrent wavefronts per render (1 or 2)
     int blocks_trace_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_shade4_[3] = {0, 0, 0}, blocks_generate_ = 0, shade_occ_ = 3;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
     int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
     FetchTuning tune_{24, 128, 1};  // RTB_REFILL / RTB_CHUNK / RTB_PREFETCH override (tuning runs)
-    int pooled_ = 1;  // RTB_POOLED: pooled triangle tests (1) or each ray's lane on its own (0)
+    int pooled_ = -1;  // RTB_POOLED: pooled triangle tests (1), each ray's lane on its own (0), by scene size (-1)
     int fused_ = 1;   // RTB_FUSED: extend + shadow rays of one iteration in one launch
-    int pool_ = 1 << 23;    // default path pool, RTB_POOL overrides (tuning)
+    int pool_ = 1 << 26;    // default path pool, RTB_POOL overrides (tuning)
 
     explicit CudaBackend(int device) {
         int count = 0;
@@ -294,16 +305,19 @@ struct CudaBackend {
         dev_ = device;
         num_sms_ = prop.multiProcessorCount;
         RTB_CUDA_CHECK(cudaSetDevice(dev_));
-        RTB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamDefault));
+        for (int k = 0; k < kMaxPipelines; ++k) RTB_CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[k], cudaStreamDefault));
+        stream_ = streams_[0];
+        RTB_CUDA_CHECK(cudaEventCreateWithFlags(&sync_ev_, cudaEventDisableTiming));
         // stream-ordered allocator that keeps freed blocks: scene builds and renders reuse memory
         // instead of paying cudaMalloc/cudaFree (each an implicit device synchronisation) every call
         cudaMemPool_t mp;
         RTB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&mp, dev_));
         unsigned long long keep = ~0ull;
         RTB_CUDA_CHECK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
-        RTB_CUDA_CHECK(cudaHostAlloc((void **)&h_done_, sizeof(int32_t), cudaHostAllocMapped));
+        RTB_CUDA_CHECK(cudaHostAlloc((void **)&h_done_, kMaxPipelines * sizeof(int32_t), cudaHostAllocMapped));
         RTB_CUDA_CHECK(cudaHostGetDevicePointer((void **)&d_done_, h_done_, 0));
-        *h_done_ = 0;
+        for (int k = 0; k < kMaxPipelines; ++k) h_done_[k] = 0;
+        if (const char *e = getenv("RTB_PIPELINES")) { int v = atoi(e); if (v >= 1 && v <= kMaxPipelines) pipelines_ = v; }
         if (const char *e = getenv("RTB_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tune_.refill = v; }
         if (const char *e = getenv("RTB_CHUNK")) { int v = atoi(e); if (v >= 32) tune_.chunk = v; }
         if (const char *e = getenv("RTB_PREFETCH")) tune_.prefetch = atoi(e);
@@ -332,11 +346,13 @@ struct CudaBackend {
     ~CudaBackend() {
         if (dev_ < 0) return;
         cudaSetDevice(dev_);
-        if (stream_) cudaStreamSynchronize(stream_);
+        stream_ = streams_[0];
+        for (int k = 0; k < kMaxPipelines; ++k) if (streams_[k]) cudaStreamSynchronize(streams_[k]);
         if (cub_temp_) cudaFreeAsync(cub_temp_, stream_);
         if (d_count_) cudaFreeAsync(d_count_, stream_);
         if (h_done_) cudaFreeHost(h_done_);
-        if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
+        if (sync_ev_) cudaEventDestroy(sync_ev_);
+        for (int k = 0; k < kMaxPipelines; ++k) if (streams_[k]) { cudaStreamSynchronize(streams_[k]); cudaStreamDestroy(streams_[k]); }
     }
     CudaBackend(const CudaBackend &) = delete;
     CudaBackend &operator=(const CudaBackend &) = delete;
@@ -395,33 +411,45 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     // mode 0: persistent, 1: one thread per ray, 2: one thread per ray + work counters
+    bool big_scene(const SceneView &S) const {  // nodes + triangles beyond what stays resident in the 126 MB L2
+        return (size_t)S.bvh.num_nodes * 80 + (size_t)S.bvh.num_tris * 48 > ((size_t)48 << 20);
+    }
+    bool use_pooled(const SceneView &S) const { return pooled_ < 0 ? big_scene(S) : pooled_ != 0; }
     void extend(const WaveState &W, const SceneView &S, int mode) {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
         else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else if (pooled_) k_trace<1, true><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
-        else k_trace<1, false><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
+        else launch_trace_kernel<1>(blocks_trace_, stream_, use_pooled(S), W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shadow(const WaveState &W, const SceneView &S, int mode) {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
         else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else if (pooled_) k_trace<2, true><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
-        else k_trace<2, false><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
+        else launch_trace_kernel<2>(blocks_trace_, stream_, use_pooled(S), W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     // both ray types in one launch; false = not available in this mode
     bool trace_fused(const WaveState &W, const SceneView &S, int mode) {
         if (mode != 0 || !fused_) return false;
-        if (pooled_) k_trace<3, true><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
-        else k_trace<3, false><<<blocks_trace_, kBlock, 0, stream_>>>(W, S, tune_);
+        launch_trace_kernel<3>(blocks_trace_, stream_, use_pooled(S), W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
         return true;
     }
-    int32_t *done_flag_device() { return d_done_; }
-    void reset_done() { *(volatile int32_t *)h_done_ = 0; }
-    bool done() const { return *(volatile int32_t *)h_done_ != 0; }
+    // ---- concurrent wavefronts (rtb_engine.h, render_accumulate) ----
+    int pipelines() const { return pipelines_; }
+    void use_stream(int k) { stream_ = streams_[k]; }
+    void fork(int k) {  // stream k continues after what is queued on the main stream
+        RTB_CUDA_CHECK(cudaEventRecord(sync_ev_, streams_[0]));
+        RTB_CUDA_CHECK(cudaStreamWaitEvent(streams_[k], sync_ev_, 0));
+    }
+    void join(int k) {  // the main stream continues after what is queued on stream k
+        RTB_CUDA_CHECK(cudaEventRecord(sync_ev_, streams_[k]));
+        RTB_CUDA_CHECK(cudaStreamWaitEvent(streams_[0], sync_ev_, 0));
+    }
+    int32_t *done_flag_device(int k) { return d_done_ + k; }
+    void reset_done(int k) { ((volatile int32_t *)h_done_)[k] = 0; }
+    bool done(int k) const { return ((volatile int32_t *)h_done_)[k] != 0; }
     void wait(cudaEvent_t e) { RTB_CUDA_CHECK(cudaEventSynchronize(e)); }
 
     void ensure_temp(size_t bytes) {

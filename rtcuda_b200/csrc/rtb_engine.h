@@ -101,6 +101,7 @@ struct TraceAnyK {
 };
 
 // ---- scene ----
+constexpr int kMaxPipelines = 2;
 template <class BE>
 struct SceneT {
     BE *be = nullptr;
@@ -116,8 +117,8 @@ struct SceneT {
     rtb_bvh_stats stats{};
     // render state kept between calls (the reference re-allocates ~293 MB per
     // render() and never frees it, render.cuh:374-391)
-    WaveState W{};
-    int32_t pool = 0;
+    WaveState W[kMaxPipelines]{};
+    int32_t pool = 0, pipes = 0;  // pool = queue entries PER pipeline
     float *own_accum = nullptr; int64_t own_accum_floats = 0;
 
     SceneView view() const {
@@ -129,20 +130,25 @@ struct SceneT {
         return S;
     }
     void free_wave() {
-        if (!pool) return;
-        be->free(W.ea); be->free(W.eb); be->free(W.ec); be->free(W.ma); be->free(W.mb); be->free(W.mc);
-        be->free(W.sh_o); be->free(W.sh_d); be->free(W.sh_L); be->free(W.c);
-        pool = 0;
+        for (int k = 0; k < pipes; ++k) {
+            WaveState &w = W[k];
+            be->free(w.ea); be->free(w.eb); be->free(w.ec); be->free(w.ma); be->free(w.mb); be->free(w.mc);
+            be->free(w.sh_o); be->free(w.sh_d); be->free(w.sh_L); be->free(w.c);
+        }
+        pool = 0; pipes = 0;
     }
-    void ensure_wave(int32_t p) {
-        if (pool == p) return;
+    void ensure_wave(int32_t p, int np) {
+        if (pool == p && pipes == np) return;
         free_wave();
-        W.ea = be->template alloc<F4>(p); W.eb = be->template alloc<F4>(p); W.ec = be->template alloc<F4>(p);
-        W.ma = be->template alloc<F4>(3 * (size_t)p); W.mb = be->template alloc<F4>(3 * (size_t)p); W.mc = be->template alloc<F4>(3 * (size_t)p);
-        W.sh_o = be->template alloc<F4>(p); W.sh_d = be->template alloc<F4>(p); W.sh_L = be->template alloc<F4>(p);
-        W.c = be->template alloc<Counters>(1);
-        W.pool = p;
-        pool = p;
+        for (int k = 0; k < np; ++k) {
+            WaveState &w = W[k];
+            w.ea = be->template alloc<F4>(p); w.eb = be->template alloc<F4>(p); w.ec = be->template alloc<F4>(p);
+            w.ma = be->template alloc<F4>(3 * (size_t)p); w.mb = be->template alloc<F4>(3 * (size_t)p); w.mc = be->template alloc<F4>(3 * (size_t)p);
+            w.sh_o = be->template alloc<F4>(p); w.sh_d = be->template alloc<F4>(p); w.sh_L = be->template alloc<F4>(p);
+            w.c = be->template alloc<Counters>(1);
+            w.pool = p;
+        }
+        pool = p; pipes = np;
     }
     ~SceneT() {
         if (!be) return;
@@ -394,9 +400,17 @@ SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const 
 
 // ---- wavefront loop ----
 // One iteration = shade (one launch per material type present) -> generate ->
-// control -> extend -> shadow, all on one stream.  The host never waits for an
-// iteration: it keeps two batches of launches in flight and watches a `done`
-// word that the control kernel raises in mapped host memory.
+// control -> trace (extend + shadow rays), in stream order.  The host never
+// waits for an iteration: it keeps two batches of launches in flight and
+// watches a `done` word that the control kernel raises in mapped host memory.
+//
+// Two pipelines.  A trace launch ends with a tail: its last rays are latency
+// bound and leave most SMs idle (10 M-triangle scene, 8 Mi-ray iterations: ~1.8 ms
+// of every ~4 ms iteration, profiles/r1_pool_sweep.md).  So the render is split
+// into two independent wavefronts — the even and the odd paths, each with its
+// own queues and counters, half the pool each — on two streams: while one is in
+// the tail of its trace kernel, the blocks of the other one's kernels fill the
+// SMs that fall idle.  They only meet in the accumulation buffer (atomic adds).
 template <class BE>
 void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_render_params &p, float *d_accum,
                        rtb_render_stats *stats) {
@@ -406,65 +420,84 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     if (p.first_sample < 0 || (long long)p.first_sample + p.spp > kMaxSampleIndex) throw Error(RTB_ERR_INVALID, "rtb_render: sample index >= 2^24");
     const unsigned long long total = (unsigned long long)p.width * (unsigned long long)p.height * (unsigned long long)p.spp;
     if ((unsigned long long)p.width * (unsigned long long)p.height > 0x7fffffffull) throw Error(RTB_ERR_INVALID, "image too large");
-    int pool = p.pool_size > 0 ? p.pool_size : be.default_pool();
-    if ((unsigned long long)pool > total) pool = (int)total;
-    pool = (pool + 31) & ~31;
-    sc.ensure_wave(pool);
-    WaveState W = sc.W;
-    W.accum = d_accum;
-    W.host_done = be.done_flag_device();
+    const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
+    long long pool_all = p.pool_size > 0 ? p.pool_size : be.default_pool();
+    if ((unsigned long long)pool_all > total) pool_all = (long long)total;
+    int np = be.pipelines();
+    if (np > kMaxPipelines) np = kMaxPipelines;
+    if (np < 1 || mode != 0 || (p.flags & RTB_RENDER_SINGLE_PIPELINE) || pool_all < (1 << 16)) np = 1;
+    const int pool = (int)(((pool_all + np - 1) / np + 31) & ~31ll);
+    sc.ensure_wave(pool, np);
     const SceneView S = sc.view();
-    RenderConsts rc;
-    rc.cam = cam; rc.width = p.width; rc.height = p.height; rc.spp = p.spp; rc.first_sample = p.first_sample;
-    rc.max_bounces = p.max_bounces; rc.rr_start = p.rr_start; rc.rr_threshold = p.rr_threshold; rc.seed = p.seed; rc.flags = p.flags;
-    Counters c0;
-    memset(&c0, 0, sizeof c0);
-    c0.total_paths = total;
-    be.reset_done();
+    const bool shadows = sc.num_lights > 0 && !(p.flags & RTB_RENDER_NO_SHADOW);
+    WaveState W[kMaxPipelines];
+    RenderConsts rc[kMaxPipelines];
     auto t0 = be.now();
-    be.upload(W.c, &c0, 1);
+    for (int k = 0; k < np; ++k) {
+        W[k] = sc.W[k];
+        W[k].accum = d_accum;
+        W[k].host_done = be.done_flag_device(k);
+        RenderConsts &r = rc[k];
+        r.cam = cam; r.width = p.width; r.height = p.height; r.spp = p.spp; r.first_sample = p.first_sample;
+        r.max_bounces = p.max_bounces; r.rr_start = p.rr_start; r.rr_threshold = p.rr_threshold; r.seed = p.seed; r.flags = p.flags;
+        r.path_offset = k; r.path_stride = np;
+        Counters c0;
+        memset(&c0, 0, sizeof c0);
+        c0.total_paths = (total - (unsigned long long)k + (unsigned long long)np - 1ull) / (unsigned long long)np;
+        be.reset_done(k);
+        be.upload(W[k].c, &c0, 1);
+    }
+    for (int k = 1; k < np; ++k) be.fork(k);  // stream k starts after everything queued so far on the main stream
     unsigned long long launches = 0;
     const int batch = 4;
-    const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
-    const bool time_stages = stats != nullptr;
-    const bool shadows = sc.num_lights > 0 && !(p.flags & RTB_RENDER_NO_SHADOW);
+    const bool time_stages = stats != nullptr && np == 1;
     // per iteration: [0] before shade, [1] before the traversal kernels, [2] after extend (or after the
     // fused extend+shadow launch), [3] after shadow
-    std::vector<typename BE::Time> stage_times, fences;
-    size_t fence_head = 0;
-    int it = 0;
+    std::vector<typename BE::Time> stage_times, fences[kMaxPipelines];
+    size_t fence_head[kMaxPipelines] = {0, 0};
+    bool finished[kMaxPipelines] = {false, false};
     bool fused = false;
-    while (true) {
-        for (int k = 0; k < batch; ++k, ++it) {
-            if (time_stages) stage_times.push_back(be.now());
-            for (int type = 0; type < 3; ++type) {
-                if (!(sc.type_mask >> type & 1u)) continue;
-                ShadeK ks; ks.W = W; ks.S = S; ks.rc = rc; ks.type = type; ks.shadows = shadows;
-                be.shade(ks);
-                ++launches;
-            }
-            { GenerateK kg; kg.W = W; kg.rc = rc; be.generate(kg); }
-            be.control(W, shadows);
-            if (time_stages) stage_times.push_back(be.now());
-            if (be.trace_fused(W, S, mode)) {
-                fused = true;
-                if (time_stages) { stage_times.push_back(be.now()); stage_times.push_back(be.now()); }
-                launches += 3;
-            } else {
-                be.extend(W, S, mode);
+    int live = np;
+    while (live > 0) {
+        for (int k = 0; k < np; ++k) {
+            if (finished[k]) continue;
+            be.use_stream(k);
+            for (int b = 0; b < batch; ++b) {
                 if (time_stages) stage_times.push_back(be.now());
-                be.shadow(W, S, mode);
+                for (int type = 0; type < 3; ++type) {
+                    if (!(sc.type_mask >> type & 1u)) continue;
+                    ShadeK ks; ks.W = W[k]; ks.S = S; ks.rc = rc[k]; ks.type = type; ks.shadows = shadows;
+                    be.shade(ks);
+                    ++launches;
+                }
+                { GenerateK kg; kg.W = W[k]; kg.rc = rc[k]; be.generate(kg); }
+                be.control(W[k], shadows);
                 if (time_stages) stage_times.push_back(be.now());
-                launches += 4;
+                if (be.trace_fused(W[k], S, mode)) {
+                    fused = true;
+                    if (time_stages) { stage_times.push_back(be.now()); stage_times.push_back(be.now()); }
+                    launches += 3;
+                } else {
+                    be.extend(W[k], S, mode);
+                    if (time_stages) stage_times.push_back(be.now());
+                    be.shadow(W[k], S, mode);
+                    if (time_stages) stage_times.push_back(be.now());
+                    launches += 4;
+                }
             }
+            fences[k].push_back(be.now());
         }
-        fences.push_back(be.now());
-        if (fences.size() - fence_head > 2) be.wait(fences[fence_head++]);
-        if (be.done()) break;
+        for (int k = 0; k < np; ++k) {
+            if (finished[k]) continue;
+            if (fences[k].size() - fence_head[k] > 2) be.wait(fences[k][fence_head[k]++]);
+            if (be.done(k)) { finished[k] = true; --live; }
+        }
     }
+    be.use_stream(0);
+    for (int k = 1; k < np; ++k) be.join(k);  // the main stream continues after stream k's work
     auto t1 = be.now();
     be.wait(t1);
-    for (auto &e : fences) be.release(e);
+    for (int k = 0; k < np; ++k) for (auto &e : fences[k]) be.release(e);
     float ms_extend = 0.f, ms_shadow = 0.f, ms_shade = 0.f;
     for (size_t i = 0; i + 3 < stage_times.size(); i += 4) {
         ms_shade += be.elapsed_keep(stage_times[i], stage_times[i + 1]);
@@ -474,23 +507,26 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     for (auto &e : stage_times) be.release(e);
     const float ms_total = be.elapsed_ms(t0, t1);
     if (stats) {
-        Counters c;
-        be.download(&c, W.c, 1);
         memset(stats, 0, sizeof *stats);
-        stats->paths = c.stat_paths;
-        stats->extend_rays = c.stat_extend;
-        stats->shadow_rays = c.stat_shadow;
-        stats->iterations = c.stat_iters;
+        for (int k = 0; k < np; ++k) {
+            Counters c;
+            be.download(&c, W[k].c, 1);
+            stats->paths += c.stat_paths;
+            stats->extend_rays += c.stat_extend;
+            stats->shadow_rays += c.stat_shadow;
+            stats->iterations += c.stat_iters;
+            stats->extend_nodes += c.work[0]; stats->extend_tris += c.work[1];
+            stats->shadow_nodes += c.work[2]; stats->shadow_tris += c.work[3];
+            stats->hits += c.stat_hits;
+        }
         stats->kernel_launches = launches;
-        stats->extend_nodes = c.work[0]; stats->extend_tris = c.work[1];
-        stats->shadow_nodes = c.work[2]; stats->shadow_tris = c.work[3];
-        stats->extend_launches = c.stat_iters; stats->shadow_launches = c.stat_iters;
-        stats->hits = c.stat_hits;
+        stats->extend_launches = stats->iterations; stats->shadow_launches = stats->iterations;
         stats->ms_extend = ms_extend; stats->ms_shadow = ms_shadow;
         stats->ms_total = ms_total;
         stats->ms_other = ms_total - ms_extend - ms_shadow;
         stats->ms_shade = ms_shade;
         stats->fused_trace = fused ? 1 : 0;
+        stats->pipelines = np;
     }
 }
 

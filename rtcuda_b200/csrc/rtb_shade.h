@@ -48,6 +48,7 @@ struct RenderConsts {
     float rr_threshold;
     uint32_t seed;
     int32_t flags;
+    int32_t path_offset, path_stride;  // this wavefront renders paths offset, offset + stride, ...
 };
 
 // ------------------------------------------------------------------ camera

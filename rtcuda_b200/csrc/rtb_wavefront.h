@@ -115,7 +115,7 @@ RTB_HD int generate_count(const WaveState &W) {
 }
 RTB_HD void generate_body(const WaveState &W, const RenderConsts &rc, int tid) {
     const Counters &c = *W.c;
-    const unsigned long long path = c.next_path + (unsigned long long)tid;
+    const unsigned long long path = (unsigned long long)rc.path_offset + (c.next_path + (unsigned long long)tid) * (unsigned long long)rc.path_stride;
     const uint32_t pixel = (uint32_t)(path / (unsigned long long)rc.spp);
     const uint32_t sample = (uint32_t)rc.first_sample + (uint32_t)(path % (unsigned long long)rc.spp);
     V3 o, d;

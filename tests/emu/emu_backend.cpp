@@ -63,9 +63,13 @@ struct HostBackend {
     }
     bool trace_fused(const WaveState &, const SceneView &, int) { return false; }
     int32_t done_word_ = 0;
-    int32_t *done_flag_device() { return &done_word_; }
-    void reset_done() { done_word_ = 0; }
-    bool done() const { return done_word_ != 0; }
+    int pipelines() const { return 1; }
+    void use_stream(int) {}
+    void fork(int) {}
+    void join(int) {}
+    int32_t *done_flag_device(int) { return &done_word_; }
+    void reset_done(int) { done_word_ = 0; }
+    bool done(int) const { return done_word_ != 0; }
     void sort_pairs(uint64_t *keys, int32_t *vals, int n) {
         std::vector<int> idx(n);
         std::iota(idx.begin(), idx.end(), 0);
