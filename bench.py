@@ -348,7 +348,9 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("k_trace_dram_bytes_per_launch")
+                per_ray = json.load(f).get(args.workload, {}).get("k_trace_dram_bytes_per_ray")
+                if per_ray is not None:  # ncu DRAM bytes per ray of this kernel x the rays one launch of this run processes
+                    traffic = per_ray * (ext_rays + shd_rays) / max(tr_launches, 1)
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "k_trace<3> (extend + shadow rays, one persistent launch per iteration)" if fused else "k_trace<1> + k_trace<2>",
@@ -365,13 +367,15 @@ def main():
                             % ((bst.node_bytes + bst.triangle_bytes) / 1e6,
                                "is L2-resident: the kernel is bound by instruction issue, not by HBM (see profiles/)" if bst.node_bytes + bst.triangle_bytes < 100e6
                                else "exceeds L2")}
+        pool_used = min(int(p.pool_size) or int(os.environ.get("RTB_POOL", 1 << 26)), int(stats[0].paths))
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": desc_txt, "spp_per_gpu": spp, "total_spp": total_spp,
                            "sharding": "sample pass per rank, scene replicated, NCCL all-reduce of the accumulation buffer" if world > 1 else "single GPU",
-                           "pool_size": int(p.pool_size) or int(os.environ.get("RTB_POOL", 1 << 23)),
-                           "l2": "256 MB device memset between timed steps (L2 flush); ray queues (2 GB) are streamed every iteration"},
+                           "pool_size": pool_used,
+                           "l2": "256 MB device memset between timed steps (L2 flush); the ray / hit queues (%.1f GB) are streamed every iteration"
+                                 % (pool_used * 240 / 1e9)},
                 "ms_per_spp": ms_per_step / total_spp * world, "paths_per_step": int(stats[0].paths) * world,
                 "rays_per_step": rays_total.item() / args.steps,
                 "iterations_per_step": int(stats[0].iterations), "pipelines": int(stats[0].pipelines), "bvh_build_ms": bst.build_ms, "bvh_nodes": int(bst.num_nodes),

@@ -229,6 +229,32 @@ def test_pool_size_does_not_change_the_image(L, s1, s1_dev):
     assert mean_rel_err(a, b) <= 1e-5
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [
+    {"RTB_POOLED": "0", "RTB_PIPELINES": "1", "RTB_FUSED": "0"},  # each lane tests its own triangles, extend and shadow launches apart
+    {"RTB_POOLED": "1", "RTB_PIPELINES": "1", "RTB_FUSED": "1"},  # pooled triangle tests (shared memory), one trace launch
+    {"RTB_POOLED": "1", "RTB_PIPELINES": "2", "RTB_FUSED": "1", "RTB_CHUNK": "32", "RTB_REFILL": "32"},
+    {"RTB_POOLED": "0", "RTB_PIPELINES": "2", "RTB_FUSED": "1", "RTB_PREFETCH": "0", "RTB_REFILL": "1"},
+])
+def test_every_traversal_kernel_variant_matches_the_oracle(gpu, oracle, bunny, monkeypatch, env):
+    """the tuning knobs CudaBackend reads when a context is created select different kernels / schedules;
+    all of them must give the oracle's image and ray counts (hits are bit-exact, so the counts are equal
+    up to the ulp-level differences of the shading arithmetic)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    hs = gpu.host_scene(capi.RTB_SCENE_S1, *bunny)
+    ctx2 = gpu.context(0)
+    sc = ctx2.scene(hs.desc)
+    cam = hs.camera(1.0)
+    img, st, ref, ost = render_pair(gpu, sc, oracle.scene(hs.desc), cam, width=320, height=320, spp=4, max_bounces=10)
+    assert st.pipelines == int(env["RTB_PIPELINES"]) and st.fused_trace == int(env["RTB_FUSED"])
+    assert st.paths == ost[0]
+    assert abs(int(st.extend_rays) - int(ost[1])) <= 2e-3 * ost[1]
+    assert abs(int(st.shadow_rays) - int(ost[2])) <= 2e-3 * ost[2]
+    assert mean_rel_err(img, ref) <= IMAGE_TOL
+    sc.close()
+
+
 def test_bad_arguments_return_status_codes(L, ctx, s1_dev):
     lib = L.lib
     assert lib.rtb_scene_create(ctx.h, None, None, None) == -1

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rtcuda_b200 import capi  # noqa: E402
 
-W = {"c1": (1, 0, 600, 600, 10, 10), "c2": (1, 0, 1920, 1080, 64, 8), "c2s": (1, 0, 1920, 1080, 4, 8),
+W = {"c1": (1, 0, 600, 600, 10, 10), "c2": (1, 0, 1920, 1080, 64, 8), "c2s": (1, 0, 1920, 1080, 4, 8), "c2m": (1, 0, 1920, 1080, 16, 8),
      "c3s": (3, 12, 3840, 2160, 1, 8), "c4s": (2, 0, 1920, 1080, 4, 16)}
 
 ap = argparse.ArgumentParser()
@@ -34,6 +34,6 @@ p = capi.render_params(L, width=w, height=h, spp=spp, max_bounces=depth, flags=a
 for r in range(a.reps):
     img, st = sc.render(cam, p)
     rays = st.extend_rays + st.shadow_rays
-    print(f"rep {r}: {st.ms_total:.2f} ms total, extend {st.ms_extend:.2f} ms ({st.extend_rays} rays), shadow {st.ms_shadow:.2f} ms "
-          f"({st.shadow_rays} rays), other {st.ms_other:.2f} ms, {st.iterations} iterations, {st.kernel_launches} launches, "
+    print(f"rep {r}: {st.ms_total:.2f} ms total, {st.pipelines} pipeline(s), trace {st.ms_extend + st.ms_shadow:.2f} ms ({st.extend_rays} extend + "
+          f"{st.shadow_rays} shadow rays), shade+generate+control {st.ms_shade:.2f} ms, {st.iterations} iterations, {st.kernel_launches} launches, "
           f"{rays / st.ms_total * 1e-3:.1f} Mrays/s, mean {img.mean():.4f}")
