@@ -242,11 +242,18 @@ def main():
     out = torch.empty_like(accum)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    def step():
+    seg_events = []  # (after render, after all-reduce) of the timed steps: where a multi-GPU step spends its time
+
+    def step(timed=False):
         accum.zero_()
         st = scene.render_accumulate(cam, p, accum.data_ptr())
+        if timed and world > 1:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record()
         if world > 1:
             dist.all_reduce(accum)
+        if timed and world > 1:
+            e2 = torch.cuda.Event(enable_timing=True); e2.record()
+            seg_events.append((e1, e2))
         ctx.tonemap_device(accum.data_ptr(), nfl, total_spp, out.data_ptr())
         return st
 
@@ -268,11 +275,19 @@ def main():
         flush.zero_()  # evict L2 between timed steps
         torch.cuda.synchronize()
         ev[k][0].record()
-        stats.append(step())
+        stats.append(step(timed=True))
         ev[k][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_steps = [a.elapsed_time(b) for a, b in ev]
+    allreduce_ms = sum(a.elapsed_time(b) for a, b in seg_events) / max(len(seg_events), 1) if seg_events else 0.0
+    render_ms = sum(ev[k][0].elapsed_time(seg_events[k][0]) for k in range(len(seg_events))) / max(len(seg_events), 1) if seg_events else 0.0
+    per_rank = None
+    if world > 1:  # every rank's own render / all-reduce time (the all-reduce time includes waiting for the slowest rank)
+        mine = torch.tensor([render_ms, allreduce_ms], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"render_ms": [round(float(t[0]), 2) for t in allr], "allreduce_ms": [round(float(t[1]), 2) for t in allr]}
     t_total = torch.tensor([sum(ms_steps)], dtype=torch.float64, device="cuda")
     rays_total = torch.tensor([float(sum(s.extend_rays + s.shadow_rays for s in stats))], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -378,7 +393,8 @@ def main():
                                  % (pool_used * 240 / 1e9)},
                 "ms_per_spp": ms_per_step / total_spp * world, "paths_per_step": int(stats[0].paths) * world,
                 "rays_per_step": rays_total.item() / args.steps,
-                "iterations_per_step": int(stats[0].iterations), "pipelines": int(stats[0].pipelines), "bvh_build_ms": bst.build_ms, "bvh_nodes": int(bst.num_nodes),
+                "iterations_per_step": int(stats[0].iterations), "pipelines": int(stats[0].pipelines),
+                "per_rank": per_rank, "bvh_build_ms": bst.build_ms, "bvh_nodes": int(bst.num_nodes),
                 "bvh_sah": bst.sah_cost,
                 "e2e": {"value": e2e_r.item() / e2e_t.item() * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(nfl * 4), "steps": n_e2e, "ms_per_step": e2e_t.item() / n_e2e * 1e3,

@@ -103,92 +103,65 @@ RTB_HD RaySetup ray_setup(V3 o, V3 d) {
 
 RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 
-// 0 = integer->float conversion per plane (I2F), 1 = byte permute into the mantissa (PRMT).
-// Measured on B200 (profiles/r1_variants.md): I2F is 1.4-1.6x faster end to end, so it is the default.
-#ifndef RTB_DEFAULT_DECODE
-#define RTB_DEFAULT_DECODE 0
-#endif
-
-// A/B variant kept for measurements (decode 1): byte j of `w` as the float
-// 1 + q * 2^-15, built by one byte permute that drops q into mantissa bits
-// 8..15 of 1.0f, instead of an integer->float conversion (XU pipe, 74-80 % busy
-// in the first ncu capture).  It lost on the B200: see profiles/r1_variants.md.
-template <int J>
-RTB_HD float byte_as_unit_float(uint32_t w) {
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (J << 4)));
-#else
-    return u2f(0x3F800000u | (((w >> (8 * J)) & 0xffu) << 8));
-#endif
-}
-
 // Slab-test the 8 quantised child boxes of one node against the ray segment
 // [0, tmax]; returns the hit mask: inner children in bits 24..31 at position
 // 24 + (slot ^ octinv) (so the highest set bit is the nearest child in octant
 // order), triangles of leaf children in bits 0..23.
 //
-// Plane distance: t = (origin_node + q*2^e - origin_ray) / d.  With
-// v = 1 + q*2^-15 (see byte_as_unit_float), a = 2^(e+15)/d and
-// c = (origin_node - origin_ray)/d - a this is t = v*a + c: one FMA per plane.
+// Plane distance along one axis: t(q) = (origin_node + q*2^e - origin_ray) / d
+// = q*a + c with a = 2^e/d and c = (origin_node - origin_ray)/d: one
+// integer->float conversion (I2F.U8 with a byte selector) and one FMA per
+// plane.  (A byte permute into the mantissa instead of the conversion was
+// measured 1.4-2x slower on the B200: profiles/r1_variants.md.)
+//
+// The test is CONSERVATIVE: it never culls a box the exact reference triangle
+// test (triangle.cuh:39-58) could still hit inside.  Error of the computed t:
+// c carries two roundings and the 1-ulp reciprocal (|dc| <= 2^-22 |c|), a is
+// exact up to the reciprocal, the FMA rounds once; so per AXIS
+//   |t - t_exact| <= 2^-22 |c_axis| + 2^-21 |t|.
+// The absolute part is folded into the constant of the FMA — near planes use
+// c - 2^-21|c|, far planes c + 2^-21|c| (twice the bound) — and the relative
+// part into the final comparison tn <= tf * (1 + 2^-19).  The pad of an axis
+// depends on that axis alone: a ray almost parallel to one axis (|c| huge
+// there) must not loosen the test on the other two.  (Round 1 first used one
+// pad 2^-21 max|c| for all three axes: such rays then passed every slab test
+// and walked whole slices of a 10 M-triangle scene; see profiles/README.md.)
 struct NodeFrame {
-    float ax, ay, az, cx, cy, cz, eps;
+    float ax, ay, az;     // 2^e / d
+    float nx, ny, nz;     // c lowered: for the entry planes
+    float fx, fy, fz;     // c raised: for the exit planes
 };
 RTB_HD NodeFrame node_frame(const Q4 &n0, const RaySetup &r) {
     NodeFrame f;
-    f.ax = fmul(u2f((byte_of(n0.w, 0) + 15u) << 23), r.idir.x);
-    f.ay = fmul(u2f((byte_of(n0.w, 1) + 15u) << 23), r.idir.y);
-    f.az = fmul(u2f((byte_of(n0.w, 2) + 15u) << 23), r.idir.z);
-    const float bx = fmul(fsub(u2f(n0.x), r.o.x), r.idir.x);
-    const float by = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
-    const float bz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
-    f.cx = fsub(bx, f.ax); f.cy = fsub(by, f.ay); f.cz = fsub(bz, f.az);
-    // Error bound of the slab arithmetic: an ABSOLUTE error of about
-    // 2^-23 * max(|b|, |a|) (b cancels against q*a when the ray starts close to
-    // the planes) plus a relative 2^-23 * |t|.  The far plane is pushed out by
-    // both so that the box test never culls a triangle the exact reference
-    // test (triangle.cuh:39-58) would accept.
-    const float m = fmaxf(fmaxf(fmaxf(fabsf(bx), fabsf(by)), fabsf(bz)), fmaxf(fmaxf(fabsf(f.ax), fabsf(f.ay)), fabsf(f.az)));
-    f.eps = fmul(m, 4.76837158203125e-07f);  // 2^-21
+    f.ax = fmul(u2f(byte_of(n0.w, 0) << 23), r.idir.x);
+    f.ay = fmul(u2f(byte_of(n0.w, 1) << 23), r.idir.y);
+    f.az = fmul(u2f(byte_of(n0.w, 2) << 23), r.idir.z);
+    const float cx = fmul(fsub(u2f(n0.x), r.o.x), r.idir.x);
+    const float cy = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
+    const float cz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
+    const float k = 4.76837158203125e-07f;  // 2^-21
+    f.nx = ffma(-fabsf(cx), k, cx); f.fx = ffma(fabsf(cx), k, cx);
+    f.ny = ffma(-fabsf(cy), k, cy); f.fy = ffma(fabsf(cy), k, cy);
+    f.nz = ffma(-fabsf(cz), k, cz); f.fz = ffma(fabsf(cz), k, cz);
     return f;
 }
+// The per-child meta decode is done four children at a time in packed bytes
+// (bits4 = unary triangle count or 1 for an inner child, pos4 = bit position
+// in the hit mask with the octant permutation already applied to inner
+// children), after Ylitie et al. 2017, so a hit child costs two byte
+// extracts, a shift and an OR.
 template <int J>
-RTB_HD uint32_t child_hit_bits(const NodeFrame &f, uint32_t meta4, uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4,
-                               uint32_t fy4, uint32_t fz4, float tmax, uint32_t octinv) {
-    const float tnx = ffma(byte_as_unit_float<J>(nx4), f.ax, f.cx);
-    const float tny = ffma(byte_as_unit_float<J>(ny4), f.ay, f.cy);
-    const float tnz = ffma(byte_as_unit_float<J>(nz4), f.az, f.cz);
-    const float tfx = ffma(byte_as_unit_float<J>(fx4), f.ax, f.cx);
-    const float tfy = ffma(byte_as_unit_float<J>(fy4), f.ay, f.cy);
-    const float tfz = ffma(byte_as_unit_float<J>(fz4), f.az, f.cz);
+RTB_HD uint32_t child_hit_bits(const NodeFrame &f, uint32_t bits4, uint32_t pos4, uint32_t nx4, uint32_t ny4, uint32_t nz4,
+                               uint32_t fx4, uint32_t fy4, uint32_t fz4, float tmax) {
+    const float tnx = ffma((float)byte_of(nx4, J), f.ax, f.nx);
+    const float tny = ffma((float)byte_of(ny4, J), f.ay, f.ny);
+    const float tnz = ffma((float)byte_of(nz4, J), f.az, f.nz);
+    const float tfx = ffma((float)byte_of(fx4, J), f.ax, f.fx);
+    const float tfy = ffma((float)byte_of(fy4, J), f.ay, f.fy);
+    const float tfz = ffma((float)byte_of(fz4, J), f.az, f.fz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-    if (tn <= ffma(tf, 1.0000019f, f.eps)) {
-        const uint32_t meta = byte_of(meta4, J);
-        const uint32_t bits = meta >> 5;             // unary triangle count, or 1 for an inner child
-        const bool inner = (meta & 0x18u) == 0x18u;  // low 5 bits in 24..31
-        const uint32_t pos = inner ? ((meta & 0x1fu) ^ octinv) : (meta & 0x1fu);
-        return bits << pos;
-    }
-    return 0u;
-}
-// Default decode (0): plane distance with an integer->float conversion per
-// byte, t = q * (2^e/d) + (origin_node - origin_ray)/d.  The per-child meta
-// decode is done four children at a time in packed bytes (bits4 = unary
-// triangle count or 1 for an inner child, pos4 = bit position in the hit mask
-// with the octant permutation already applied to inner children), after
-// Ylitie et al. 2017, so a hit child costs two byte extracts, a shift and an OR.
-template <int J>
-RTB_HD uint32_t child_hit_bits_i2f(const NodeFrame &f, uint32_t bits4, uint32_t pos4, uint32_t nx4, uint32_t ny4, uint32_t nz4,
-                                   uint32_t fx4, uint32_t fy4, uint32_t fz4, float tmax) {
-    const float tnx = ffma((float)byte_of(nx4, J), f.ax, f.cx);
-    const float tny = ffma((float)byte_of(ny4, J), f.ay, f.cy);
-    const float tnz = ffma((float)byte_of(nz4, J), f.az, f.cz);
-    const float tfx = ffma((float)byte_of(fx4, J), f.ax, f.cx);
-    const float tfy = ffma((float)byte_of(fy4, J), f.ay, f.cy);
-    const float tfz = ffma((float)byte_of(fz4, J), f.az, f.cz);
-    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
-    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-    if (tn <= ffma(tf, 1.0000019f, f.eps)) return byte_of(bits4, J) << byte_of(pos4, J);
+    if (tn <= fmul(tf, 1.0000019f)) return byte_of(bits4, J) << byte_of(pos4, J);
     return 0u;
 }
 // meta4 -> (bits4, pos4) for four children at once
@@ -198,22 +171,10 @@ RTB_HD void meta_decode4(uint32_t meta4, uint32_t oct4, uint32_t &bits4, uint32_
     pos4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1f1f1f1fu;
     bits4 = (meta4 >> 5) & 0x07070707u;
 }
-RTB_HD NodeFrame node_frame_i2f(const Q4 &n0, const RaySetup &r) {
-    NodeFrame f;
-    f.ax = fmul(u2f(byte_of(n0.w, 0) << 23), r.idir.x);
-    f.ay = fmul(u2f(byte_of(n0.w, 1) << 23), r.idir.y);
-    f.az = fmul(u2f(byte_of(n0.w, 2) << 23), r.idir.z);
-    f.cx = fmul(fsub(u2f(n0.x), r.o.x), r.idir.x);
-    f.cy = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
-    f.cz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
-    f.eps = fmul(fmaxf(fmaxf(fabsf(f.cx), fabsf(f.cy)), fabsf(f.cz)), 4.76837158203125e-07f);
-    return f;
-}
 
-template <int DEC = RTB_DEFAULT_DECODE>
 RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 &n3, const Q4 &n4,
                              const RaySetup &r, float tmax) {
-    const NodeFrame f = DEC ? node_frame(n0, r) : node_frame_i2f(n0, r);
+    const NodeFrame f = node_frame(n0, r);
     const bool px = (r.octinv & 1u) != 0, py = (r.octinv & 2u) != 0, pz = (r.octinv & 4u) != 0;
     uint32_t mask = 0;
 #pragma unroll
@@ -224,19 +185,12 @@ RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 
         const uint32_t nx4 = px ? lox : hix, fx4 = px ? hix : lox;
         const uint32_t ny4 = py ? loy : hiy, fy4 = py ? hiy : loy;
         const uint32_t nz4 = pz ? loz : hiz, fz4 = pz ? hiz : loz;
-        if (DEC) {
-            mask |= child_hit_bits<0>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-            mask |= child_hit_bits<1>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-            mask |= child_hit_bits<2>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-            mask |= child_hit_bits<3>(f, meta4, nx4, ny4, nz4, fx4, fy4, fz4, tmax, r.octinv);
-        } else {
-            uint32_t bits4, pos4;
-            meta_decode4(meta4, r.octinv * 0x01010101u, bits4, pos4);
-            mask |= child_hit_bits_i2f<0>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
-            mask |= child_hit_bits_i2f<1>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
-            mask |= child_hit_bits_i2f<2>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
-            mask |= child_hit_bits_i2f<3>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
-        }
+        uint32_t bits4, pos4;
+        meta_decode4(meta4, r.octinv * 0x01010101u, bits4, pos4);
+        mask |= child_hit_bits<0>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
+        mask |= child_hit_bits<1>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
+        mask |= child_hit_bits<2>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
+        mask |= child_hit_bits<3>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
     }
     return mask;
 }
@@ -249,7 +203,7 @@ constexpr int kStackSize = 48;
 // leaf-order index differs from `excluded` (the light's own triangle,
 // bvh.cuh:239-248).  Otherwise find the closest hit with the reference's
 // accept rule 0 < t <= tmax, tmax shrinking (bvh.cuh:222-236).
-template <bool ANY, bool COUNT, int DEC = RTB_DEFAULT_DECODE>
+template <bool ANY, bool COUNT>
 struct Traversal {
     RaySetup r;
     float tmax;
@@ -287,7 +241,7 @@ struct Traversal {
             const Q4 *np = B.nodes + (size_t)(base + rel) * kNodeWords;
             const Q4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
             if (COUNT) cnt.nodes++;
-            const uint32_t hm = node_hitmask<DEC>(n0, n1, n2, n3, n4, r, tmax);
+            const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, tmax);
             gx = n1.x; gy = (hm & 0xff000000u) | (n0.w >> 24);
             tx = n1.y; ty = hm & 0x00ffffffu;
         }
@@ -334,48 +288,6 @@ struct Traversal {
         return advance(stack_x, stack_y);
     }
 };
-
-// A/B variant kept for measurements: the same traversal written as one loop
-template <bool ANY, int DEC>
-RTB_HD bool bvh8_trace_mono(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, HitRec &hit) {
-    const RaySetup r = ray_setup(o, d);
-    uint32_t stack_x[kStackSize], stack_y[kStackSize];
-    int sp = 0;
-    uint32_t gx = 0, gy = 0x80000000u, tx = 0, ty = 0;
-    hit.t = 0.f; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
-    bool found = false;
-    while (true) {
-        if (gy & 0xff000000u) {
-            const int bit = bfind(gy);
-            gy &= ~(1u << bit);
-            const uint32_t base = gx, imask = gy & 0xffu;
-            if (gy & 0xff000000u) { stack_x[sp] = gx; stack_y[sp] = gy; ++sp; }
-            const uint32_t slot = ((uint32_t)bit - 24u) ^ r.octinv;
-            const uint32_t rel = popc(imask & ~(0xffffffffu << slot));
-            const Q4 *np = B.nodes + (size_t)(base + rel) * kNodeWords;
-            const Q4 n0 = ldg(np), n1 = ldg(np + 1), n2 = ldg(np + 2), n3 = ldg(np + 3), n4 = ldg(np + 4);
-            const uint32_t hm = node_hitmask<DEC>(n0, n1, n2, n3, n4, r, tmax);
-            gx = n1.x; gy = (hm & 0xff000000u) | (n0.w >> 24);
-            tx = n1.y; ty = hm & 0x00ffffffu;
-        }
-        while (ty) {
-            const int bit = bfind(ty);
-            ty &= ~(1u << bit);
-            const int idx = (int)(tx + (uint32_t)bit);
-            const Tri48 tr = load_tri(B.tris, idx);
-            float t, u, v;
-            if (tri_intersect(tr, o, d, tmax, t, u, v)) {
-                if (ANY) { if (idx != excluded) return true; }
-                else { tmax = t; hit.t = t; hit.u = u; hit.v = v; hit.tri = idx; found = true; }
-            }
-        }
-        if ((gy & 0xff000000u) == 0) {
-            if (sp == 0) break;
-            --sp; gx = stack_x[sp]; gy = stack_y[sp];
-        }
-    }
-    return found;
-}
 
 template <bool ANY, bool COUNT>
 RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, HitRec &hit,

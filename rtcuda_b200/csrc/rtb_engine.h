@@ -66,12 +66,20 @@ struct TonemapK {  // post_process_framebuffer, render.cuh:330-338
     const float *in; float *out; int64_t n; float inv_spp;
     RTB_HD void operator()(int i) const { if (i < n) out[i] = fsqrt(fmul(in[i], inv_spp)); }
 };
+RTB_HD bool ray_is_finite(const rtb_ray &r) {
+    return finite3(v3(r.origin[0], r.origin[1], r.origin[2])) && finite3(v3(r.dir[0], r.dir[1], r.dir[2]));
+}
 struct TraceClosestK {
     Bvh8View B; const rtb_ray *rays; rtb_hit *hits; int64_t n; unsigned long long *counts;
     RTB_HD void operator()(int i) const {
         if (i >= n) return;
         const rtb_ray r = rays[i];
         HitRec h;
+        if (!ray_is_finite(r)) {  // can hit nothing, would walk the whole tree
+            rtb_hit o; o.t = 0.f; o.u = 0.f; o.v = 0.f; o.prim = -1;
+            hits[i] = o;
+            return;
+        }
         if (counts) {
             TraceCounters c; c.nodes = 0; c.tris = 0;
             bvh8_trace<false, true>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, -1, h, &c);
@@ -93,6 +101,7 @@ struct TraceAnyK {
     RTB_HD void operator()(int i) const {
         if (i >= n) return;
         const rtb_ray r = rays[i];
+        if (!ray_is_finite(r)) { occluded[i] = 0; return; }
         int ex = excluded ? excluded[i] : -1;
         if (ex >= 0) ex = leaf_of_prim[ex];
         HitRec h;

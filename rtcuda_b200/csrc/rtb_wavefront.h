@@ -176,6 +176,16 @@ RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConst
     PathStepOut out;
     path_step<TYPE>(S, rc, in, out);
     if (out.emit) accum_add(W.accum, in.pixel, out.emission);
+    // A ray with a non-finite component can hit nothing (every comparison of the triangle test fails),
+    // but it would pass every slab test and walk the whole tree: retire it here with the result it
+    // would have had — a miss ends the path, an unoccluded shadow ray splats.  (MATTE sampling yields
+    // normalize(0) = NaN with probability 2^-24 per bounce: a few rays per frame, each worth seconds
+    // on a 10 M-triangle scene.)
+    if (out.extend && !(finite3(out.o) && finite3(out.d))) out.extend = false;
+    if (out.shadow && !(finite3(out.so) && finite3(out.sd) && out.stmax > 0.f)) {
+        out.shadow = false;
+        if (finite3(out.sL)) accum_add(W.accum, in.pixel, out.sL);
+    }
     // slot of this path in the ray queues = its position in the concatenated hit queues
     const Counters &c = *W.c;
     const int j = tid + (TYPE > 0 ? c.n_mat[0] : 0) + (TYPE > 1 ? c.n_mat[1] : 0);

@@ -118,6 +118,41 @@ def test_axis_aligned_and_degenerate_rays(s1_dev, s1_orc):
     assert_hits_equal(s1_dev.trace_closest(rays), s1_orc.trace_closest(rays, capi.HIT_DTYPE))
 
 
+def test_non_finite_rays_miss_without_walking_the_tree(s1_dev, s1_orc):
+    """a ray with a NaN / infinite component can hit nothing (every comparison of triangle.cuh:39-58 fails) but
+    passes every slab test: the kernels must retire it at once instead of visiting all nodes and triangles"""
+    rays = random_rays(64, seed=11)
+    nan, inf = np.float32("nan"), np.float32("inf")
+    rays["dir"][0] = (nan, nan, nan)
+    rays["dir"][1] = (nan, 0.3, -0.9)
+    rays["origin"][2] = (nan, 0.5, -0.5)
+    rays["dir"][3] = (inf, 0.0, 0.0)
+    rays["origin"][4] = (inf, 0.0, 0.0)
+    hits = s1_dev.trace_closest(rays)
+    ref = s1_orc.trace_closest(rays, capi.HIT_DTYPE)
+    assert (hits["prim"][:5] == -1).all() and (ref["prim"][:5] == -1).all()
+    assert_hits_equal(hits, ref)
+    assert (s1_dev.trace_any(rays[:5]) == 0).all()
+    nodes, tris = s1_dev.trace_counts(rays[:5])
+    assert nodes == 0 and tris == 0
+
+
+def test_slab_test_pads_each_axis_on_its_own(s1_dev, s1_orc):
+    """a ray almost parallel to one axis has a huge (origin - plane) / d on that axis; the conservative pad of the
+    slab test must come from each axis alone, or such a ray passes every box whose slab it starts in and walks a
+    whole slice of the scene (round 1: seconds per ray on the 10 M-triangle scene).  Same hits as the oracle, and
+    no more nodes than the same ray tilted a little."""
+    base = np.zeros(4, capi.RAY_DTYPE)
+    base["origin"] = (0.45, 0.2, 0.9)
+    base["tmax"] = 3.0e38
+    for k, dx in enumerate((1e-3, 1e-9, 1e-20, 1e-35)):
+        d = np.array((dx, 0.02, -1.0), np.float64)
+        base["dir"][k] = (d / np.linalg.norm(d)).astype(np.float32)
+    assert_hits_equal(s1_dev.trace_closest(base), s1_orc.trace_closest(base, capi.HIT_DTYPE))
+    counts = [s1_dev.trace_counts(base[k:k + 1])[0] for k in range(4)]
+    assert max(counts) <= counts[0] + 2, counts
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 9, 33, 200])
 def test_small_and_empty_scenes(L, ctx, oracle, n):
     """empty, single-triangle and ragged triangle counts; degenerate (zero-area) triangles included"""

@@ -26,6 +26,8 @@ ap.add_argument("--fused", default="1")
 ap.add_argument("--prefetch", default="1")
 ap.add_argument("--shade-occ", default="3")
 ap.add_argument("--pipelines", default="2")
+ap.add_argument("--first-sample", type=int, default=0)
+ap.add_argument("--device", type=int, default=0)
 ap.add_argument("--radius", type=int, default=0)
 ap.add_argument("--leaf", type=int, default=0)
 ap.add_argument("--count", action="store_true", help="also print nodes / triangles per ray (counting kernels)")
@@ -40,14 +42,14 @@ print(f"workload {a.workload}: {hs.desc.num_triangles} triangles, {w}x{h}x{spp}s
 for refill, chunk, pool, pooled, fused, pf, occ, pipes in itertools.product(a.refill.split(","), a.chunk.split(","), a.pool.split(","), a.pooled.split(","),
                                                                  a.fused.split(","), a.prefetch.split(","), a.shade_occ.split(","), a.pipelines.split(",")):
     os.environ.update(RTB_REFILL=refill, RTB_CHUNK=chunk, RTB_POOL=pool, RTB_POOLED=pooled, RTB_FUSED=fused, RTB_PREFETCH=pf, RTB_SHADE_OCC=occ, RTB_PIPELINES=pipes)
-    ctx = L.context(0)
+    ctx = L.context(a.device)
     bp = capi.BuildParams()
     L.lib.rtb_build_params_default(C.byref(bp))
     if a.radius: bp.ploc_radius = a.radius
     if a.leaf: bp.max_leaf_tris = a.leaf
     sc = ctx.scene(hs.desc, bp)
     bs = sc.stats()
-    p = capi.render_params(L, width=w, height=h, spp=spp, max_bounces=depth, flags=a.flags)
+    p = capi.render_params(L, width=w, height=h, spp=spp, max_bounces=depth, flags=a.flags, first_sample=a.first_sample, total_spp=spp + a.first_sample)
     best = None
     for _ in range(a.reps):
         img, st = sc.render(cam, p)
