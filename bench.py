@@ -382,7 +382,7 @@ def main():
                             % ((bst.node_bytes + bst.triangle_bytes) / 1e6,
                                "is L2-resident: the kernel is bound by instruction issue, not by HBM (see profiles/)" if bst.node_bytes + bst.triangle_bytes < 100e6
                                else "exceeds L2")}
-        pool_used = min(int(p.pool_size) or int(os.environ.get("RTB_POOL", 1 << 26)), int(stats[0].paths))
+        pool_used = min(int(p.pool_size) or int(os.environ.get("RTB_POOL", 1 << 25)), int(stats[0].paths))
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",

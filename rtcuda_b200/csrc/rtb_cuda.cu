@@ -288,7 +288,7 @@ struct CudaBackend {
     FetchTuning tune_{24, 128, 1};  // RTB_REFILL / RTB_CHUNK / RTB_PREFETCH override (tuning runs)
     int pooled_ = -1;  // RTB_POOLED: pooled triangle tests (1), each ray's lane on its own (0), by scene size (-1)
     int fused_ = 1;   // RTB_FUSED: extend + shadow rays of one iteration in one launch
-    int pool_ = 1 << 26;    // default path pool, RTB_POOL overrides (tuning)
+    int pool_ = 1 << 25;    // default path pool, RTB_POOL overrides (tuning)
 
     explicit CudaBackend(int device) {
         int count = 0;

@@ -413,13 +413,12 @@ SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const 
 // waits for an iteration: it keeps two batches of launches in flight and
 // watches a `done` word that the control kernel raises in mapped host memory.
 //
-// Two pipelines.  A trace launch ends with a tail: its last rays are latency
-// bound and leave most SMs idle (10 M-triangle scene, 8 Mi-ray iterations: ~1.8 ms
-// of every ~4 ms iteration, profiles/r1_pool_sweep.md).  So the render is split
-// into two independent wavefronts — the even and the odd paths, each with its
-// own queues and counters, half the pool each — on two streams: while one is in
-// the tail of its trace kernel, the blocks of the other one's kernels fill the
-// SMs that fall idle.  They only meet in the accumulation buffer (atomic adds).
+// Two pipelines.  Every launch ends with a tail in which the last warps leave SMs idle, and between
+// two launches of a stream nothing runs.  The render is therefore split into two independent
+// wavefronts — the even and the odd paths, each with its own queues and counters, half the pool each —
+// on two streams: while one drains, the blocks of the other one's kernels fill the idle SMs.  They only
+// meet in the accumulation buffer (atomic adds).  Worth 2-3 % on C2 (40.3 -> 39.2 ms), nothing on the
+// 10 M-triangle scene (profiles/README.md).
 template <class BE>
 void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_render_params &p, float *d_accum,
                        rtb_render_stats *stats) {
