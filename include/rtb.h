@@ -136,6 +136,9 @@ typedef struct rtb_render_params {
     int32_t pool_size;      /* path slots (NUM_WORKING_PATHS, constant.hpp:8); 0 = auto */
     int32_t flags;          /* RTB_RENDER_* */
     int32_t _reserved;
+    float env_L[3];         /* radiance of a constant environment seen by rays that leave the scene (the reference's
+                               TODO at render.cuh:105,243,325); (0,0,0) = none, as in the reference */
+    int32_t _reserved2;
 } rtb_render_params;
 
 enum {
@@ -144,7 +147,13 @@ enum {
     RTB_RENDER_NO_SHADOW = 2,    /* skip next-event estimation (debug) */
     RTB_RENDER_NONPERSISTENT = 4, /* one-thread-per-ray traversal launch (A/B for the persistent kernel) */
     RTB_RENDER_COUNT_WORK = 8,    /* counting kernel variants: fill the *_nodes / *_tris statistics (slower) */
-    RTB_RENDER_SINGLE_PIPELINE = 16 /* one wavefront on one stream (per-stage timing; default is two concurrent ones) */
+    RTB_RENDER_SINGLE_PIPELINE = 16, /* one wavefront on one stream (per-stage timing; default is two concurrent ones) */
+    /* ---- beyond the reference: OFF by default, parity mode is untouched ---- */
+    RTB_RENDER_TRUE_MIS = 32,     /* power_heuristic(float, float) for the light sample, and the path ray itself is the
+                                     BSDF sample of the MIS pair: emitters met after a bounce add beta * L * w (the
+                                     reference truncates the BSDF pdf to int and aims its MIS ray at the wrong triangle,
+                                     utility.cuh:53, render.cuh:236; specular paths then never see a light) */
+    RTB_RENDER_RR_TERMINATE = 64  /* a Russian-roulette kill ends the path (the reference only pauses it, render.cuh:112-126) */
 };
 
 typedef struct rtb_render_stats {

@@ -384,10 +384,33 @@ void trace_path(const Scene &s, const rtb_camera &cam, const rtb_render_params &
     st.extend++;
     bool hit = traverse<false>(s, ray, is, prim, -1, nullptr);
     const int nl = (int)s.lights.size();
+    // beyond the reference (off by default): rtb.h RTB_RENDER_TRUE_MIS / RTB_RENDER_RR_TERMINATE / env_L
+    const bool true_mis = (p.flags & RTB_RENDER_TRUE_MIS) != 0;
+    const bool has_env = p.env_L[0] != 0.f || p.env_L[1] != 0.f || p.env_L[2] != 0.f;
+    auto add_env = [&](const Vec3 &bt) {
+        Vec3 L = bt * V(p.env_L[0], p.env_L[1], p.env_L[2]);
+        if (fabsf(L.x) <= FLT_MAX && fabsf(L.y) <= FLT_MAX && fabsf(L.z) <= FLT_MAX) { fb[0] += L.x; fb[1] += L.y; fb[2] += L.z; }
+    };
+    if (!hit && has_env) add_env(beta);
+    float prev_pdf = 0.f;  // solid-angle pdf of the BSDF sample that produced `ray`, 0 = delta / camera
     while (true) {
-        if (b == 0 && hit && s.light_id[prim] >= 0) {  // render.cuh:98-107
+        if (hit && s.light_id[prim] >= 0 && (b == 0 || true_mis)) {  // render.cuh:98-107
             const rtb_light &l = s.lights[s.light_id[prim]];
-            fb[0] += l.L[0]; fb[1] += l.L[1]; fb[2] += l.L[2];
+            if (b == 0) {
+                fb[0] += l.L[0]; fb[1] += l.L[1]; fb[2] += l.L[2];
+            } else {  // the path ray is the BSDF sample of the MIS pair
+                float w = 1.f;
+                const Triangle &lt = s.tris[prim];
+                if (prev_pdf > 0.f) {
+                    float area = 0.5f * length_dev(lt.n);
+                    float cosl = fabsf(dot_dev(unit_dev(lt.n), ray.unit_d));
+                    float pdf_l = ((is.t * is.t) / (area * cosl)) / (float)nl;
+                    float a2 = prev_pdf * prev_pdf;
+                    w = a2 / (a2 + pdf_l * pdf_l);
+                }
+                Vec3 L = (V(l.L[0], l.L[1], l.L[2]) * w) * beta;
+                if (fabsf(L.x) <= FLT_MAX && fabsf(L.y) <= FLT_MAX && fabsf(L.z) <= FLT_MAX) { fb[0] += L.x; fb[1] += L.y; fb[2] += L.z; }
+            }
         }
         if (b >= p.max_bounces) break;  // render.cuh:109
         if (!hit) break;                // the reference idles the slot instead (Quirk B)
@@ -396,7 +419,10 @@ void trace_path(const Scene &s, const rtb_camera &cam, const rtb_render_params &
             if (bm < p.rr_threshold) {
                 float pt = fmaxf(0.05f, 1.f - bm);
                 float u = rand4(p.seed, pixel, sample, 2u * (uint32_t)b + 1u).a;
-                if (u < pt) { b++; continue; }  // Quirk A: pause, roll again on the same hit
+                if (u < pt) {
+                    if (p.flags & RTB_RENDER_RR_TERMINATE) break;
+                    b++; continue;  // Quirk A: pause, roll again on the same hit
+                }
                 beta = beta / (1.f - pt);
             }
         }
@@ -444,10 +470,16 @@ void trace_path(const Scene &s, const rtb_camera &cam, const rtb_render_params &
                 Vec3 f = (V(m.albedo[0], m.albedo[1], m.albedo[2]) * INV_PI_F) * cosl;
                 float spdf = cosl * INV_PI_F;
                 Vec3 L = ((beta_old * (float)nl) * f) * Li;
-                if (l.type != RTB_POINT_LIGHT) {  // power_heuristic(float, int): Quirk C
-                    int g = (int)spdf;
-                    float f2 = pdfL * pdfL;
-                    L = L * (f2 / (f2 + (float)(g * g)));
+                if (l.type != RTB_POINT_LIGHT) {
+                    if (true_mis) {
+                        float pl = pdfL / (float)nl;
+                        float a2 = pl * pl;
+                        L = L * (a2 / (a2 + spdf * spdf));
+                    } else {  // power_heuristic(float, int): Quirk C
+                        int g = (int)spdf;
+                        float f2 = pdfL * pdfL;
+                        L = L * (f2 / (f2 + (float)(g * g)));
+                    }
                 }
                 L = L * (1.f / pdfL);
                 Ray sh{offset_ray_origin(P, nL), wiL, tL};
@@ -462,8 +494,10 @@ void trace_path(const Scene &s, const rtb_camera &cam, const rtb_render_params &
         }
         if (b >= p.max_bounces) break;  // the reference traces `next` and discards the result
         ray = next;
+        prev_pdf = m.type == RTB_MATTE ? pdf1 : 0.f;
         st.extend++;
         hit = traverse<false>(s, ray, is, prim, -1, nullptr);
+        if (!hit && has_env) add_env(beta);
     }
 }
 

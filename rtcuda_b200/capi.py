@@ -17,6 +17,7 @@ BUNNY_BIN = os.path.join(HERE, "data", "bunny.rtbm")
 RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2 = 1, 2, 3
 RTB_RENDER_PIXEL_CENTRE, RTB_RENDER_NO_SHADOW, RTB_RENDER_NONPERSISTENT, RTB_RENDER_COUNT_WORK = 1, 2, 4, 8
 RTB_RENDER_SINGLE_PIPELINE = 16
+RTB_RENDER_TRUE_MIS, RTB_RENDER_RR_TERMINATE = 32, 64
 
 
 class Material(C.Structure):
@@ -55,7 +56,7 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_bounces", C.c_int32),
                 ("rr_start", C.c_int32), ("rr_threshold", C.c_float), ("seed", C.c_uint32),
                 ("first_sample", C.c_int32), ("total_spp", C.c_int32), ("pool_size", C.c_int32),
-                ("flags", C.c_int32), ("_reserved", C.c_int32)]
+                ("flags", C.c_int32), ("_reserved", C.c_int32), ("env_L", C.c_float * 3), ("_reserved2", C.c_int32)]
 
 
 class RenderStats(C.Structure):
@@ -208,7 +209,10 @@ def render_params(L, **kw):
     p = RenderParams()
     L.check(L.lib.rtb_render_params_default(C.byref(p)))
     for k, v in kw.items():
-        setattr(p, k, v)
+        if k == "env_L":
+            p.env_L[0], p.env_L[1], p.env_L[2] = v
+        else:
+            setattr(p, k, v)
     return p
 
 

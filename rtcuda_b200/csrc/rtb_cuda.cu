@@ -48,11 +48,11 @@ __global__ void __launch_bounds__(kBlock) k_generate(WaveState W, RenderConsts r
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) generate_body(W, rc, i);
 }
 
-template <int TYPE, int MINB = 3>
+template <int TYPE, int MINB = 3, bool EXT = false>
 __global__ void __launch_bounds__(kBlock, MINB) k_shade(WaveState W, SceneView S, RenderConsts rc, bool shadows) {
     const int n = W.c->n_mat[TYPE];
     ShadeTally tally; tally.extend = 0u; tally.shadow = 0u;
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) shade_body<TYPE>(W, S, rc, shadows, i, tally);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) shade_body<TYPE, EXT>(W, S, rc, shadows, i, tally);
     tally_flush(W.c, tally);
 }
 
@@ -162,7 +162,9 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
         if (pending) {
             if (ANY) {
                 shadow_finish(W, qi, T.found);
-            } else if (T.hit.tri >= 0) {
+            } else if (T.hit.tri < 0) {
+                if (W.has_env) extend_miss(W, __float_as_uint(ws.ro[lane].w), xyz(ldg(W.ec + qi)));
+            } else {
                 const int mat = S.tri_meta[T.hit.tri].material;
                 const int type = mat >> 24;
                 int j;
@@ -175,6 +177,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                 F4 mb; mb.x = beta.x; mb.y = beta.y; mb.z = beta.z; mb.w = d.w;
                 F4 mc; mc.x = i2f(mat); mc.y = T.hit.u; mc.z = T.hit.v; mc.w = i2f(T.hit.tri);
                 W.ma[j] = ma; W.mb[j] = mb; W.mc[j] = mc;
+                if (W.mis) { W.mis[2 * (size_t)j] = beta.w; W.mis[2 * (size_t)j + 1] = T.hit.t; }
             }
             pending = false;
         }
@@ -392,18 +395,21 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shade(const ShadeK &k) {
-        if (shade_occ_ == 4) {  // tuning: 64 registers (small spills), 4 blocks per SM
+        const int grid = blocks_shade_[k.type];  // exactly one resident wave: the kernels are grid-stride loops
+        if (k.rc.flags & (RTB_RENDER_TRUE_MIS | RTB_RENDER_RR_TERMINATE)) {  // beyond-the-reference estimator
+            if (k.type == 0) k_shade<0, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 1) k_shade<1, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else k_shade<2, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+        } else if (shade_occ_ == 4) {  // tuning: 64 registers (small spills), 4 blocks per SM
             const int g4 = blocks_shade4_[k.type];
             if (k.type == 0) k_shade<0, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else if (k.type == 1) k_shade<1, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else k_shade<2, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            RTB_CUDA_CHECK(cudaGetLastError());
-            return;
+        } else {
+            if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         }
-        const int grid = blocks_shade_[k.type];  // exactly one resident wave: the kernels are grid-stride loops
-        if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-        else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-        else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void control(const WaveState &W, bool shadows) {

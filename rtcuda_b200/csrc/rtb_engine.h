@@ -142,7 +142,8 @@ struct SceneT {
         for (int k = 0; k < pipes; ++k) {
             WaveState &w = W[k];
             be->free(w.ea); be->free(w.eb); be->free(w.ec); be->free(w.ma); be->free(w.mb); be->free(w.mc);
-            be->free(w.sh_o); be->free(w.sh_d); be->free(w.sh_L); be->free(w.c);
+            be->free(w.sh_o); be->free(w.sh_d); be->free(w.sh_L); be->free(w.c); be->free(w.mis);
+            w.mis = nullptr;
         }
         pool = 0; pipes = 0;
     }
@@ -156,6 +157,7 @@ struct SceneT {
             w.sh_o = be->template alloc<F4>(p); w.sh_d = be->template alloc<F4>(p); w.sh_L = be->template alloc<F4>(p);
             w.c = be->template alloc<Counters>(1);
             w.pool = p;
+            w.mis = nullptr;
         }
         pool = p; pipes = np;
     }
@@ -442,13 +444,18 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     RenderConsts rc[kMaxPipelines];
     auto t0 = be.now();
     for (int k = 0; k < np; ++k) {
+        if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(6 * (size_t)pool);
         W[k] = sc.W[k];
+        if (!(p.flags & RTB_RENDER_TRUE_MIS)) W[k].mis = nullptr;
+        W[k].env[0] = p.env_L[0]; W[k].env[1] = p.env_L[1]; W[k].env[2] = p.env_L[2];
+        W[k].has_env = (p.env_L[0] != 0.f || p.env_L[1] != 0.f || p.env_L[2] != 0.f) ? 1 : 0;
         W[k].accum = d_accum;
         W[k].host_done = be.done_flag_device(k);
         RenderConsts &r = rc[k];
         r.cam = cam; r.width = p.width; r.height = p.height; r.spp = p.spp; r.first_sample = p.first_sample;
         r.max_bounces = p.max_bounces; r.rr_start = p.rr_start; r.rr_threshold = p.rr_threshold; r.seed = p.seed; r.flags = p.flags;
         r.path_offset = k; r.path_stride = np;
+        r.env[0] = p.env_L[0]; r.env[1] = p.env_L[1]; r.env[2] = p.env_L[2];
         Counters c0;
         memset(&c0, 0, sizeof c0);
         c0.total_paths = (total - (unsigned long long)k + (unsigned long long)np - 1ull) / (unsigned long long)np;

@@ -49,6 +49,7 @@ struct RenderConsts {
     uint32_t seed;
     int32_t flags;
     int32_t path_offset, path_stride;  // this wavefront renders paths offset, offset + stride, ...
+    float env[3];                      // constant environment radiance (rtb_render_params.env_L)
 };
 
 // ------------------------------------------------------------------ camera
@@ -188,6 +189,10 @@ RTB_HD float power_heuristic_ref(float f_pdf, float g_pdf_float) {
     return fdiv(f2, fadd(f2, (float)(g * g)));
 }
 
+RTB_HD bool finite3(V3 a) {
+    return fabsf(a.x) <= FLT_MAX && fabsf(a.y) <= FLT_MAX && fabsf(a.z) <= FLT_MAX;
+}
+
 // ------------------------------------------------------------------ path step
 struct PathStepIn {
     V3 wo;  // direction of the ray that produced the hit
@@ -196,17 +201,20 @@ struct PathStepIn {
     uint32_t pixel, sample;
     int32_t bounces;
     int32_t material;  // TriMeta::material of the hit triangle (index | type << 24)
+    float prev_pdf;    // RTB_RENDER_TRUE_MIS: solid-angle pdf of the BSDF sample that produced this ray (0 = delta)
+    float t;           // RTB_RENDER_TRUE_MIS: hit distance
 };
 struct PathStepOut {
     bool emit; V3 emission;
-    bool extend; V3 o, d, beta; int32_t bounces;
+    bool extend; V3 o, d, beta; int32_t bounces; float pdf;  // pdf: of the BSDF sample, 0 for MIRROR / GLASS
     bool shadow; V3 so, sd, sL; float stmax; int32_t sexcl;
 };
 
 // One visit of a path that HIT something: everything the reference does to it
 // between two closest-hit traversals.  MT >= 0 tells the compiler the material
 // type of the hit (the per-type shade kernels), -1 = read it from the material.
-template <int MT>
+// EXT = false compiles the beyond-the-reference branches (RTB_RENDER_TRUE_MIS / RR_TERMINATE) out of the parity kernels.
+template <int MT, bool EXT = true>
 RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStepIn &in, PathStepOut &out) {
     out.emit = false; out.extend = false; out.shadow = false;
     // issue every load that only depends on the hit before the roulette logic: the shade kernel is
@@ -217,12 +225,28 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
     int b = in.bounces;
     V3 beta = in.beta;
     // init, render.cuh:98-107: only camera rays see emitters
-    if (b == 0) {
+    const bool true_mis = EXT && (rc.flags & RTB_RENDER_TRUE_MIS) != 0;
+    if (b == 0 || true_mis) {
         const int light = S.tri_meta[in.hit.tri].light;
         if (light >= 0) {
             const LightDev &l = S.lights[light];
             out.emit = true;
             out.emission = v3(l.Lx, l.Ly, l.Lz);
+            if (b > 0) {
+                // RTB_RENDER_TRUE_MIS: this path ray was the BSDF sample of the previous bounce; weigh it against
+                // the light sample that could have produced the same direction (Light::pdf_Li, light.cuh:50-64,
+                // times the 1/num_lights of the uniform light pick); a delta BSDF has no competitor
+                float w = 1.f;
+                if (in.prev_pdf > 0.f) {
+                    const float area = fmul(0.5f, vlen(tri_n(tr)));
+                    const float cosl = fabsf(vdot(vnormalize(tri_n(tr)), in.wo));
+                    const float pdf_l = fdiv(fdiv(fmul(in.t, in.t), fmul(area, cosl)), (float)S.num_lights);
+                    const float a2 = fmul(in.prev_pdf, in.prev_pdf);
+                    w = fdiv(a2, fadd(a2, fmul(pdf_l, pdf_l)));
+                }
+                out.emission = vmul(vscale(out.emission, w), in.beta);
+                if (!finite3(out.emission)) out.emit = false;
+            }
         }
     }
     // init, render.cuh:109-126: depth cut + Russian roulette (Quirk A: a kill
@@ -234,7 +258,10 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
             if (bm < rc.rr_threshold) {
                 float p = fmaxf(0.05f, fsub(1.f, bm));
                 float u = rand4(rc.seed, in.pixel, in.sample, 2u * (uint32_t)b + 1u).a;
-                if (u < p) { b++; continue; }
+                if (u < p) {
+                    if (EXT && (rc.flags & RTB_RENDER_RR_TERMINATE)) return;
+                    b++; continue;
+                }
                 beta = vscale(beta, frcp(fsub(1.f, p)));
             }
         }
@@ -253,6 +280,7 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
         out.d = bs.wi;
         out.beta = beta;
         out.bounces = b;
+        out.pdf = m.type == RTB_MATTE ? bs.pdf : 0.f;
         // the reference traces this ray even when the depth cut will discard
         // its result (render.cuh:109); skipping it does not change the image
         out.extend = b < rc.max_bounces;
@@ -271,7 +299,15 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
         float scattering_pdf = fmul(cosl, kInvPi);
         V3 mult = vscale(beta_old, (float)S.num_lights);
         V3 L = vmul(vmul(mult, f), ls.Li);
-        if (l.type != RTB_POINT_LIGHT) L = vscale(L, power_heuristic_ref(ls.pdf, scattering_pdf));
+        if (l.type != RTB_POINT_LIGHT) {
+            if (true_mis) {  // both pdfs in solid angle, the light's including the 1/num_lights of the pick
+                const float pl = fdiv(ls.pdf, (float)S.num_lights);
+                const float a2 = fmul(pl, pl);
+                L = vscale(L, fdiv(a2, fadd(a2, fmul(scattering_pdf, scattering_pdf))));
+            } else {
+                L = vscale(L, power_heuristic_ref(ls.pdf, scattering_pdf));
+            }
+        }
         L = vscale(L, frcp(ls.pdf));
         out.shadow = true;
         out.so = offset_ray_origin(P, nl);
@@ -284,8 +320,5 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
     // contributes, consumes no dimensions of the counter-based RNG.
 }
 
-RTB_HD bool finite3(V3 a) {
-    return fabsf(a.x) <= FLT_MAX && fabsf(a.y) <= FLT_MAX && fabsf(a.z) <= FLT_MAX;
-}
 
 }  // namespace rtb

@@ -39,7 +39,7 @@ struct Counters {
 };
 
 // Record layouts (each field array has `pool` entries, 16 bytes per entry):
-//   extend queue   ea = origin.xyz | pixel      eb = dir.xyz | sample<<8|bounces   ec = beta.xyz | -
+//   extend queue   ea = origin.xyz | pixel      eb = dir.xyz | sample<<8|bounces   ec = beta.xyz | pdf of the BSDF sample
 //   hit queue[t]   ma = dir.xyz    | pixel      mb = beta.xyz | sample<<8|bounces  mc = material word,u,v | leaf-order triangle
 //   shadow queue   sh_o = origin.xyz | tmax     sh_d = dir.xyz | excluded triangle sh_L = radiance | pixel
 // Hit queues are dense (extend appends to them with warp-aggregated atomics).  The two ray queues
@@ -55,6 +55,11 @@ struct WaveState {
     int32_t *host_done;  // mapped pinned host word (or null): lets the host poll without a stream sync
     float *accum;        // 3 floats per pixel, radiance sums
     int32_t pool;
+    // beyond the reference (off in parity mode): per-hit {pdf of the BSDF sample that produced the ray, hit
+    // distance} for RTB_RENDER_TRUE_MIS ([3][pool], null otherwise); constant environment radiance
+    float *mis;
+    float env[3];
+    int32_t has_env;
 };
 
 constexpr int kMaxBounces = 255;       // bounces share a word with the sample index
@@ -129,8 +134,15 @@ RTB_HD void generate_body(const WaveState &W, const RenderConsts &rc, int tid) {
 // ------------------------------------------------------------ extend
 // ch, render.cuh:297-328 (PATH_RAY part), one queue entry.  A miss ends the
 // path (the reference parks the slot until max_bounces, Quirk B).
+RTB_HD void extend_miss(const WaveState &W, uint32_t pixel, V3 beta) {  // environment light, rtb_render_params.env_L
+    const V3 L = vmul(beta, v3(W.env[0], W.env[1], W.env[2]));
+    if (finite3(L)) accum_add(W.accum, pixel, L);
+}
 RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const HitRec &h) {
-    if (h.tri < 0) return;
+    if (h.tri < 0) {
+        if (W.has_env) extend_miss(W, f2u(ldg(W.ea + qi).w), xyz(ldg(W.ec + qi)));
+        return;
+    }
     const int mat = S.tri_meta[h.tri].material;
     const int type = mat >> 24;
     int j;
@@ -144,6 +156,7 @@ RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const 
     W.ma[j] = f4(xyz(b), a.w);
     W.mb[j] = f4(xyz(beta), b.w);
     W.mc[j] = hr;
+    if (W.mis) { W.mis[2 * (size_t)j] = beta.w; W.mis[2 * (size_t)j + 1] = h.t; }
 }
 template <bool COUNT>
 RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
@@ -159,7 +172,7 @@ RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
 
 // ------------------------------------------------------------ shade
 // init + mat (render.cuh:84-248) for entry `tid` of hit queue `type`
-template <int TYPE>
+template <int TYPE, bool EXT = true>
 RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConsts &rc, bool shadows, int tid, ShadeTally &tally) {
     const int type = TYPE;
     const int q = type * W.pool + tid;
@@ -173,8 +186,10 @@ RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConst
     in.bounces = (int)(packed & 0xffu);
     in.sample = packed >> 8;
     in.pixel = f2u(a.w);
+    in.prev_pdf = 0.f; in.t = 0.f;
+    if (EXT && W.mis) { in.prev_pdf = W.mis[2 * (size_t)q]; in.t = W.mis[2 * (size_t)q + 1]; }
     PathStepOut out;
-    path_step<TYPE>(S, rc, in, out);
+    path_step<TYPE, EXT>(S, rc, in, out);
     if (out.emit) accum_add(W.accum, in.pixel, out.emission);
     // A ray with a non-finite component can hit nothing (every comparison of the triangle test fails),
     // but it would pass every slab test and walk the whole tree: retire it here with the result it
@@ -192,7 +207,7 @@ RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConst
     if (out.extend) {
         W.ea[j] = f4(out.o, a.w);
         W.eb[j] = f4(out.d, u2f((in.sample << 8) | (uint32_t)out.bounces));
-        W.ec[j] = f4(out.beta, 0.f);
+        W.ec[j] = f4(out.beta, out.pdf);
     } else {
         W.ea[j] = f4(v3(0.f), u2f(kHolePixel));
     }

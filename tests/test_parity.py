@@ -239,6 +239,78 @@ def test_russian_roulette_and_depth_limits(L, s1, s1_dev, s1_orc):
     assert (img0 > 0).any() and (img0 == 0).mean() > 0.9
 
 
+# ---- beyond the reference: flags that are OFF in parity mode ----
+@pytest.mark.parametrize("kind,depth", [(capi.RTB_SCENE_S1, 8), (capi.RTB_SCENE_S1_MIXED, 12)])
+def test_true_mis_rr_termination_and_environment_match_the_oracle(L, bunny, ctx, oracle, kind, depth):
+    """RTB_RENDER_TRUE_MIS | RTB_RENDER_RR_TERMINATE with a constant environment: the product and the oracle implement
+    the same corrected estimator (power heuristic on float pdfs, emitters seen after a bounce weighed as the BSDF
+    sample, roulette kills end the path, rays leaving the scene pick up env_L)"""
+    hs = L.host_scene(kind, *bunny)
+    sc, osc = ctx.scene(hs.desc), oracle.scene(hs.desc)
+    cam = hs.camera(4 / 3)
+    flags = capi.RTB_RENDER_TRUE_MIS | capi.RTB_RENDER_RR_TERMINATE
+    img, st, ref, ost = render_pair(L, sc, osc, cam, width=128, height=96, spp=8, max_bounces=depth, flags=flags,
+                                    rr_start=1, env_L=(0.3, 0.4, 0.6))
+    assert st.paths == ost[0]
+    assert abs(int(st.extend_rays) - int(ost[1])) <= 5e-3 * ost[1]
+    assert abs(int(st.shadow_rays) - int(ost[2])) <= 5e-3 * ost[2]
+    assert np.isfinite(img).all()
+    assert mean_rel_err(img, ref) <= IMAGE_TOL
+    # the flags change the estimator: not the parity image
+    par, _ = sc.render(cam, capi.render_params(L, width=128, height=96, spp=8, max_bounces=depth))
+    assert mean_rel_err(img, par) > 10 * IMAGE_TOL
+
+
+def test_true_mis_and_light_sampling_only_agree_in_the_mean(L, oracle):
+    """direct lighting of a floor by a large, low, black-bodied emitter: the reference's estimator (weight-1 light
+    sampling) and the MIS estimator (light sample + BSDF sample, complete at depth 2) are both unbiased,
+    so the floor converges to the same radiance; at depth 1 MIS lacks its BSDF half (56 % of the light here), which
+    shows that the test weighs that branch"""
+    floor = [[[-3, 0, 3], [3, 0, 3], [3, 0, -3]], [[-3, 0, 3], [3, 0, -3], [-3, 0, -3]]]
+    lamp = [[[-1, 0.3, 1], [1, 0.3, 1], [0.0, 0.3, -1]]]
+    verts = np.array(floor + lamp, np.float32).reshape(-1, 9)
+    grey, black = capi.Material(), capi.Material()
+    grey.albedo[0] = grey.albedo[1] = grey.albedo[2] = 0.6
+    desc, keep = make_desc(verts, np.array([0, 0, 1], np.int32), np.array([-1, -1, 0], np.int32), [grey, black], [area_light(2, 2.0)])
+    osc = oracle.scene(desc)
+    cam = L.camera_look_at((0.0, 0.25, 3.5), (0.0, 0.0, 0.0), (0, 1, 0), 50.0, 1.0)
+    w = h = 32
+    prim = osc.trace_closest(L.primary_rays(cam, w, h), capi.HIT_DTYPE)["prim"].reshape(h, w)
+    on_floor = (prim == 0) | (prim == 1)
+    mask = on_floor.copy()
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            mask &= np.roll(np.roll(on_floor, dy, 0), dx, 1)  # pixel jitter stays on the floor
+    assert mask.sum() > 300
+
+    def floor_mean(**kw):
+        tot = 0.0
+        for seed in (1, 5):
+            _, acc, _ = osc.render(cam, capi.render_params(L, width=w, height=h, spp=1024, seed=seed, **kw), want_accum=True)
+            tot += float(acc[mask].mean())
+        return tot / 2
+
+    nee = floor_mean(max_bounces=2)
+    mis = floor_mean(max_bounces=2, flags=capi.RTB_RENDER_TRUE_MIS)
+    mis_half = floor_mean(max_bounces=1, flags=capi.RTB_RENDER_TRUE_MIS)
+    assert abs(mis - nee) <= 0.025 * nee, (mis, nee)
+    assert mis_half < 0.6 * nee
+
+
+def test_environment_light_reaches_open_scenes_only_through_misses(L, s1, s1_dev, s1_orc):
+    """env_L adds beta * env for every ray that leaves the scene and nothing else: the image is the parity image plus a
+    term linear in env_L"""
+    cam = s1.camera(1.0)
+    kw = dict(width=64, height=64, spp=4, max_bounces=6)
+    base, _ = s1_dev.render(cam, capi.render_params(L, **kw))
+    e1, _, r1, _ = render_pair(L, s1_dev, s1_orc, cam, env_L=(1.0, 1.0, 1.0), **kw)
+    e2, _ = s1_dev.render(cam, capi.render_params(L, env_L=(2.0, 2.0, 2.0), **kw))
+    assert mean_rel_err(e1, r1) <= IMAGE_TOL
+    lin = lambda x: x.astype(np.float64) ** 2  # images are sqrt(sum / spp)
+    assert (lin(e1) >= lin(base) - 1e-6).all() and lin(e1).sum() > lin(base).sum() * 1.01
+    assert mean_rel_err(lin(e2) - lin(base), 2 * (lin(e1) - lin(base))) <= 1e-4
+
+
 def test_sample_pass_sharding_is_additive(L, s1, s1_dev):
     """the multi-GPU decomposition: samples [0,a) + [a,a+b) == samples [0,a+b) (per-pixel RNG keyed by sample index)"""
     cam = s1.camera(1.0)
