@@ -102,11 +102,19 @@ typedef struct rtb_scene_desc {
 /* BVH builder selection (rtb_build_params.builder) */
 enum { RTB_BUILDER_PLOC = 0 }; /* the only builder so far; other values are rejected */
 
+/* how the binary tree is collapsed into 8-wide nodes (rtb_build_params.collapse) */
+enum {
+    RTB_COLLAPSE_LARGEST_FIRST = 0, /* greedy: open the child with the largest surface area until 8 children (default) */
+    RTB_COLLAPSE_SAH_OPTIMAL = 1    /* dynamic programme: cheapest layout of every subtree in 1..7 child slots; a third
+                                       fewer nodes, 0-3 % faster renders, but exact-t ties at shared edges then resolve
+                                       differently from the reference on 48 rays of the golden fixture */
+};
+
 typedef struct rtb_build_params {
     int32_t builder;      /* RTB_BUILDER_* */
     int32_t ploc_radius;  /* nearest-neighbour search radius, 0 = default (16) */
     int32_t max_leaf_tris;/* 1..3, 0 = default (3) */
-    int32_t _reserved;
+    int32_t collapse;     /* RTB_COLLAPSE_* */
 } rtb_build_params;
 
 typedef struct rtb_bvh_stats {

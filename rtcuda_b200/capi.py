@@ -42,7 +42,7 @@ class SceneDesc(C.Structure):
 
 class BuildParams(C.Structure):
     _fields_ = [("builder", C.c_int32), ("ploc_radius", C.c_int32), ("max_leaf_tris", C.c_int32),
-                ("_reserved", C.c_int32)]
+                ("collapse", C.c_int32)]
 
 
 class BvhStats(C.Structure):

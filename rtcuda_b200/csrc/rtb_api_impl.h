@@ -31,7 +31,7 @@ int guarded(F f) {
 }
 inline rtb_build_params build_defaults() {
     rtb_build_params p;
-    p.builder = RTB_BUILDER_PLOC; p.ploc_radius = 16; p.max_leaf_tris = 3; p._reserved = 0;
+    p.builder = RTB_BUILDER_PLOC; p.ploc_radius = 16; p.max_leaf_tris = 3; p.collapse = RTB_COLLAPSE_LARGEST_FIRST;
     return p;
 }
 }  // namespace rtb

@@ -8,11 +8,19 @@
 //   3. PLOC           parallel locally-ordered clustering (Meister & Bittner
 //                     2018): nearest neighbour within a window of the Morton
 //                     order, merge mutual pairs, compact; repeat to one root
-//   4. collapse       top-down, level-synchronous: pull up to 8 children per
-//                     node (largest surface area opened first), subtrees of
-//                     <= 3 triangles become leaf children, slot assignment
-//                     for octant-ordered traversal, 8-bit quantisation,
-//                     triangles rewritten in leaf order
+//   4. collapse plan  (optional, RTB_COLLAPSE_SAH_OPTIMAL; default is the greedy
+//                     "largest child first" of step 5)
+//                     bottom-up dynamic programme over the binary tree (after
+//                     Ylitie, Karras & Laine 2017): for every subtree, the
+//                     cheapest way (SAH) to lay it out in 1..7 child slots of
+//                     a wide node — one leaf child (<= 3 triangles), one inner
+//                     child (its own wide node), or split between its two
+//                     children; run round by round in PLOC merge order, which
+//                     is a topological order
+//   5. collapse       top-down, level-synchronous: expand each wide node's
+//                     children as the plan says, slot assignment for
+//                     octant-ordered traversal, 8-bit quantisation, triangles
+//                     rewritten in leaf order
 // Bodies are RTB_HD; see rtb_wavefront.h for why.
 #pragma once
 #include "rtb_shade.h"
@@ -178,7 +186,88 @@ RTB_HD void ploc_merge_body(const PlocArgs &a, int n_leaves, int i) {
     (void)n_leaves;
 }
 
-// ------------------------------------------------------------ 4. collapse
+// ------------------------------------------------------------ 4. collapse plan
+// cost[n][i-1], i = 1..7: SAH cost of subtree n laid out in at most i child
+// slots.  plan[n][i-1]: kPlanLeaf / kPlanInner (one slot), k = 1..6 (split:
+// the left child gets k slots, the right one i-k), 0 (same as with i-1
+// slots).  plan[n][7]: how a wide node rooted at n splits its 8 slots.
+constexpr uint8_t kPlanLeaf = 100, kPlanInner = 101;
+struct PlanArgs {
+    const B2Node *nodes;
+    const int32_t *count;
+    float *cost;      // [num binary nodes][7]
+    uint8_t *plan;    // [num binary nodes][8]
+    int32_t first, n; // this launch covers binary nodes first .. first+n-1 (one PLOC round: children are older)
+    int32_t max_leaf;
+};
+RTB_HD void plan_child_costs(const PlanArgs &a, int c, float *d) {
+    const B2Node x = a.nodes[c];
+    if (x.right < 0) {  // a single triangle: a leaf child whatever the slot budget
+        const float v = fmul(b2_half_area(x), kSahTriCost);
+        for (int i = 0; i < 7; ++i) d[i] = v;
+    } else {
+        for (int i = 0; i < 7; ++i) d[i] = a.cost[(size_t)c * 7 + i];
+    }
+}
+RTB_HD void plan_body(const PlanArgs &a, int tid) {
+    if (tid >= a.n) return;
+    const int id = a.first + tid;
+    const B2Node self = a.nodes[id];
+    if (self.right < 0) return;
+    float dl[7], dr[7];
+    plan_child_costs(a, self.left, dl);
+    plan_child_costs(a, self.right, dr);
+    // best split of i slots between the two children, i = 2..8
+    float split[9]; uint8_t split_k[9];
+    for (int i = 2; i <= 8; ++i) {
+        float best = FLT_MAX; int bk = 1;
+        for (int k = 1; k < i; ++k) {
+            if (k > 7 || i - k > 7) continue;
+            const float v = fadd(dl[k - 1], dr[i - k - 1]);
+            if (v < best) { best = v; bk = k; }
+        }
+        split[i] = best; split_k[i] = (uint8_t)bk;
+    }
+    const float area = b2_half_area(self);
+    const int cnt = a.count[id];
+    const float as_inner = ffma(area, kSahNodeCost, split[8]);
+    const float as_leaf = cnt <= a.max_leaf ? fmul(area, fmul(kSahTriCost, (float)cnt)) : FLT_MAX;
+    float *cost = a.cost + (size_t)id * 7;
+    uint8_t *plan = a.plan + (size_t)id * 8;
+    float cur = as_leaf <= as_inner ? as_leaf : as_inner;
+    cost[0] = cur; plan[0] = as_leaf <= as_inner ? kPlanLeaf : kPlanInner;
+    for (int i = 2; i <= 7; ++i) {
+        if (split[i] < cur) { cur = split[i]; plan[i - 1] = split_k[i]; }
+        else plan[i - 1] = 0;
+        cost[i - 1] = cur;
+    }
+    plan[7] = split_k[8];
+}
+// children of the wide node rooted at binary node `root`, as planned; returns their number (<= 8)
+RTB_HD int plan_expand(const B2Node *nodes, const uint8_t *plan, int root, int *ch) {
+    int nc = 0;
+    int st_n[16], st_i[16]; int sp = 0;
+    const B2Node r = nodes[root];
+    const int k8 = plan[(size_t)root * 8 + 7];
+    st_n[sp] = r.right; st_i[sp] = 8 - k8; ++sp;
+    st_n[sp] = r.left; st_i[sp] = k8; ++sp;
+    while (sp) {
+        --sp;
+        const int n = st_n[sp]; int i = st_i[sp];
+        const B2Node x = nodes[n];
+        if (x.right < 0) { ch[nc++] = n; continue; }
+        if (i > 7) i = 7;
+        const uint8_t *pl = plan + (size_t)n * 8;
+        while (i > 1 && pl[i - 1] == 0) --i;
+        const int d = pl[i - 1];
+        if (i == 1 || d == kPlanLeaf || d == kPlanInner) { ch[nc++] = n; continue; }
+        st_n[sp] = x.right; st_i[sp] = i - d; ++sp;
+        st_n[sp] = x.left; st_i[sp] = d; ++sp;
+    }
+    return nc;
+}
+
+// ------------------------------------------------------------ 5. collapse
 struct WorkItem {
     int32_t b2;    // binary node to expand
     int32_t wide;  // index of the 8-wide node to write
@@ -186,6 +275,7 @@ struct WorkItem {
 struct CollapseArgs {
     const B2Node *nodes;
     const int32_t *count;
+    const uint8_t *plan;       // collapse plan, or null: open the largest child first (A/B)
     const Tri48 *tri_in;       // caller order
     const TriMeta *meta_in;    // caller order
     Q4 *nodes8;
@@ -208,9 +298,10 @@ RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
     int ch[8];
     int nc;
     if (a.count[item.b2] <= a.max_leaf) { ch[0] = item.b2; nc = 1; }  // tiny scene: root is one leaf
+    else if (a.plan) { nc = plan_expand(a.nodes, a.plan, item.b2, ch); }
     else { ch[0] = self.left; ch[1] = self.right; nc = 2; }
-    // open the largest child until 8 children or only leaves remain
-    while (nc < 8) {
+    // without a plan: open the largest child until 8 children or only leaves remain
+    while (!a.plan && nc < 8) {
         int best = -1; float best_a = -1.f;
         for (int k = 0; k < nc; ++k) {
             if (a.count[ch[k]] > a.max_leaf) {

@@ -247,8 +247,15 @@ struct Traversal {
         }
     }
     // (2) the accept rule of Triangle::intersect / intersect_leaf (triangle.cuh:49, bvh.cuh:222-248)
-    //     for a candidate whose barycentric test passed; true when an any-hit ray is finished
-    RTB_HD bool accept(int idx, float t, float u, float v) {
+    //     for a candidate whose barycentric test passed; true when an any-hit ray is finished.
+    //     `t <= tmax` with tmax shrinking: on an exact tie (a ray through the shared edge of two
+    //     triangles, bit-identical t) the triangle tested LAST wins, as in the reference.  Which one
+    //     that is depends on the tree; with the default collapse it is the reference's choice on every
+    //     tie of the fixtures (more than a hundred in tests/golden/s1_hits.npz: rays through the wall
+    //     diagonals and corners).  An index-based, tree-independent rule was tried (higher caller index
+    //     wins): it disagrees with the reference on 89 of those rays; the SAH-optimal collapse on 48.
+    RTB_HD bool accept(const Bvh8View &B, int idx, float t, float u, float v) {
+        (void)B;
         if (0.0f < t && t <= tmax) {
             if (ANY) {
                 if (idx != excluded) { found = true; return true; }
@@ -276,14 +283,9 @@ struct Traversal {
             const int idx = (int)(tx + (uint32_t)bit);
             const Tri48 tr = load_tri(B.tris, idx);
             if (COUNT) cnt.tris++;
-            float t, u, v;
-            if (tri_intersect(tr, r.o, r.d, tmax, t, u, v)) {
-                if (ANY) {
-                    if (idx != excluded) { found = true; return false; }
-                } else {
-                    tmax = t; hit.t = t; hit.u = u; hit.v = v; hit.tri = idx; found = true;
-                }
-            }
+            float u, v;
+            const float t = tri_candidate(tr, r.o, r.d, u, v);
+            if (accept(B, idx, t, u, v)) return false;
         }
         return advance(stack_x, stack_y);
     }

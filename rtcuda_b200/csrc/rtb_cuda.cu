@@ -121,7 +121,7 @@ __device__ __forceinline__ void pooled_triangles(WarpScratch &ws, const Bvh8View
         for (int k = 0; k < 3; ++k) {
             if (k < take && has) {
                 const float4 c = ws.res[first + k];
-                if (T.accept(__float_as_int(c.w), c.x, c.y, c.z)) {  // any-hit ray occluded: finished
+                if (T.accept(B, __float_as_int(c.w), c.x, c.y, c.z)) {  // any-hit ray occluded: finished
                     ty = 0u; has = false; pending = true;
                 }
             }
@@ -140,7 +140,7 @@ __device__ __forceinline__ void own_triangles(const Bvh8View &B, Traversal<ANY, 
         const Tri48 tr = load_tri(B.tris, idx);
         float u, v;
         const float t = tri_candidate(tr, T.r.o, T.r.d, u, v);
-        if (T.accept(idx, t, u, v)) { has = false; pending = true; break; }
+        if (T.accept(B, idx, t, u, v)) { has = false; pending = true; break; }
     }
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

@@ -34,6 +34,7 @@ struct PlocLeafK {
 };
 struct PlocNnK { PlocArgs a; RTB_HD void operator()(int i) const { ploc_nn_body(a, i); } };
 struct PlocMergeK { PlocArgs a; int n_leaves; RTB_HD void operator()(int i) const { ploc_merge_body(a, n_leaves, i); } };
+struct PlanK { PlanArgs a; RTB_HD void operator()(int i) const { plan_body(a, i); } };
 struct CollapseK { CollapseArgs a; RTB_HD void operator()(int i) const { collapse_body(a, i); } };
 struct LightFixK {
     LightDev *lights; const int64_t *light_tri; const int32_t *leaf_of_prim; int n;
@@ -234,11 +235,16 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
         be.upload(ctr, init, 4);
     }
     int ncl = n, iters = 0;
+    std::vector<int> round_first, round_count;  // binary nodes created by each PLOC round: ids are handed out in merge order
+    int next_id = n;
     while (ncl > 1) {
         PlocArgs a; a.nodes = b2; a.count = count; a.cin = ca; a.cout = cb; a.nn = nn; a.node_counter = ctr; a.ncl = ncl; a.radius = radius;
         PlocNnK k1; k1.a = a; be.launch(ncl, k1);
         PlocMergeK k2; k2.a = a; k2.n_leaves = n; be.launch(ncl, k2);
+        const int before = ncl;
         ncl = be.compact_nonneg(cb, ca, ncl);
+        round_first.push_back(next_id); round_count.push_back(before - ncl);
+        next_id += before - ncl;
         ++iters;
     }
     int32_t root_b2 = 0;
@@ -246,7 +252,18 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
     sc.stats.ploc_iterations = iters;
     sc.stats.num_bvh2_nodes = n_b2;
     be.free(prim_lo); be.free(prim_hi); be.free(keys); be.free(sorted); be.free(cb); be.free(nn); be.free(ca);
-    // 4. collapse to the 8-wide compressed tree
+    // 4. collapse plan: bottom-up over the binary tree, one launch per PLOC round (a round's nodes only have older children)
+    float *plan_cost = nullptr; uint8_t *plan = nullptr;
+    if (bp.collapse == RTB_COLLAPSE_SAH_OPTIMAL && n > max_leaf) {
+        plan_cost = be.template alloc<float>((size_t)n_b2 * 7);
+        plan = be.template alloc<uint8_t>((size_t)n_b2 * 8);
+        for (size_t r = 0; r < round_first.size(); ++r) {
+            PlanK k; k.a.nodes = b2; k.a.count = count; k.a.cost = plan_cost; k.a.plan = plan;
+            k.a.first = round_first[r]; k.a.n = round_count[r]; k.a.max_leaf = max_leaf;
+            be.launch(round_count[r], k);
+        }
+    }
+    // 5. collapse to the 8-wide compressed tree
     const int max_nodes = n > 1 ? n : 1;
     Q4 *nodes_tmp = be.template alloc<Q4>((size_t)max_nodes * kNodeWords);
     WorkItem *wa = be.template alloc<WorkItem>(max_nodes), *wb = be.template alloc<WorkItem>(max_nodes);
@@ -261,7 +278,7 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
         int32_t zero = 0;
         be.upload(ctr + 3, &zero, 1);
         CollapseK k;
-        k.a.nodes = b2; k.a.count = count; k.a.tri_in = tri_in; k.a.meta_in = meta_in;
+        k.a.nodes = b2; k.a.count = count; k.a.plan = plan; k.a.tri_in = tri_in; k.a.meta_in = meta_in;
         k.a.nodes8 = nodes_tmp; k.a.tris_out = (Tri48 *)sc.tris; k.a.meta_out = sc.meta; k.a.prim_out = sc.prim;
         k.a.leaf_of_prim = sc.leaf_of_prim; k.a.node_counter = ctr + 1; k.a.tri_counter = ctr + 2;
         k.a.work_in = wa; k.a.n_in = n_in; k.a.work_out = wb; k.a.n_out = ctr + 3; k.a.sah = sah; k.a.max_leaf = max_leaf;
@@ -279,7 +296,7 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
     if (c4[2] != n) throw Error(RTB_ERR_INVALID, "internal: collapse lost triangles");
     sc.nodes8 = be.template alloc<Q4>((size_t)sc.num_nodes * kNodeWords);
     be.copy(sc.nodes8, nodes_tmp, (size_t)sc.num_nodes * kNodeWords);
-    be.free(nodes_tmp); be.free(wa); be.free(wb);
+    be.free(nodes_tmp); be.free(wa); be.free(wb); be.free(plan_cost); be.free(plan);
     if (sc.num_lights > 0) {
         LightFixK k; k.lights = sc.lights; k.light_tri = d_light_tri; k.leaf_of_prim = sc.leaf_of_prim; k.n = sc.num_lights;
         be.launch(sc.num_lights, k);

@@ -153,6 +153,27 @@ def test_slab_test_pads_each_axis_on_its_own(s1_dev, s1_orc):
     assert max(counts) <= counts[0] + 2, counts
 
 
+def test_sah_optimal_collapse_is_a_valid_smaller_tree(L, ctx, s1, s1_dev, s1_orc):
+    """rtb_build_params.collapse = RTB_COLLAPSE_SAH_OPTIMAL (dynamic programme over the binary tree): fewer 8-wide nodes
+    and a lower SAH cost than the default greedy collapse, the same hits — except on exact-t ties (a ray through the
+    shared edge of two triangles), where either triangle is a correct answer and the choice follows the test order"""
+    bp = capi.BuildParams()
+    L.lib.rtb_build_params_default(C.byref(bp))
+    assert bp.collapse == 0
+    bp.collapse = 1
+    sc = ctx.scene(s1.desc, bp)
+    a, b = sc.stats(), s1_dev.stats()
+    assert a.num_nodes < 0.8 * b.num_nodes and a.sah_cost <= b.sah_cost
+    rays = np.concatenate([L.primary_rays(s1.camera(1.0), 300, 300), random_rays(100000, seed=9)])
+    hits, ref = sc.trace_closest(rays), s1_orc.trace_closest(rays, capi.HIT_DTYPE)
+    diff = hits["prim"] != ref["prim"]
+    assert (hits["t"].view(np.uint32) == ref["t"].view(np.uint32)).all()  # t is bit-exact everywhere
+    assert diff.sum() <= 1e-3 * len(rays)  # ties only
+    occ = sc.trace_any(rays[:50000])
+    assert (occ == s1_orc.trace_any(rays[:50000])).all()
+    sc.close()
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 9, 33, 200])
 def test_small_and_empty_scenes(L, ctx, oracle, n):
     """empty, single-triangle and ragged triangle counts; degenerate (zero-area) triangles included"""
