@@ -3,14 +3,18 @@
 //
 // Kernels (all plain SIMT; nothing on this path is a dense contraction, so
 // no tensor cores):
-//   k_extend / k_shadow   persistent traversal kernels: grid = SMs x resident
-//                         blocks, each warp claims 32 queue entries with one
-//                         atomicAdd (lane 0) and a shuffle broadcast
-//                         (replaces kernels ch / ah, render.cuh:278-328, which
-//                         launch one thread per ray in 64-thread blocks)
-//   k_shade<type>         grid-stride over one material queue (replaces mat +
-//                         init, render.cuh:84-248)
-//   k_generate            grid-stride over the free-slot queue (gen, :250-275)
+//   k_trace<which, pool>  persistent traversal kernel for the extend (closest
+//                         hit) and shadow (any hit) rays of one iteration:
+//                         grid = SMs x resident blocks, a warp claims 128 queue
+//                         entries with one atomicAdd (lane 0) and a shuffle
+//                         broadcast and refills idle lanes while the others
+//                         keep traversing; triangle tests pooled per warp in
+//                         shared memory on large scenes (replaces kernels ch /
+//                         ah, render.cuh:278-328, which launch one thread per
+//                         ray in 64-thread blocks)
+//   k_shade<type>         grid-stride over one material queue, writes the next
+//                         rays in place (replaces mat + init, render.cuh:84-248)
+//   k_generate            new camera paths behind the shaded ones (gen, :250-275)
 //   k_control             single-thread queue bookkeeping; raises `done` in
 //                         mapped host memory (replaces the four blocking
 //                         4-byte device->host copies per iteration,
@@ -283,7 +287,7 @@ struct CudaBackend {
     cudaStream_t streams_[kMaxPipelines] = {nullptr, nullptr};
     cudaEvent_t sync_ev_ = nullptr;
     int pipelines_ = 2;  // RTB_PIPELINES: concurrent wavefronts per render (1 or 2)
-    int blocks_trace_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_shade4_[3] = {0, 0, 0}, blocks_generate_ = 0, shade_occ_ = 3;
+    int blocks_trace_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_generate_ = 0;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
@@ -336,13 +340,6 @@ struct CudaBackend {
         blocks_shade_[1] = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<2>, kBlock, 0));
         blocks_shade_[2] = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<0, 4>, kBlock, 0));
-        blocks_shade4_[0] = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<1, 4>, kBlock, 0));
-        blocks_shade4_[1] = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<2, 4>, kBlock, 0));
-        blocks_shade4_[2] = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        if (const char *e = getenv("RTB_SHADE_OCC")) shade_occ_ = atoi(e);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate, kBlock, 0));
         blocks_generate_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
     }
@@ -400,11 +397,6 @@ struct CudaBackend {
             if (k.type == 0) k_shade<0, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else if (k.type == 1) k_shade<1, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else k_shade<2, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-        } else if (shade_occ_ == 4) {  // tuning: 64 registers (small spills), 4 blocks per SM
-            const int g4 = blocks_shade4_[k.type];
-            if (k.type == 0) k_shade<0, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else if (k.type == 1) k_shade<1, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else k_shade<2, 4><<<g4, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         } else {
             if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);

@@ -1,4 +1,4 @@
-"""Tuning sweep over the persistent-kernel knobs (RTB_REFILL / RTB_CHUNK / RTB_POOL / RTB_POOLED / RTB_FUSED / RTB_PREFETCH / RTB_SHADE_OCC are read
+"""Tuning sweep over the persistent-kernel knobs (RTB_REFILL / RTB_CHUNK / RTB_POOL / RTB_POOLED / RTB_FUSED / RTB_PREFETCH are read
 when a context is created), one process, one scene build per setting.
 
     python tools/sweep.py --workload c2 --refill 8,16,24 --pooled 0,1 --fused 0,1 --chunk 128 --pool 8388608
@@ -24,7 +24,6 @@ ap.add_argument("--pool", default="33554432")
 ap.add_argument("--pooled", default="-1")
 ap.add_argument("--fused", default="1")
 ap.add_argument("--prefetch", default="1")
-ap.add_argument("--shade-occ", default="3")
 ap.add_argument("--pipelines", default="2")
 ap.add_argument("--first-sample", type=int, default=0)
 ap.add_argument("--device", type=int, default=0)
@@ -40,9 +39,9 @@ L = capi.Lib()
 hs = L.host_scene(kind, *L.load_mesh(), grid=grid)
 cam = hs.camera(w / h)
 print(f"workload {a.workload}: {hs.desc.num_triangles} triangles, {w}x{h}x{spp}spp depth {depth}")
-for refill, chunk, pool, pooled, fused, pf, occ, pipes in itertools.product(a.refill.split(","), a.chunk.split(","), a.pool.split(","), a.pooled.split(","),
-                                                                 a.fused.split(","), a.prefetch.split(","), a.shade_occ.split(","), a.pipelines.split(",")):
-    os.environ.update(RTB_REFILL=refill, RTB_CHUNK=chunk, RTB_POOL=pool, RTB_POOLED=pooled, RTB_FUSED=fused, RTB_PREFETCH=pf, RTB_SHADE_OCC=occ, RTB_PIPELINES=pipes)
+for refill, chunk, pool, pooled, fused, pf, pipes in itertools.product(a.refill.split(","), a.chunk.split(","), a.pool.split(","), a.pooled.split(","),
+                                                                 a.fused.split(","), a.prefetch.split(","), a.pipelines.split(",")):
+    os.environ.update(RTB_REFILL=refill, RTB_CHUNK=chunk, RTB_POOL=pool, RTB_POOLED=pooled, RTB_FUSED=fused, RTB_PREFETCH=pf, RTB_PIPELINES=pipes)
     ctx = L.context(a.device)
     bp = capi.BuildParams()
     L.lib.rtb_build_params_default(C.byref(bp))
@@ -58,7 +57,7 @@ for refill, chunk, pool, pooled, fused, pf, occ, pipes in itertools.product(a.re
         if best is None or st.ms_total < best.ms_total:
             best = st
     rays = best.extend_rays + best.shadow_rays
-    print(f"pipes {best.pipelines} pooled {pooled} fused {best.fused_trace} pf {pf} occ {occ} refill {refill:>2} chunk {chunk:>4} pool {pool:>9}: {best.ms_total:8.2f} ms  trace/extend {best.ms_extend:7.2f} "
+    print(f"pipes {best.pipelines} pooled {pooled} fused {best.fused_trace} pf {pf} refill {refill:>2} chunk {chunk:>4} pool {pool:>9}: {best.ms_total:8.2f} ms  trace/extend {best.ms_extend:7.2f} "
           f"shadow {best.ms_shadow:7.2f} shade {best.ms_shade:6.2f} other {best.ms_other:6.2f}  {rays / best.ms_total * 1e-3:8.1f} Mrays/s  "
           f"iters {best.iterations}  build {bs.build_ms:.1f} ms nodes {bs.num_nodes} sah {bs.sah_cost:.2f} mean {img.mean():.4f}", flush=True)
     if a.count:
