@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -284,6 +284,17 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # nvidia-smi needs ~0.1-0.3 s before its first sample and a timed region can be that short: keep the GPU under the
+    # same load (untimed steps, every rank alike) until the sampler is running, so that the samples are taken under load
+    t_spin = time.perf_counter()
+    step()
+    torch.cuda.synchronize()
+    n_extra = torch.tensor([max(0, min(32, int(0.6 / max(time.perf_counter() - t_spin, 1e-3))))], device="cuda")
+    if world > 1:
+        dist.broadcast(n_extra, src=0)  # every rank runs the same number of steps (each holds an all-reduce)
+    for _ in range(int(n_extra.item())):
+        step()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stats = []
     for k in range(args.steps):
