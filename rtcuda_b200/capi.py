@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(HERE, "librtb.so")
+DEFAULT_LIB = os.environ.get("RTB_LIB") or os.path.join(HERE, "librtb.so")  # RTB_LIB: A/B builds (tuning runs only)
 BUNNY_BIN = os.path.join(HERE, "data", "bunny.rtbm")
 
 RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2 = 1, 2, 3
