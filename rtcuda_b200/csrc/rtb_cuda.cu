@@ -73,6 +73,7 @@ struct FetchTuning {
     int refill;    // refill idle lanes when fewer than this many lanes hold a live ray
     int chunk;     // queue entries a warp claims with one atomicAdd
     int prefetch;  // prefetch a claimed chunk's rays into L2
+    int tri_step;  // own-lane triangle tests: 0 = all of a node's triangles at once, k = at most k per step (the rest carries over)
 };
 
 // Pooled triangle tests (POOL).  ncu r1 (profiles/r1_ncu_full_big_launches_session6.txt and the
@@ -160,6 +161,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
     bool has = false, exhausted = false, pending = false;
     int qi = 0;
     int chunk_next = 0, chunk_end = 0;  // warp-uniform: the part of the queue this warp has claimed
+    uint32_t tx = 0u, ty = 0u;          // triangles of the current node still to test: base | bits
     while (true) {
         // results of the rays that finished since the last refill are written here, together, so
         // that the hit-record / atomic code runs with many lanes instead of one at a time
@@ -213,7 +215,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                         ws.ro[lane] = make_float4(o.x, o.y, o.z, 0.f);
                         ws.rd[lane] = make_float4(d.x, d.y, d.z, 0.f);
                         T.init(xyz(o), xyz(d), o.w, f2i(d.w));
-                        qi = idx; has = true;
+                        qi = idx; has = true; ty = 0u;
                     }
                 } else {
                     const F4 a = ldg(W.ea + idx);
@@ -222,7 +224,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                         ws.ro[lane] = make_float4(a.x, a.y, a.z, a.w);
                         ws.rd[lane] = make_float4(b.x, b.y, b.z, b.w);
                         T.init(xyz(a), xyz(b), FLT_MAX, -1);
-                        qi = idx; has = true;
+                        qi = idx; has = true; ty = 0u;
                     }
                 }
             }
@@ -236,11 +238,31 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
         }
         const int keep_going = exhausted ? 1 : tune.refill;
         do {
-            uint32_t tx = 0u, ty = 0u;
-            if (has) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
-            if (POOL) pooled_triangles<ANY>(ws, S.bvh, T, tx, ty, has, pending, lane, lanes_below);
-            else own_triangles<ANY>(S.bvh, T, tx, ty, has, pending);
-            if (has && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
+            if (!POOL && tune.tri_step > 0) {
+                // stepped: at most tri_step triangle tests per lane and step; a lane with more keeps them for
+                // the next steps and sits out the node phase meanwhile (its own order of events is unchanged:
+                // the next node is fetched only once all triangles of the current one are tested), so one
+                // lane's long triangle list no longer idles the rest of the warp
+                if (has && ty == 0u) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+#pragma unroll 1
+                for (int k = 0; k < tune.tri_step && ty != 0u; ++k) {
+                    const int bit = 31 - __clz(ty);
+                    ty &= ~(1u << bit);
+                    const int idx = (int)(tx + (uint32_t)bit);
+                    const Tri48 tr = load_tri(S.bvh.tris, idx);
+                    float u, v;
+                    const float t = tri_candidate(tr, T.r.o, T.r.d, u, v);
+                    if (T.accept(S.bvh, idx, t, u, v)) { has = false; pending = true; ty = 0u; }
+                }
+                if (has && ty == 0u && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
+            } else {
+                tx = 0u; ty = 0u;
+                if (has) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+                if (POOL) pooled_triangles<ANY>(ws, S.bvh, T, tx, ty, has, pending, lane, lanes_below);
+                else own_triangles<ANY>(S.bvh, T, tx, ty, has, pending);
+                ty = 0u;
+                if (has && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
+            }
             act = __ballot_sync(0xffffffffu, has);
         } while (__popc(act) >= keep_going);
     }
@@ -248,8 +270,9 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
 // extend and shadow rays of one iteration in ONE launch (WHICH = 3): a warp that runs out of extend
 // rays goes on with shadow rays, so the tail of the first queue overlaps the start of the second.
 // WHICH = 1 / 2: extend / shadow only (A/B, and per-stage timing).
-// POOL is chosen by scene size (CudaBackend::use_pooled): pooled triangle tests win when triangle fetches
-// miss L2 (10 M triangles: 116 vs 123 ms), each lane on its own wins when everything hits in cache (C2: 46.2 vs 47.9 ms).
+// Triangle tests, three schedules (profiles/README.md): each lane walks all the triangles of its node at once
+// (tri_step 0); at most tri_step per step, the rest carried over (default, 2: C2 39.5 -> 39.1 ms, C3 116.5 ->
+// 108.9 ms); pooled per warp in shared memory (POOL, RTB_POOLED=1: C3 113.5 ms, C2 47.9 ms).
 // Tried and dropped: prefetching the next node into L2 during the triangle tests (C3 116 -> 140 ms, C2 40 -> 49 ms).
 template <int WHICH, bool POOL>
 __global__ void __launch_bounds__(kBlock, 4) k_trace(WaveState W, SceneView S, FetchTuning tune) {
@@ -292,8 +315,8 @@ struct CudaBackend {
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
     int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
-    FetchTuning tune_{24, 128, 1};  // RTB_REFILL / RTB_CHUNK / RTB_PREFETCH override (tuning runs)
-    int pooled_ = -1;  // RTB_POOLED: pooled triangle tests (1), each ray's lane on its own (0), by scene size (-1)
+    FetchTuning tune_{24, 128, 1, 2};  // RTB_REFILL / RTB_CHUNK / RTB_PREFETCH override (tuning runs)
+    int pooled_ = 0;  // RTB_POOLED: pooled triangle tests (1), each ray's lane on its own (0, default), by scene size (-1)
     int fused_ = 1;   // RTB_FUSED: extend + shadow rays of one iteration in one launch
     int pool_ = 1 << 25;    // default path pool, RTB_POOL overrides (tuning)
 
@@ -328,6 +351,7 @@ struct CudaBackend {
         if (const char *e = getenv("RTB_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tune_.refill = v; }
         if (const char *e = getenv("RTB_CHUNK")) { int v = atoi(e); if (v >= 32) tune_.chunk = v; }
         if (const char *e = getenv("RTB_PREFETCH")) tune_.prefetch = atoi(e);
+        if (const char *e = getenv("RTB_TRI_STEP")) tune_.tri_step = atoi(e);
         if (const char *e = getenv("RTB_POOLED")) pooled_ = atoi(e);
         if (const char *e = getenv("RTB_FUSED")) fused_ = atoi(e);
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }

@@ -359,7 +359,8 @@ def test_pool_size_does_not_change_the_image(L, s1, s1_dev):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [
-    {"RTB_POOLED": "0", "RTB_PIPELINES": "1", "RTB_FUSED": "0"},  # each lane tests its own triangles, extend and shadow launches apart
+    {"RTB_POOLED": "0", "RTB_PIPELINES": "1", "RTB_FUSED": "0", "RTB_TRI_STEP": "0"},  # each lane walks all its triangles, extend and shadow launches apart
+    {"RTB_POOLED": "0", "RTB_PIPELINES": "2", "RTB_FUSED": "1", "RTB_TRI_STEP": "1"},  # one triangle per lane and step, the rest carried over
     {"RTB_POOLED": "1", "RTB_PIPELINES": "1", "RTB_FUSED": "1"},  # pooled triangle tests (shared memory), one trace launch
     {"RTB_POOLED": "1", "RTB_PIPELINES": "2", "RTB_FUSED": "1", "RTB_CHUNK": "32", "RTB_REFILL": "32"},
     {"RTB_POOLED": "0", "RTB_PIPELINES": "2", "RTB_FUSED": "1", "RTB_PREFETCH": "0", "RTB_REFILL": "1"},
