@@ -172,11 +172,11 @@ RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
 
 // ------------------------------------------------------------ shade
 // init + mat (render.cuh:84-248) for entry `tid` of hit queue `type`
+// one hit record (a, b, hr = its three words, already loaded) of hit queue TYPE, entry tid
 template <int TYPE, bool EXT = true>
-RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConsts &rc, bool shadows, int tid, ShadeTally &tally) {
-    const int type = TYPE;
-    const int q = type * W.pool + tid;
-    const F4 a = ldg(W.ma + q), b = ldg(W.mb + q), hr = ldg(W.mc + q);
+RTB_HD void shade_item(const WaveState &W, const SceneView &S, const RenderConsts &rc, bool shadows, int tid, const F4 &a,
+                       const F4 &b, const F4 &hr, ShadeTally &tally) {
+    const int q = TYPE * W.pool + tid;
     PathStepIn in;
     in.wo = xyz(a);
     in.hit.t = 0.f; in.hit.u = hr.y; in.hit.v = hr.z; in.hit.tri = f2i(hr.w);
@@ -222,6 +222,12 @@ RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConst
     }
     tally.extend += out.extend ? 1u : 0u;
     tally.shadow += out.shadow ? 1u : 0u;
+}
+template <int TYPE, bool EXT = true>
+RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConsts &rc, bool shadows, int tid, ShadeTally &tally) {
+    const int q = TYPE * W.pool + tid;
+    const F4 a = ldg(W.ma + q), b = ldg(W.mb + q), hr = ldg(W.mc + q);
+    shade_item<TYPE, EXT>(W, S, rc, shadows, tid, a, b, hr, tally);
 }
 
 // ------------------------------------------------------------ shadow
