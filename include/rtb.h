@@ -258,6 +258,13 @@ RTB_API int rtb_render_accumulate(rtb_scene *scene, const rtb_camera *cam,
 RTB_API int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t num_floats,
                                int32_t total_spp, float *d_out);
 
+/* Feature buffers of the primary hits, one camera ray through every pixel centre (what a denoiser wants next to the
+ * radiance; SURVEY 8f-4 — the reference has nothing of the kind): albedo of the hit material (float[3*W*H]), geometric
+ * unit normal turned towards the camera (float[3*W*H]), hit distance (float[W*H], 0 for a miss) and triangle index in
+ * the caller's list (int32[W*H], -1 for a miss).  Any pointer may be NULL.  Row 0 = top, like rtb_render. */
+RTB_API int rtb_render_aovs(rtb_scene *scene, const rtb_camera *cam, int32_t width, int32_t height,
+                            float *h_albedo, float *h_normal, float *h_depth, int32_t *h_prim);
+
 /* ---- host-side scene I/O and procedural scenes (host C++, no GPU work) ---- */
 typedef struct rtb_host_scene rtb_host_scene; /* owns the arrays a rtb_scene_desc points to */
 /* ASCII PLY (what main.cu:60-62 reads through happly.h:1289,1451,1498) */

@@ -76,7 +76,7 @@ SYMBOLS = [
     "rtb_last_error", "rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_context_device",
     "rtb_build_params_default", "rtb_scene_create", "rtb_scene_create_from_primitives", "rtb_scene_destroy",
     "rtb_scene_stats", "rtb_trace_closest", "rtb_trace_any", "rtb_trace_closest_device", "rtb_trace_any_device",
-    "rtb_trace_closest_counts", "rtb_camera_look_at", "rtb_camera_primary_rays", "rtb_render_params_default",
+    "rtb_trace_closest_counts", "rtb_render_aovs", "rtb_camera_look_at", "rtb_camera_primary_rays", "rtb_render_params_default",
     "rtb_render", "rtb_render_accumulate", "rtb_tonemap_device", "rtb_mesh_load_ply", "rtb_mesh_load_bin",
     "rtb_mesh_save_bin", "rtb_free", "rtb_host_scene_build", "rtb_host_scene_desc", "rtb_host_scene_camera",
     "rtb_host_scene_destroy", "rtb_scene_desc_save", "rtb_host_scene_load", "rtb_write_ppm",
@@ -252,6 +252,14 @@ class Scene:
         self.L.check(self.L.lib.rtb_trace_closest_counts(self.h, rays.ctypes.data_as(C.c_void_p),
                                                          C.c_int64(len(rays)), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def render_aovs(self, cam, width, height):
+        """primary-hit feature buffers: (albedo[h,w,3], normal[h,w,3], depth[h,w], prim[h,w])"""
+        al = np.zeros((height, width, 3), np.float32); no = np.zeros((height, width, 3), np.float32)
+        de = np.zeros((height, width), np.float32); pr = np.zeros((height, width), np.int32)
+        self.L.check(self.L.lib.rtb_render_aovs(self.h, C.byref(cam), width, height, al.ctypes.data_as(C.c_void_p),
+                                                no.ctypes.data_as(C.c_void_p), de.ctypes.data_as(C.c_void_p), pr.ctypes.data_as(C.c_void_p)))
+        return al, no, de, pr
 
     def render(self, cam, params):
         out = np.zeros((params.height, params.width, 3), dtype=np.float32)

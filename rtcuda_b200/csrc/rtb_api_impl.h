@@ -195,6 +195,29 @@ int rtb_camera_primary_rays(const rtb_camera *cam, int32_t w, int32_t h, rtb_ray
     return RTB_OK;
 }
 
+int rtb_render_aovs(rtb_scene *s, const rtb_camera *cam, int32_t w, int32_t h, float *h_albedo, float *h_normal, float *h_depth,
+                    int32_t *h_prim) {
+    if (!s || !cam || w <= 0 || h <= 0 || (int64_t)w * h > 0x7fffffff) return rtb::set_error(RTB_ERR_INVALID, "rtb_render_aovs: bad arguments");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = s->ctx->be;
+        be.make_current();
+        const size_t n = (size_t)w * (size_t)h;
+        rtb::AovK k;
+        k.S = s->impl->view(); k.cam = *cam; k.width = w; k.height = h;
+        k.albedo = h_albedo ? be.template alloc<float>(3 * n) : nullptr;
+        k.normal = h_normal ? be.template alloc<float>(3 * n) : nullptr;
+        k.depth = h_depth ? be.template alloc<float>(n) : nullptr;
+        k.prim = h_prim ? be.template alloc<int32_t>(n) : nullptr;
+        be.launch_trace((int)n, k);
+        if (h_albedo) be.download(h_albedo, k.albedo, 3 * n);
+        if (h_normal) be.download(h_normal, k.normal, 3 * n);
+        if (h_depth) be.download(h_depth, k.depth, n);
+        if (h_prim) be.download(h_prim, k.prim, n);
+        be.sync();
+        be.free(k.albedo); be.free(k.normal); be.free(k.depth); be.free(k.prim);
+    });
+}
+
 int rtb_render_accumulate(rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, float *d_accum, rtb_render_stats *stats) {
     if (!s || !cam || !p) return rtb::set_error(RTB_ERR_INVALID, "rtb_render_accumulate: null argument");
     return rtb::guarded([&] {

@@ -110,6 +110,30 @@ struct TraceAnyK {
     }
 };
 
+// primary-hit feature buffers (rtb_render_aovs)
+struct AovK {
+    SceneView S; rtb_camera cam; int32_t width, height;
+    float *albedo, *normal, *depth; int32_t *prim;
+    RTB_HD void operator()(int i) const {
+        if (i >= width * height) return;
+        V3 o, d;
+        camera_ray(cam, fdiv(fadd((float)(i % width), 0.5f), (float)width), fdiv(fadd((float)(i / width), 0.5f), (float)height), o, d);
+        HitRec h;
+        bvh8_trace<false, false>(S.bvh, o, d, FLT_MAX, -1, h, nullptr);
+        V3 al = v3(0.f), n = v3(0.f);
+        if (h.tri >= 0) {
+            const rtb_material m = S.materials[S.tri_meta[h.tri].material & 0xffffff];
+            al = v3(m.albedo[0], m.albedo[1], m.albedo[2]);
+            n = vneg(vnormalize(tri_n(load_tri(S.bvh.tris, h.tri))));  // the shading normal of render.cuh:153
+            if (vdot(n, d) > 0.f) n = vneg(n);
+        }
+        if (albedo) { albedo[3 * (size_t)i] = al.x; albedo[3 * (size_t)i + 1] = al.y; albedo[3 * (size_t)i + 2] = al.z; }
+        if (normal) { normal[3 * (size_t)i] = n.x; normal[3 * (size_t)i + 1] = n.y; normal[3 * (size_t)i + 2] = n.z; }
+        if (depth) depth[i] = h.tri >= 0 ? h.t : 0.f;
+        if (prim) prim[i] = h.tri >= 0 ? S.bvh.prim[h.tri] : -1;
+    }
+};
+
 // ---- scene ----
 constexpr int kMaxPipelines = 2;
 template <class BE>

@@ -332,6 +332,29 @@ def test_environment_light_reaches_open_scenes_only_through_misses(L, s1, s1_dev
     assert mean_rel_err(lin(e2) - lin(base), 2 * (lin(e1) - lin(base))) <= 1e-4
 
 
+def test_primary_hit_feature_buffers(L, s1, s1_dev, s1_orc):
+    """rtb_render_aovs: albedo / normal / depth / triangle index of the pixel-centre primary hits, against the oracle's
+    hits and the scene arrays"""
+    w, h = 96, 64
+    cam = s1.camera(w / h)
+    al, no, de, pr = s1_dev.render_aovs(cam, w, h)
+    rays = L.primary_rays(cam, w, h)
+    ref = s1_orc.trace_closest(rays, capi.HIT_DTYPE)
+    assert (pr.ravel() == ref["prim"]).all()
+    assert (de.ravel().view(np.uint32) == ref["t"].view(np.uint32)).all()
+    arr = s1.arrays()
+    hit = ref["prim"] >= 0
+    V = arr["vertices"].reshape(-1, 3, 3)[ref["prim"][hit]].astype(np.float64)
+    n = -np.cross(V[:, 0] - V[:, 1], V[:, 2] - V[:, 0])
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    flip = (n * rays["dir"][hit]).sum(1) > 0
+    n[flip] *= -1
+    assert np.abs(no.reshape(-1, 3)[hit] - n).max() < 1e-5
+    assert (no.reshape(-1, 3)[~hit] == 0).all() and (al.reshape(-1, 3)[~hit] == 0).all()
+    mats = np.array([[0.65, 0.05, 0.05], [0.12, 0.45, 0.15], [0.73, 0.73, 0.73], [0.62, 0.57, 0.54]], np.float32)  # main.cu:42-45
+    assert np.allclose(al.reshape(-1, 3)[hit], mats[arr["material_ids"][ref["prim"][hit]]])
+
+
 def test_sample_pass_sharding_is_additive(L, s1, s1_dev):
     """the multi-GPU decomposition: samples [0,a) + [a,a+b) == samples [0,a+b) (per-pixel RNG keyed by sample index)"""
     cam = s1.camera(1.0)
