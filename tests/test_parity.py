@@ -332,6 +332,33 @@ def test_environment_light_reaches_open_scenes_only_through_misses(L, s1, s1_dev
     assert mean_rel_err(lin(e2) - lin(base), 2 * (lin(e1) - lin(base))) <= 1e-4
 
 
+def test_render_edge_cases(L, ctx, oracle, s1, s1_dev, s1_orc):
+    """empty scene, scene without lights, 1x1 image, one sample, depth 0, image sizes changing between calls on one scene,
+    a second context alive at the same time"""
+    cam = L.camera_look_at((0.5, 0.5, 1.5), (0.5, 0.5, 0.0), (0, 1, 0), 37.8, 1.0)
+    empty, keep0 = make_desc(np.zeros((0, 9), np.float32), np.zeros(0, np.int32), np.zeros(0, np.int32), std_materials(), [])
+    sc0 = ctx.scene(empty)
+    img, st = sc0.render(cam, capi.render_params(L, width=8, height=4, spp=3, max_bounces=5))
+    assert (img == 0).all() and st.paths == 96 and st.extend_rays == 96 and st.shadow_rays == 0
+    img, st = sc0.render(cam, capi.render_params(L, width=8, height=4, spp=3, max_bounces=5, env_L=(4.0, 1.0, 0.25)))
+    assert np.allclose(img, np.array([2.0, 1.0, 0.5], np.float32))  # sqrt(env): every camera ray leaves the scene
+    verts, mat, lid = small_scene_arrays(seed=2, n=40)
+    dark, keep1 = make_desc(verts, mat, np.full(len(mat), -1, np.int32), std_materials(), [])
+    sc1, osc1 = ctx.scene(dark), oracle.scene(dark)
+    img, st, ref, ost = render_pair(L, sc1, osc1, cam, width=33, height=17, spp=2, max_bounces=6)
+    assert (img == 0).all() and (ref == 0).all() and st.shadow_rays == 0 and st.extend_rays == ost[1]
+    ctx2 = L.context(0)
+    sc2 = ctx2.scene(s1.desc)
+    for (w, h, spp, depth) in ((1, 1, 1, 1), (1, 1, 5, 0), (7, 3, 1, 12), (64, 2, 2, 3), (2, 64, 2, 3)):
+        c = s1.camera(w / h)
+        a, sa, r, so = render_pair(L, s1_dev, s1_orc, c, width=w, height=h, spp=spp, max_bounces=depth)
+        b, sb = sc2.render(c, capi.render_params(L, width=w, height=h, spp=spp, max_bounces=depth))
+        assert sa.paths == so[0] == w * h * spp and sa.extend_rays == sb.extend_rays
+        assert mean_rel_err(a, r) <= IMAGE_TOL or np.abs(r).max() == 0
+        assert mean_rel_err(a, b) <= 1e-5 or np.abs(b).max() == 0
+    sc2.close(); sc1.close(); sc0.close()
+
+
 def test_primary_hit_feature_buffers(L, s1, s1_dev, s1_orc):
     """rtb_render_aovs: albedo / normal / depth / triangle index of the pixel-centre primary hits, against the oracle's
     hits and the scene arrays"""
