@@ -416,7 +416,7 @@ def main():
                            "sharding": "sample pass per rank, scene replicated, NCCL all-reduce of the accumulation buffer" if world > 1 else "single GPU",
                            "pool_size": pool_used,
                            "l2": "256 MB device memset between timed steps (L2 flush); the ray / hit queues (%.1f GB) are streamed every iteration"
-                                 % (pool_used * 240 / 1e9)},
+                                 % (pool_used * 288 / 1e9)},
                 "ms_per_spp": ms_per_step / total_spp * (1 if strong else world), "paths_per_step": int(stats[0].paths) * world,
                 "rays_per_step": rays_total.item() / args.steps,
                 "iterations_per_step": int(stats[0].iterations), "pipelines": int(stats[0].pipelines),

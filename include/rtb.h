@@ -37,8 +37,9 @@ typedef enum rtb_status {
     RTB_ERR_OOM = -5
 } rtb_status;
 
-/* material.cuh:4-8 */
-enum { RTB_MATTE = 0, RTB_MIRROR = 1, RTB_GLASS = 2 };
+/* material.cuh:4-8, plus RTB_GLOSSY which the reference does not have (SURVEY 8f-3 "a real glossy BSDF"): an
+ * energy-normalised Phong lobe around the mirror direction, albedo = specular colour, `ior` = Phong exponent */
+enum { RTB_MATTE = 0, RTB_MIRROR = 1, RTB_GLASS = 2, RTB_GLOSSY = 3 };
 /* light.cuh:4-7 */
 enum { RTB_POINT_LIGHT = 0, RTB_AREA_LIGHT = 1 };
 
@@ -280,7 +281,8 @@ RTB_API void rtb_free(void *p);
 enum {
     RTB_SCENE_S1 = 1,  /* main.cu:41-148 Cornell box + bunny, all matte (configs C1, C2) */
     RTB_SCENE_S1_MIXED = 2, /* same geometry, MATTE/MIRROR/GLASS round-robin by triangle index (C4) */
-    RTB_SCENE_S2 = 3   /* Cornell shell + grid x grid bunny instances, ~10M triangles at grid=12 (C3, C5) */
+    RTB_SCENE_S2 = 3,  /* Cornell shell + grid x grid bunny instances, ~10M triangles at grid=12 (C3, C5) */
+    RTB_SCENE_S1_GLOSSY = 4 /* S1 geometry, the bunny RTB_GLOSSY (exponent 50), the x = 1 wall RTB_GLOSSY (exponent 400) */
 };
 RTB_API int rtb_host_scene_build(int32_t kind, const float *mesh_verts, int64_t num_verts,
                                  const int32_t *mesh_faces, int64_t num_faces, int32_t grid,

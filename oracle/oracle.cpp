@@ -328,9 +328,40 @@ Vec3 sample_sphere(float u1, float u2) {  // utility.cuh:70-77
     return V(r * cs, r * sn, z);
 }
 
+// ---- RTB_GLOSSY: not in the reference (rtb.h); an energy-normalised Phong lobe around the mirror direction ----
+void onb(Vec3 n, Vec3 &t, Vec3 &b) {  // Duff et al. 2017
+    float sg = copysignf(1.f, n.z);
+    float a = -1.f / (sg + n.z);
+    float c = n.x * n.y * a;
+    t = V(fmaf(sg * (n.x * n.x), a, 1.f), sg * c, -sg * n.x);
+    b = V(c, fmaf(n.y * n.y, a, sg), -n.y);
+}
+void glossy_eval(const rtb_material &m, Vec3 wo, Vec3 n, Vec3 wi, Vec3 &f, float &pdf) {
+    float ca = dot_dev(reflect(wo, n), wi);
+    if (ca <= 0.f) { f = V(0, 0, 0); pdf = 0.f; return; }
+    float lobe = powf(ca, m.ior) * 0.15915494309189535f;
+    pdf = (m.ior + 1.f) * lobe;
+    f = V(m.albedo[0], m.albedo[1], m.albedo[2]) * ((m.ior + 2.f) * lobe);
+}
+
 // material.cuh:60-109
 Vec3 sample_f(const rtb_material &m, Vec3 wo, float u1, float u2, Vec3 &n, Vec3 &wi, float &pdf) {
     Vec3 albedo = V(m.albedo[0], m.albedo[1], m.albedo[2]);
+    if (m.type == RTB_GLOSSY) {
+        if (dot_dev(wo, n) > 0.f) n = -n;
+        Vec3 r = reflect(wo, n);
+        float e = m.ior;
+        float ca = powf(u1, 1.f / (e + 1.f));
+        float sa = sqrtf(fmaxf(0.f, 1.f - ca * ca));
+        float sp, cp;
+        sincosf(TWO_PI_F * u2, &sp, &cp);
+        Vec3 t, b;
+        onb(r, t, b);
+        wi = (t * (sa * cp) + b * (sa * sp)) + r * ca;
+        float lobe = powf(ca, e) * 0.15915494309189535f;
+        pdf = (e + 1.f) * lobe;
+        return albedo * ((e + 2.f) * lobe);
+    }
     if (m.type == RTB_MATTE || m.type == RTB_MIRROR) {
         if (dot_dev(wo, n) > 0.f) n = -n;
         if (m.type == RTB_MATTE) {
@@ -439,6 +470,7 @@ void trace_path(const Scene &s, const rtb_camera &cam, const rtb_render_params &
         Vec3 f1 = sample_f(m, wo, xi.a, xi.b, n1, wi1, pdf1);
         beta = beta * ((f1 * dot_dev(wi1, n1)) * (1.f / pdf1));
         Ray next{offset_ray_origin(P, n1), wi1, FLT_MAX};
+        const bool next_ok = !(m.type == RTB_GLOSSY && !(dot_dev(wi1, n1) > 0.f && pdf1 > 0.f));  // lobe sample below the surface
         // render.cuh:170-211
         if (nl > 0 && !(p.flags & RTB_RENDER_NO_SHADOW)) {
             int li = (int)(xi.c * (float)nl);
@@ -465,17 +497,18 @@ void trace_path(const Scene &s, const rtb_camera &cam, const rtb_render_params &
                 excl = (int)l.triangle;
             }
             Vec3 nL = dot_dev(ng, wiL) > 0.f ? ng : -ng;
-            if (m.type == RTB_MATTE && dot_dev(wo, nL) * dot_dev(wiL, nL) < 0.f) {  // get_f + same_hemisphere
+            if ((m.type == RTB_MATTE || m.type == RTB_GLOSSY) && dot_dev(wo, nL) * dot_dev(wiL, nL) < 0.f) {  // get_f + same_hemisphere
                 float cosl = dot_dev(wiL, nL);
                 Vec3 f = (V(m.albedo[0], m.albedo[1], m.albedo[2]) * INV_PI_F) * cosl;
                 float spdf = cosl * INV_PI_F;
+                if (m.type == RTB_GLOSSY) { glossy_eval(m, wo, nL, wiL, f, spdf); f = f * cosl; }
                 Vec3 L = ((beta_old * (float)nl) * f) * Li;
                 if (l.type != RTB_POINT_LIGHT) {
                     if (true_mis) {
                         float pl = pdfL / (float)nl;
                         float a2 = pl * pl;
                         L = L * (a2 / (a2 + spdf * spdf));
-                    } else {  // power_heuristic(float, int): Quirk C
+                    } else if (m.type == RTB_MATTE) {  // power_heuristic(float, int): Quirk C (RTB_GLOSSY: weight 1)
                         int g = (int)spdf;
                         float f2 = pdfL * pdfL;
                         L = L * (f2 / (f2 + (float)(g * g)));
@@ -493,8 +526,9 @@ void trace_path(const Scene &s, const rtb_camera &cam, const rtb_render_params &
             // triangle itself (Quirk D) and never contributes: not traced.
         }
         if (b >= p.max_bounces) break;  // the reference traces `next` and discards the result
+        if (!next_ok) break;
         ray = next;
-        prev_pdf = m.type == RTB_MATTE ? pdf1 : 0.f;
+        prev_pdf = (m.type == RTB_MATTE || m.type == RTB_GLOSSY) ? pdf1 : 0.f;
         st.extend++;
         hit = traverse<false>(s, ray, is, prim, -1, nullptr);
         if (!hit && has_env) add_env(beta);

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.environ.get("RTB_LIB") or os.path.join(HERE, "librtb.so")  # RTB_LIB: A/B builds (tuning runs only)
 BUNNY_BIN = os.path.join(HERE, "data", "bunny.rtbm")
 
-RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2 = 1, 2, 3
+RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2, RTB_SCENE_S1_GLOSSY = 1, 2, 3, 4
+RTB_MATTE, RTB_MIRROR, RTB_GLASS, RTB_GLOSSY = 0, 1, 2, 3
 RTB_RENDER_PIXEL_CENTRE, RTB_RENDER_NO_SHADOW, RTB_RENDER_NONPERSISTENT, RTB_RENDER_COUNT_WORK = 1, 2, 4, 8
 RTB_RENDER_SINGLE_PIPELINE = 16
 RTB_RENDER_TRUE_MIS, RTB_RENDER_RR_TERMINATE = 32, 64

@@ -142,7 +142,7 @@ int rtb_host_scene_build(int32_t kind, const float *mv, int64_t nv, const int32_
     // bunny placement, main.cu:67-71
     M4 base = translate(0.0946899f, -0.0329874f, -0.0587997f);
     base = composite(base, scale(2.f, 2.f, 2.f));
-    if (kind == RTB_SCENE_S1 || kind == RTB_SCENE_S1_MIXED) {
+    if (kind == RTB_SCENE_S1 || kind == RTB_SCENE_S1_MIXED || kind == RTB_SCENE_S1_GLOSSY) {
         M4 t = composite(base, translate(0.3f, 0.f, -0.5f));
         add_mesh(b, t, mv, nv, mf, nf, brown);  // triangles [0, nf)
         cornell_shell(b, red, green, white);    // walls [nf, nf+10), lights nf+10, nf+11
@@ -155,6 +155,13 @@ int rtb_host_scene_build(int32_t kind, const float *mv, int64_t nv, const int32_
                 if (i % 3 == 1) b.mat[i] = mirror;
                 else if (i % 3 == 2) b.mat[i] = glass;
             }
+        }
+        if (kind == RTB_SCENE_S1_GLOSSY) {
+            // beyond the reference: the bunny a broad glossy lobe, the x = 1 wall (triangles nf+2, nf+3) a sharp one
+            const int gloss_bunny = b.add_material(RTB_GLOSSY, 0.75f, 0.65f, 0.45f, 50.f);
+            const int gloss_wall = b.add_material(RTB_GLOSSY, 0.85f, 0.85f, 0.85f, 400.f);
+            for (int64_t i = 0; i < nf; ++i) b.mat[i] = gloss_bunny;
+            b.mat[nf + 2] = gloss_wall; b.mat[nf + 3] = gloss_wall;
         }
     } else if (kind == RTB_SCENE_S2) {
         if (grid <= 0) grid = 12;

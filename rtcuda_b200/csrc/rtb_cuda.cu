@@ -201,10 +201,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
             } else {
                 const int mat = S.tri_meta[T.hit.tri].material;
                 const int type = mat >> 24;
-                int j;
-                if (type == RTB_MATTE) j = queue_push(&W.c->n_mat[0]);
-                else if (type == RTB_MIRROR) j = W.pool + queue_push(&W.c->n_mat[1]);
-                else j = 2 * W.pool + queue_push(&W.c->n_mat[2]);
+                const int j = hit_queue_push(W, type);
                 const F4 beta = ldg(W.ec + qi);
                 const float4 o = ws.ro[lane], d = ws.rd[lane];
                 F4 ma; ma.x = d.x; ma.y = d.y; ma.z = d.z; ma.w = o.w;
@@ -338,7 +335,7 @@ struct CudaBackend {
     cudaStream_t streams_[kMaxPipelines] = {nullptr, nullptr};
     cudaEvent_t sync_ev_ = nullptr;
     int pipelines_ = 2;  // RTB_PIPELINES: concurrent wavefronts per render (1 or 2)
-    int blocks_trace_ = 0, blocks_shade_[3] = {0, 0, 0}, blocks_generate_ = 0;
+    int blocks_trace_ = 0, blocks_shade_[kNumMaterialTypes] = {0, 0, 0, 0}, blocks_generate_ = 0;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
@@ -392,6 +389,8 @@ struct CudaBackend {
         blocks_shade_[1] = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<2>, kBlock, 0));
         blocks_shade_[2] = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<3>, kBlock, 0));
+        blocks_shade_[3] = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate, kBlock, 0));
         blocks_generate_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
     }
@@ -448,11 +447,13 @@ struct CudaBackend {
         if (k.rc.flags & (RTB_RENDER_TRUE_MIS | RTB_RENDER_RR_TERMINATE)) {  // beyond-the-reference estimator
             if (k.type == 0) k_shade<0, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else if (k.type == 1) k_shade<1, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else k_shade<2, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 2) k_shade<2, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else k_shade<3, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         } else {
             if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 2) k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else k_shade<3><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         }
         RTB_CUDA_CHECK(cudaGetLastError());
     }

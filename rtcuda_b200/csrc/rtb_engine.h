@@ -178,7 +178,8 @@ struct SceneT {
         for (int k = 0; k < np; ++k) {
             WaveState &w = W[k];
             w.ea = be->template alloc<F4>(p); w.eb = be->template alloc<F4>(p); w.ec = be->template alloc<F4>(p);
-            w.ma = be->template alloc<F4>(3 * (size_t)p); w.mb = be->template alloc<F4>(3 * (size_t)p); w.mc = be->template alloc<F4>(3 * (size_t)p);
+            w.ma = be->template alloc<F4>(kNumMaterialTypes * (size_t)p); w.mb = be->template alloc<F4>(kNumMaterialTypes * (size_t)p);
+            w.mc = be->template alloc<F4>(kNumMaterialTypes * (size_t)p);
             w.sh_o = be->template alloc<F4>(p); w.sh_d = be->template alloc<F4>(p); w.sh_L = be->template alloc<F4>(p);
             w.c = be->template alloc<Counters>(1);
             w.pool = p;
@@ -350,6 +351,8 @@ SceneT<BE> *scene_from_desc(BE &be, const rtb_scene_desc &d, const rtb_build_par
         throw Error(RTB_ERR_INVALID, "rtb_scene_create: incomplete scene description");
     if (d.num_lights > 0 && !d.lights) throw Error(RTB_ERR_INVALID, "rtb_scene_create: lights missing");
     const int64_t n = d.num_triangles;
+    for (int i = 0; i < d.num_materials; ++i)
+        if (d.materials[i].type < 0 || d.materials[i].type >= kNumMaterialTypes) throw Error(RTB_ERR_INVALID, "unknown material type");
     std::vector<TriMeta> meta((size_t)n);
     for (int64_t i = 0; i < n; ++i) {
         const int m = d.material_ids[i];
@@ -377,7 +380,7 @@ SceneT<BE> *scene_from_desc(BE &be, const rtb_scene_desc &d, const rtb_build_par
         sc->num_lights = d.num_lights;
         sc->materials = be.template alloc<rtb_material>(d.num_materials);
         be.upload(sc->materials, d.materials, d.num_materials);
-        for (int i = 0; i < d.num_materials; ++i) sc->type_mask |= 1u << (d.materials[i].type & 3);
+        for (int i = 0; i < d.num_materials; ++i) sc->type_mask |= 1u << d.materials[i].type;
         sc->lights = be.template alloc<LightDev>(d.num_lights > 0 ? d.num_lights : 1);
         int64_t *d_light_tri = be.template alloc<int64_t>(d.num_lights > 0 ? d.num_lights : 1);
         if (d.num_lights) { be.upload(sc->lights, lights.data(), d.num_lights); be.upload(d_light_tri, light_tri.data(), d.num_lights); }
@@ -412,7 +415,10 @@ SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const 
         {
             std::vector<rtb_material> hm((size_t)num_mats);
             be.download(hm.data(), sc->materials, (size_t)num_mats);
-            for (int i = 0; i < num_mats; ++i) sc->type_mask |= 1u << (hm[(size_t)i].type & 3);
+            for (int i = 0; i < num_mats; ++i) {
+                if (hm[(size_t)i].type < 0 || hm[(size_t)i].type >= kNumMaterialTypes) throw Error(RTB_ERR_INVALID, "unknown material type");
+                sc->type_mask |= 1u << hm[(size_t)i].type;
+            }
         }
         // Light (light.cuh:9-28): type@0 pos@4 d_triangle@16 L@24, 40 bytes
         std::vector<char> hl(40 * (size_t)(num_lights > 0 ? num_lights : 1));
@@ -485,7 +491,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     RenderConsts rc[kMaxPipelines];
     auto t0 = be.now();
     for (int k = 0; k < np; ++k) {
-        if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(6 * (size_t)pool);
+        if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(2 * kNumMaterialTypes * (size_t)pool);
         W[k] = sc.W[k];
         if (!(p.flags & RTB_RENDER_TRUE_MIS)) W[k].mis = nullptr;
         W[k].env[0] = p.env_L[0]; W[k].env[1] = p.env_L[1]; W[k].env[2] = p.env_L[2];
@@ -520,7 +526,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
             be.use_stream(k);
             for (int b = 0; b < batch; ++b) {
                 if (time_stages) stage_times.push_back(be.now());
-                for (int type = 0; type < 3; ++type) {
+                for (int type = 0; type < kNumMaterialTypes; ++type) {
                     if (!(sc.type_mask >> type & 1u)) continue;
                     ShadeK ks; ks.W = W[k]; ks.S = S; ks.rc = rc[k]; ks.type = type; ks.shadows = shadows;
                     be.shade(ks);

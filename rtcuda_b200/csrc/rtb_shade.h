@@ -90,6 +90,23 @@ RTB_HD V3 uniform_sample_sphere(float u1, float u2) {  // utility.cuh:70-77
     return v3(fmul(r, c), fmul(r, s), z);
 }
 
+// orthonormal basis around a unit vector (Duff et al. 2017)
+RTB_HD void onb(V3 n, V3 &t, V3 &b) {
+    const float sg = copysignf(1.f, n.z);
+    const float a = fdiv(-1.f, fadd(sg, n.z));
+    const float c = fmul(fmul(n.x, n.y), a);
+    t = v3(ffma(fmul(sg, fmul(n.x, n.x)), a, 1.f), fmul(sg, c), fmul(-sg, n.x));
+    b = v3(c, ffma(fmul(n.y, n.y), a, sg), -n.y);
+}
+// BRDF value and solid-angle pdf of RTB_GLOSSY for a given pair of directions (n on the side of wi)
+RTB_HD void glossy_eval(const rtb_material &m, V3 wo, V3 n, V3 wi, V3 &f, float &pdf) {
+    const float ca = vdot(reflect(wo, n), wi);
+    if (ca <= 0.f) { f = v3(0.f); pdf = 0.f; return; }
+    const float lobe = fmul(powf(ca, m.ior), 0.15915494309189535f);
+    pdf = fmul(fadd(m.ior, 1.f), lobe);
+    f = vscale(v3(m.albedo[0], m.albedo[1], m.albedo[2]), fmul(fadd(m.ior, 2.f), lobe));
+}
+
 struct BsdfSample {
     V3 f, n, wi;
     float pdf;
@@ -112,6 +129,23 @@ RTB_HD BsdfSample sample_f(const rtb_material &m, V3 wo, V3 n, float u1, float u
             s.pdf = 1.f;
             s.f = vscale(albedo, frcp(vdot(s.wi, n)));
         }
+        s.n = n;
+        return s;
+    }
+    if (m.type == RTB_GLOSSY) {  // not in the reference: Phong lobe around the mirror direction
+        if (vdot(wo, n) > 0.f) n = vneg(n);
+        const V3 r = reflect(wo, n);
+        const float e = m.ior;
+        const float ca = powf(u1, frcp(fadd(e, 1.f)));
+        const float sa = fsqrt(fmaxf(0.f, fsub(1.f, fmul(ca, ca))));
+        float sp, cp;
+        sincosf(fmul(kTwoPi, u2), &sp, &cp);
+        V3 t, b;
+        onb(r, t, b);
+        s.wi = vadd(vadd(vscale(t, fmul(sa, cp)), vscale(b, fmul(sa, sp))), vscale(r, ca));
+        const float lobe = fmul(powf(ca, e), 0.15915494309189535f);  // cos^e(alpha) / 2 pi
+        s.pdf = fmul(fadd(e, 1.f), lobe);
+        s.f = vscale(albedo, fmul(fadd(e, 2.f), lobe));
         s.n = n;
         return s;
     }
@@ -280,10 +314,11 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
         out.d = bs.wi;
         out.beta = beta;
         out.bounces = b;
-        out.pdf = m.type == RTB_MATTE ? bs.pdf : 0.f;
+        out.pdf = (m.type == RTB_MATTE || m.type == RTB_GLOSSY) ? bs.pdf : 0.f;
         // the reference traces this ray even when the depth cut will discard
         // its result (render.cuh:109); skipping it does not change the image
         out.extend = b < rc.max_bounces;
+        if (m.type == RTB_GLOSSY && !(vdot(bs.wi, bs.n) > 0.f && bs.pdf > 0.f)) out.extend = false;  // lobe sample below the surface
     }
     // mat, render.cuh:170-211: one uniformly picked light, MATTE only (get_f)
     if (S.num_lights == 0 || (rc.flags & RTB_RENDER_NO_SHADOW)) return;
@@ -293,10 +328,14 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
     const Rand4 xl = rand4(rc.seed, in.pixel, in.sample, 0x80000000u + (uint32_t)b);
     LightSample ls = sample_Li(l, S.bvh, P, xi.d, xl.a);
     V3 nl = vdot(ng, ls.wi) > 0.f ? ng : vneg(ng);
-    if (m.type == RTB_MATTE && fmul(vdot(in.wo, nl), vdot(ls.wi, nl)) < 0.f) {  // same_hemisphere, utility.cuh:57-59
+    if ((m.type == RTB_MATTE || m.type == RTB_GLOSSY) && fmul(vdot(in.wo, nl), vdot(ls.wi, nl)) < 0.f) {  // same_hemisphere, utility.cuh:57-59
         float cosl = vdot(ls.wi, nl);
         V3 f = vscale(vscale(v3(m.albedo[0], m.albedo[1], m.albedo[2]), kInvPi), cosl);
         float scattering_pdf = fmul(cosl, kInvPi);
+        if (m.type == RTB_GLOSSY) {
+            glossy_eval(m, in.wo, nl, ls.wi, f, scattering_pdf);
+            f = vscale(f, cosl);
+        }
         V3 mult = vscale(beta_old, (float)S.num_lights);
         V3 L = vmul(vmul(mult, f), ls.Li);
         if (l.type != RTB_POINT_LIGHT) {
@@ -304,9 +343,9 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
                 const float pl = fdiv(ls.pdf, (float)S.num_lights);
                 const float a2 = fmul(pl, pl);
                 L = vscale(L, fdiv(a2, fadd(a2, fmul(scattering_pdf, scattering_pdf))));
-            } else {
+            } else if (m.type == RTB_MATTE) {
                 L = vscale(L, power_heuristic_ref(ls.pdf, scattering_pdf));
-            }
+            }  // RTB_GLOSSY without RTB_RENDER_TRUE_MIS: light sampling only, weight 1 (what Quirk C makes of MATTE)
         }
         L = vscale(L, frcp(ls.pdf));
         out.shadow = true;

@@ -28,11 +28,13 @@
 
 namespace rtb {
 
+constexpr int kNumMaterialTypes = 4;  // MATTE, MIRROR, GLASS, GLOSSY: one hit queue each
+
 struct Counters {
     int32_t n_extend, n_shadow;        // entries of this iteration's ray queues (holes included), set by control
-    int32_t n_mat[3];                  // hit queue sizes: pushed by extend, consumed by shade, reset by control
+    int32_t n_mat[kNumMaterialTypes];  // hit queue sizes: pushed by extend, consumed by shade, reset by control
     int32_t extend_head, shadow_head;  // fetch cursors of the persistent kernels
-    int32_t done, _pad[2];
+    int32_t done, _pad;
     unsigned long long next_path, total_paths;
     unsigned long long stat_extend, stat_shadow, stat_paths, stat_iters, stat_hits;
     unsigned long long work[4];  // extend nodes, extend tris, shadow nodes, shadow tris (counting variants)
@@ -49,14 +51,14 @@ struct Counters {
 // 52 % of the shade kernel's stall samples sat on the return of the two queue-append atomics.
 struct WaveState {
     F4 *ea, *eb, *ec;
-    F4 *ma, *mb, *mc;  // [3][pool]
+    F4 *ma, *mb, *mc;  // [kNumMaterialTypes][pool]
     F4 *sh_o, *sh_d, *sh_L;
     Counters *c;
     int32_t *host_done;  // mapped pinned host word (or null): lets the host poll without a stream sync
     float *accum;        // 3 floats per pixel, radiance sums
     int32_t pool;
     // beyond the reference (off in parity mode): per-hit {pdf of the BSDF sample that produced the ray, hit
-    // distance} for RTB_RENDER_TRUE_MIS ([3][pool], null otherwise); constant environment radiance
+    // distance} for RTB_RENDER_TRUE_MIS ([kNumMaterialTypes][pool], null otherwise); constant environment radiance
     float *mis;
     float env[3];
     int32_t has_env;
@@ -111,7 +113,7 @@ RTB_HD V3 xyz(F4 a) { return v3(a.x, a.y, a.z); }
 // gen, render.cuh:250-275.  Tops the extend queue up to `pool` entries with
 // new camera paths; pixel = path / spp (the samples of one pixel are
 // consecutive ids, so one warp's primary rays are coherent).
-RTB_HD int hit_total(const Counters &c) { return c.n_mat[0] + c.n_mat[1] + c.n_mat[2]; }
+RTB_HD int hit_total(const Counters &c) { return c.n_mat[0] + c.n_mat[1] + c.n_mat[2] + c.n_mat[3]; }
 RTB_HD int generate_count(const WaveState &W) {
     const Counters &c = *W.c;
     const unsigned long long remaining = c.total_paths - c.next_path;
@@ -134,6 +136,14 @@ RTB_HD void generate_body(const WaveState &W, const RenderConsts &rc, int tid) {
 // ------------------------------------------------------------ extend
 // ch, render.cuh:297-328 (PATH_RAY part), one queue entry.  A miss ends the
 // path (the reference parks the slot until max_bounces, Quirk B).
+// append to the hit queue of one material type (the queues are [kNumMaterialTypes][pool]); the branches keep each
+// warp-aggregated atomic among the lanes of one type
+RTB_HD int hit_queue_push(const WaveState &W, int type) {
+    if (type == RTB_MATTE) return queue_push(&W.c->n_mat[0]);
+    if (type == RTB_MIRROR) return W.pool + queue_push(&W.c->n_mat[1]);
+    if (type == RTB_GLASS) return 2 * W.pool + queue_push(&W.c->n_mat[2]);
+    return 3 * W.pool + queue_push(&W.c->n_mat[3]);
+}
 RTB_HD void extend_miss(const WaveState &W, uint32_t pixel, V3 beta) {  // environment light, rtb_render_params.env_L
     const V3 L = vmul(beta, v3(W.env[0], W.env[1], W.env[2]));
     if (finite3(L)) accum_add(W.accum, pixel, L);
@@ -145,10 +155,7 @@ RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const 
     }
     const int mat = S.tri_meta[h.tri].material;
     const int type = mat >> 24;
-    int j;
-    if (type == RTB_MATTE) j = queue_push(&W.c->n_mat[0]);
-    else if (type == RTB_MIRROR) j = W.pool + queue_push(&W.c->n_mat[1]);
-    else j = 2 * W.pool + queue_push(&W.c->n_mat[2]);
+    const int j = hit_queue_push(W, type);
     // the shade kernel needs u, v and the triangle, not t: the slot carries the material word
     // (index | type << 24) instead, which saves shade one dependent load per hit
     F4 hr; hr.x = i2f(mat); hr.y = h.u; hr.z = h.v; hr.w = i2f(h.tri);
@@ -203,7 +210,7 @@ RTB_HD void shade_item(const WaveState &W, const SceneView &S, const RenderConst
     }
     // slot of this path in the ray queues = its position in the concatenated hit queues
     const Counters &c = *W.c;
-    const int j = tid + (TYPE > 0 ? c.n_mat[0] : 0) + (TYPE > 1 ? c.n_mat[1] : 0);
+    const int j = tid + (TYPE > 0 ? c.n_mat[0] : 0) + (TYPE > 1 ? c.n_mat[1] : 0) + (TYPE > 2 ? c.n_mat[2] : 0);
     if (out.extend) {
         W.ea[j] = f4(out.o, a.w);
         W.eb[j] = f4(out.d, u2f((in.sample << 8) | (uint32_t)out.bounces));
@@ -263,7 +270,7 @@ RTB_HD void control_body(const WaveState &W, bool shadows) {
     c.stat_hits += (unsigned long long)nh;
     c.n_extend = nh + started;
     c.n_shadow = shadows ? nh : 0;
-    c.n_mat[0] = c.n_mat[1] = c.n_mat[2] = 0;
+    c.n_mat[0] = c.n_mat[1] = c.n_mat[2] = c.n_mat[3] = 0;
     c.extend_head = 0;
     c.shadow_head = 0;
     if (c.n_extend == 0) {

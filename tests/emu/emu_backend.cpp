@@ -44,7 +44,8 @@ struct HostBackend {
         for (int i = 0; i < n; ++i) {
             if (k.type == 0) shade_body<0>(k.W, k.S, k.rc, k.shadows, i, tally);
             else if (k.type == 1) shade_body<1>(k.W, k.S, k.rc, k.shadows, i, tally);
-            else shade_body<2>(k.W, k.S, k.rc, k.shadows, i, tally);
+            else if (k.type == 2) shade_body<2>(k.W, k.S, k.rc, k.shadows, i, tally);
+            else shade_body<3>(k.W, k.S, k.rc, k.shadows, i, tally);
         }
         tally_flush(k.W.c, tally);
     }

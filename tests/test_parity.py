@@ -282,6 +282,40 @@ def test_true_mis_rr_termination_and_environment_match_the_oracle(L, bunny, ctx,
     assert mean_rel_err(img, par) > 10 * IMAGE_TOL
 
 
+@pytest.mark.parametrize("flags", [0, capi.RTB_RENDER_TRUE_MIS | capi.RTB_RENDER_RR_TERMINATE])
+def test_glossy_material_matches_the_oracle(L, bunny, ctx, oracle, flags):
+    """RTB_GLOSSY (not in the reference: energy-normalised Phong lobe, `ior` = exponent): glossy bunny (exponent 50) and a
+    sharp glossy wall (exponent 400) in the Cornell box, with and without the MIS estimator"""
+    hs = L.host_scene(capi.RTB_SCENE_S1_GLOSSY, *bunny)
+    types = [int(m["type"]) for m in hs.arrays()["materials"]]
+    assert types.count(capi.RTB_GLOSSY) == 2
+    sc, osc = ctx.scene(hs.desc), oracle.scene(hs.desc)
+    cam = hs.camera(4 / 3)
+    img, st, ref, ost = render_pair(L, sc, osc, cam, width=128, height=96, spp=8, max_bounces=8, flags=flags)
+    assert st.paths == ost[0]
+    assert abs(int(st.extend_rays) - int(ost[1])) <= 5e-3 * ost[1]
+    assert abs(int(st.shadow_rays) - int(ost[2])) <= 5e-3 * ost[2]
+    assert np.isfinite(img).all() and img.mean() > 0.05
+    assert mean_rel_err(img, ref) <= IMAGE_TOL
+    sc.close()
+
+
+def test_glossy_lobe_conserves_energy(L, ctx):
+    """white furnace: a glossy floor of albedo 1 under a constant environment of radiance 1 reflects at most what it
+    receives (the lobe is normalised; the part of it below the horizon is lost), for a broad and for a sharp lobe"""
+    floor = np.array([[[-50, 0, 50], [50, 0, 50], [50, 0, -50]], [[-50, 0, 50], [50, 0, -50], [-50, 0, -50]]], np.float32).reshape(-1, 9)
+    for exponent, lo in ((2.0, 0.6), (200.0, 0.6)):  # the Phong lobe's albedo falls like cos(theta) at oblique incidence
+        m = capi.Material(); m.type = capi.RTB_GLOSSY; m.ior = exponent
+        m.albedo[0] = m.albedo[1] = m.albedo[2] = 1.0
+        desc, keep = make_desc(floor, np.zeros(2, np.int32), np.full(2, -1, np.int32), [m], [])
+        sc = ctx.scene(desc)
+        cam = L.camera_look_at((0.0, 1.0, 0.0), (0.0, 0.0, -1.0), (0, 1, 0), 40.0, 1.0)  # 45 degrees down onto the floor
+        img, st = sc.render(cam, capi.render_params(L, width=16, height=16, spp=256, max_bounces=4, env_L=(1.0, 1.0, 1.0)))
+        lower = (img[8:] ** 2).mean()  # bottom rows look at the floor
+        assert lo <= lower <= 1.02, (exponent, lower)
+        sc.close()
+
+
 def test_true_mis_and_light_sampling_only_agree_in_the_mean(L, oracle):
     """direct lighting of a floor by a large, low, black-bodied emitter: the reference's estimator (weight-1 light
     sampling) and the MIS estimator (light sample + BSDF sample, complete at depth 2) are both unbiased,
@@ -432,6 +466,16 @@ def test_every_traversal_kernel_variant_matches_the_oracle(gpu, oracle, bunny, m
     assert abs(int(st.shadow_rays) - int(ost[2])) <= 2e-3 * ost[2]
     assert mean_rel_err(img, ref) <= IMAGE_TOL
     sc.close()
+
+
+def test_unknown_material_type_is_rejected(L, ctx):
+    verts, mat, lid = small_scene_arrays(n=5)
+    ms = std_materials()
+    ms[1].type = 7
+    desc, keep = make_desc(verts, mat, np.full(len(mat), -1, np.int32), ms, [])
+    h = C.c_void_p()
+    assert L.lib.rtb_scene_create(ctx.h, C.byref(desc), None, C.byref(h)) == -1
+    assert b"material type" in L.lib.rtb_last_error()
 
 
 def test_bad_arguments_return_status_codes(L, ctx, s1_dev):

@@ -1,0 +1,2 @@
+#!/bin/bash
+echo "== gpu tests"; timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
