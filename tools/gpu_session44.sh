@@ -1,0 +1,3 @@
+#!/bin/bash
+echo "== gpu tests"; timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for w in c1 c2 c4 c3; do timeout 900 python tools/sweep.py --workload $w --reps 3 2>&1 | tail -1 | cut -c1-170; done
