@@ -65,15 +65,17 @@ __global__ void __launch_bounds__(kBlock, MINB) k_shade(WaveState W, SceneView S
     __shared__ float4 stage[2][3][kBlock];
     const int n = W.c->n_mat[TYPE];
     const int stride = gridDim.x * kBlock, t = threadIdx.x;
-    const F4 *ma = W.ma + W.qbase[TYPE], *mb = W.mb + W.qbase[TYPE], *mc = W.mc + W.qbase[TYPE];  // this type's hit queue
     ShadeTally tally; tally.extend = 0u; tally.shadow = 0u;
     int i = blockIdx.x * kBlock + t;
-    if (i < n) { cp_async16(&stage[0][0][t], ma + i); cp_async16(&stage[0][1][t], mb + i); cp_async16(&stage[0][2][t], mc + i); }
+    if (i < n) {
+        const size_t q = (size_t)W.qbase[TYPE] + (size_t)i;
+        cp_async16(&stage[0][0][t], W.ma + q); cp_async16(&stage[0][1][t], W.mb + q); cp_async16(&stage[0][2][t], W.mc + q);
+    }
     asm volatile("cp.async.commit_group;");
     for (int buf = 0; i < n; i += stride, buf ^= 1) {
         if (i + stride < n) {
-            const int j = i + stride;
-            cp_async16(&stage[buf ^ 1][0][t], ma + j); cp_async16(&stage[buf ^ 1][1][t], mb + j); cp_async16(&stage[buf ^ 1][2][t], mc + j);
+            const size_t q = (size_t)W.qbase[TYPE] + (size_t)(i + stride);
+            cp_async16(&stage[buf ^ 1][0][t], W.ma + q); cp_async16(&stage[buf ^ 1][1][t], W.mb + q); cp_async16(&stage[buf ^ 1][2][t], W.mc + q);
         }
         asm volatile("cp.async.commit_group;");
         asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the group just committed has landed

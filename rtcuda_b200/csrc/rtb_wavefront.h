@@ -52,6 +52,7 @@ struct Counters {
 struct WaveState {
     F4 *ea, *eb, *ec;
     F4 *ma, *mb, *mc;  // one [pool] block per material type PRESENT in the scene; type t starts at qbase[t]
+    int32_t qbase[kNumMaterialTypes];
     F4 *sh_o, *sh_d, *sh_L;
     Counters *c;
     int32_t *host_done;  // mapped pinned host word (or null): lets the host poll without a stream sync
@@ -62,7 +63,6 @@ struct WaveState {
     float *mis;
     float env[3];
     int32_t has_env;
-    int32_t qbase[kNumMaterialTypes];
 };
 
 constexpr int kMaxBounces = 255;       // bounces share a word with the sample index
