@@ -409,7 +409,6 @@ def main():
                                "is L2-resident: the kernel is bound by instruction issue, not by HBM (see profiles/)" if bst.node_bytes + bst.triangle_bytes < 100e6
                                else "exceeds L2")}
         pool_used = min(int(p.pool_size) or int(os.environ.get("RTB_POOL", 1 << 25)), int(stats[0].paths))
-        n_types = len({int(m["type"]) for m in arr["materials"]})  # one hit queue per material type present
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -417,7 +416,7 @@ def main():
                            "sharding": "sample pass per rank, scene replicated, NCCL all-reduce of the accumulation buffer" if world > 1 else "single GPU",
                            "pool_size": pool_used,
                            "l2": "256 MB device memset between timed steps (L2 flush); the ray / hit queues (%.1f GB) are streamed every iteration"
-                                 % (pool_used * 48 * (2 + n_types) / 1e9)},
+                                 % (pool_used * 288 / 1e9)},
                 "ms_per_spp": ms_per_step / total_spp * (1 if strong else world), "paths_per_step": int(stats[0].paths) * world,
                 "rays_per_step": rays_total.item() / args.steps,
                 "iterations_per_step": int(stats[0].iterations), "pipelines": int(stats[0].pipelines),

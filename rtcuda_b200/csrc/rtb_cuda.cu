@@ -68,13 +68,13 @@ __global__ void __launch_bounds__(kBlock, MINB) k_shade(WaveState W, SceneView S
     ShadeTally tally; tally.extend = 0u; tally.shadow = 0u;
     int i = blockIdx.x * kBlock + t;
     if (i < n) {
-        const size_t q = (size_t)W.qbase[TYPE] + (size_t)i;
+        const size_t q = (size_t)TYPE * W.pool + (size_t)i;
         cp_async16(&stage[0][0][t], W.ma + q); cp_async16(&stage[0][1][t], W.mb + q); cp_async16(&stage[0][2][t], W.mc + q);
     }
     asm volatile("cp.async.commit_group;");
     for (int buf = 0; i < n; i += stride, buf ^= 1) {
         if (i + stride < n) {
-            const size_t q = (size_t)W.qbase[TYPE] + (size_t)(i + stride);
+            const size_t q = (size_t)TYPE * W.pool + (size_t)(i + stride);
             cp_async16(&stage[buf ^ 1][0][t], W.ma + q); cp_async16(&stage[buf ^ 1][1][t], W.mb + q); cp_async16(&stage[buf ^ 1][2][t], W.mc + q);
         }
         asm volatile("cp.async.commit_group;");

@@ -153,7 +153,6 @@ struct SceneT {
     // render() and never frees it, render.cuh:374-391)
     WaveState W[kMaxPipelines]{};
     int32_t pool = 0, pipes = 0;  // pool = queue entries PER pipeline
-    int32_t present_types() const { int c = 0; for (int t = 0; t < kNumMaterialTypes; ++t) c += (type_mask >> t) & 1u; return c ? c : 1; }
     float *own_accum = nullptr; int64_t own_accum_floats = 0;
 
     SceneView view() const {
@@ -176,15 +175,11 @@ struct SceneT {
     void ensure_wave(int32_t p, int np) {
         if (pool == p && pipes == np) return;
         free_wave();
-        int present = 0, qbase[kNumMaterialTypes];
-        for (int t = 0; t < kNumMaterialTypes; ++t) { qbase[t] = present * p; if (type_mask >> t & 1u) ++present; }
-        if (present == 0) present = 1;
         for (int k = 0; k < np; ++k) {
             WaveState &w = W[k];
             w.ea = be->template alloc<F4>(p); w.eb = be->template alloc<F4>(p); w.ec = be->template alloc<F4>(p);
-            w.ma = be->template alloc<F4>(present * (size_t)p); w.mb = be->template alloc<F4>(present * (size_t)p);
-            w.mc = be->template alloc<F4>(present * (size_t)p);
-            for (int t = 0; t < kNumMaterialTypes; ++t) w.qbase[t] = qbase[t];
+            w.ma = be->template alloc<F4>(kNumMaterialTypes * (size_t)p); w.mb = be->template alloc<F4>(kNumMaterialTypes * (size_t)p);
+            w.mc = be->template alloc<F4>(kNumMaterialTypes * (size_t)p);
             w.sh_o = be->template alloc<F4>(p); w.sh_d = be->template alloc<F4>(p); w.sh_L = be->template alloc<F4>(p);
             w.c = be->template alloc<Counters>(1);
             w.pool = p;
@@ -496,7 +491,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     RenderConsts rc[kMaxPipelines];
     auto t0 = be.now();
     for (int k = 0; k < np; ++k) {
-        if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(2 * (size_t)sc.present_types() * (size_t)pool);
+        if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(2 * kNumMaterialTypes * (size_t)pool);
         W[k] = sc.W[k];
         if (!(p.flags & RTB_RENDER_TRUE_MIS)) W[k].mis = nullptr;
         W[k].env[0] = p.env_L[0]; W[k].env[1] = p.env_L[1]; W[k].env[2] = p.env_L[2];
