@@ -60,8 +60,14 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
-template <int TYPE, int MINB = 3, bool EXT = false>
-__global__ void __launch_bounds__(kBlock, MINB) k_shade(WaveState W, SceneView S, RenderConsts rc, bool shadows) {
+// Two blocks per SM (up to 128 registers: no spills), not the three that fit at 80 registers: shade is bound by DRAM and
+// latency, and what it leaves free lets a block of the OTHER wavefront's trace kernel (64 registers, issue bound) run on
+// the same SM at the same time.  C2, two wavefronts: 38.62 -> 38.10 ms; alone (one wavefront) shade itself is slower
+// (9.1 -> 10.2 ms) and the trace kernel after it faster (30.2 -> 29.3 ms).
+// The specular kernels need 64 registers: three blocks each.
+constexpr int shade_blocks_per_sm(int type) { return (type == RTB_MIRROR || type == RTB_GLASS) ? 3 : 2; }
+template <int TYPE, bool EXT = false>
+__global__ void __launch_bounds__(kBlock, shade_blocks_per_sm(TYPE)) k_shade(WaveState W, SceneView S, RenderConsts rc, bool shadows) {
     __shared__ float4 stage[2][3][kBlock];
     const int n = W.c->n_mat[TYPE];
     const int stride = gridDim.x * kBlock, t = threadIdx.x;
@@ -335,7 +341,7 @@ struct CudaBackend {
     cudaStream_t streams_[kMaxPipelines] = {nullptr, nullptr};
     cudaEvent_t sync_ev_ = nullptr;
     int pipelines_ = 2;  // RTB_PIPELINES: concurrent wavefronts per render (1 or 2)
-    int blocks_trace_ = 0, blocks_shade_[kNumMaterialTypes] = {0, 0, 0, 0}, blocks_generate_ = 0;
+    int blocks_trace_ = 0, blocks_generate_ = 0;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
@@ -383,14 +389,6 @@ struct CudaBackend {
         int per_sm = 0;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<3, true>, kBlock, 0));
         blocks_trace_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<0>, kBlock, 0));
-        blocks_shade_[0] = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<1>, kBlock, 0));
-        blocks_shade_[1] = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<2>, kBlock, 0));
-        blocks_shade_[2] = num_sms_ * (per_sm > 0 ? per_sm : 1);
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<3>, kBlock, 0));
-        blocks_shade_[3] = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate, kBlock, 0));
         blocks_generate_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
     }
@@ -443,12 +441,12 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shade(const ShadeK &k) {
-        const int grid = blocks_shade_[k.type];  // exactly one resident wave: the kernels are grid-stride loops
+        const int grid = num_sms_ * shade_blocks_per_sm(k.type);  // one resident wave: the kernels are grid-stride loops
         if (k.rc.flags & (RTB_RENDER_TRUE_MIS | RTB_RENDER_RR_TERMINATE)) {  // beyond-the-reference estimator
-            if (k.type == 0) k_shade<0, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else if (k.type == 1) k_shade<1, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else if (k.type == 2) k_shade<2, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else k_shade<3, 3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            if (k.type == 0) k_shade<0, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 1) k_shade<1, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 2) k_shade<2, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else k_shade<3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         } else {
             if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
