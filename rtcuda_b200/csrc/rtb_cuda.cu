@@ -122,6 +122,7 @@ struct FetchTuning {
 struct alignas(16) WarpScratch {
     float4 ro[32];   // per lane: ray origin | pixel (extend)
     float4 rd[32];   // per lane: ray direction | sample<<8|bounces (extend)
+    float4 fin[32];  // per lane: the queue word only the finish needs (extend: beta | pdf, shadow: radiance | pixel), by cp.async
     float4 res[32];  // per candidate: t (or -1), u, v, leaf-order triangle index
     uint2 item[32];  // per candidate: leaf-order triangle index, owner lane
 };
@@ -200,15 +201,20 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
         // results of the rays that finished since the last refill are written here, together, so
         // that the hit-record / atomic code runs with many lanes instead of one at a time
         if (pending) {
+            asm volatile("cp.async.wait_all;" ::: "memory");  // this lane's finish word (copied when the ray was fetched)
+            const float4 fw = ws.fin[lane];
             if (ANY) {
-                shadow_finish(W, qi, T.found);
+                if (!T.found) {  // ah, render.cuh:278-294: unoccluded -> splat
+                    const V3 L = v3(fw.x, fw.y, fw.z);
+                    if (finite3(L)) accum_add(W.accum, __float_as_uint(fw.w), L);
+                }
             } else if (T.hit.tri < 0) {
-                if (W.has_env) extend_miss(W, __float_as_uint(ws.ro[lane].w), xyz(ldg(W.ec + qi)));
+                if (W.has_env) extend_miss(W, __float_as_uint(ws.ro[lane].w), v3(fw.x, fw.y, fw.z));
             } else {
                 const int mat = S.tri_meta[T.hit.tri].material;
                 const int type = mat >> 24;
                 const int j = hit_queue_push(W, type);
-                const F4 beta = ldg(W.ec + qi);
+                F4 beta; beta.x = fw.x; beta.y = fw.y; beta.z = fw.z; beta.w = fw.w;
                 const float4 o = ws.ro[lane], d = ws.rd[lane];
                 F4 ma; ma.x = d.x; ma.y = d.y; ma.z = d.z; ma.w = o.w;
                 F4 mb; mb.x = beta.x; mb.y = beta.y; mb.z = beta.z; mb.w = d.w;
@@ -240,18 +246,18 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
             const int idx = chunk_next + __popc(need & lanes_below);
             if (!has && idx < chunk_end) {
                 if (ANY) {
-                    const F4 o = ldg(W.sh_o + idx);
+                    const F4 o = ldg(W.sh_o + idx), d = ldg(W.sh_d + idx);  // both at once: holes are rare, latency is not
                     if (o.w > 0.f) {
-                        const F4 d = ldg(W.sh_d + idx);
+                        cp_async16(&ws.fin[lane], W.sh_L + idx);
                         ws.ro[lane] = make_float4(o.x, o.y, o.z, 0.f);
                         ws.rd[lane] = make_float4(d.x, d.y, d.z, 0.f);
                         T.init(xyz(o), xyz(d), o.w, f2i(d.w));
                         qi = idx; has = true; ty = 0u;
                     }
                 } else {
-                    const F4 a = ldg(W.ea + idx);
+                    const F4 a = ldg(W.ea + idx), b = ldg(W.eb + idx);
                     if (f2u(a.w) != kHolePixel) {
-                        const F4 b = ldg(W.eb + idx);
+                        cp_async16(&ws.fin[lane], W.ec + idx);
                         ws.ro[lane] = make_float4(a.x, a.y, a.z, a.w);
                         ws.rd[lane] = make_float4(b.x, b.y, b.z, b.w);
                         T.init(xyz(a), xyz(b), FLT_MAX, -1);
