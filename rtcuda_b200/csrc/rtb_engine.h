@@ -489,6 +489,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     const bool shadows = sc.num_lights > 0 && !(p.flags & RTB_RENDER_NO_SHADOW);
     WaveState W[kMaxPipelines];
     RenderConsts rc[kMaxPipelines];
+    be.use_stream(0);  // (an error thrown out of an earlier call may have left another stream selected)
     auto t0 = be.now();
     for (int k = 0; k < np; ++k) {
         if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(2 * kNumMaterialTypes * (size_t)pool);
