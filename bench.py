@@ -394,6 +394,19 @@ def main():
                     traffic = per_ray * (ext_rays + shd_rays) / max(tr_launches, 1)
         except Exception:
             pass
+        # second roofline for an L2-resident scene: ncu L2 bytes per ray of this kernel against the measured L2 read bandwidth
+        l2 = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                l2_per_ray = json.load(f).get(args.workload, {}).get("k_trace_l2_bytes_per_ray")
+            with open(os.path.join(ROOT, "profiles", "l2_bandwidth.json")) as f:
+                l2_peak = float(json.load(f)["l2_read_gbs"])
+            if l2_per_ray is not None and avg_launch_ms > 0:
+                l2_ach = l2_per_ray * (ext_rays + shd_rays) / max(tr_launches, 1) / (avg_launch_ms * 1e-3) * 1e-9
+                l2 = {"achieved": l2_ach, "peak": l2_peak, "unit": "GB/s", "frac": l2_ach / l2_peak,
+                      "note": "ncu lts__t_bytes per ray x rays per launch / launch duration; peak = tools/l2_bandwidth.cu on this pool's B200 (profiles/l2_bandwidth.json)"}
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_trace<3> (extend + shadow rays, one persistent launch per iteration)" if fused else "k_trace<1> + k_trace<2>",
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -403,7 +416,7 @@ def main():
                     "avg_launch_ms": avg_launch_ms, "launches": int(tr_launches), "timed_with": "single pipeline (kernel alone on one stream), %d steps" % len(s0),
                     "single_pipeline_ms_per_step": tot_ms / len(s0),
                     "kernel_share_of_step": tr_ms / tot_ms if tot_ms else None,
-                    "shade_share_of_step": sh_ms / tot_ms if tot_ms else None,
+                    "shade_share_of_step": sh_ms / tot_ms if tot_ms else None, "l2": l2,
                     "note": "scene (%.1f MB nodes+triangles) %s; node/triangle counts from the counting kernel variant"
                             % ((bst.node_bytes + bst.triangle_bytes) / 1e6,
                                "is L2-resident: the kernel is bound by instruction issue, not by HBM (see profiles/)" if bst.node_bytes + bst.triangle_bytes < 100e6
