@@ -47,7 +47,12 @@ WORKLOADS = {
     # C5 is STRONG scaling: 1024 spp in total, split evenly over the ranks (the spp entry is the total)
     "c5": (3, 12, 3840, 2160, 1024, 8, "C5 144-bunny field 10,000,956 tris, 3840x2160, 1024 spp in total (sample passes split over the GPUs), depth 8"),
 }
-STRONG = {"c5"}
+# the same scenes given as INSTANCES (rtb_scene_create_instanced, two-level BVH): identical flattened triangles,
+# 4 MB of nodes + triangles instead of 600 MB; results equal the flat scene's up to the rounding of the ray transform
+WORKLOADS["c3i"] = WORKLOADS["c3"][:6] + ("C3 as instances: 144 placements of one 69,451-triangle bunny + Cornell shell (two-level BVH; flattens to the 10,000,956 triangles of C3), 3840x2160, 16 spp, depth 8",)
+WORKLOADS["c5i"] = WORKLOADS["c5"][:6] + ("C5 as instances (two-level BVH; flattens to the 10,000,956 triangles of C5), 3840x2160, 1024 spp in total, depth 8",)
+INSTANCED = {"c3i", "c5i"}
+STRONG = {"c5", "c5i"}
 METRIC = "Mrays/s (extend+shadow)"
 
 
@@ -106,8 +111,10 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def load_scene(L, capi, kind, grid):
+def load_scene(L, capi, kind, grid, instanced=False):
     verts, faces = L.load_mesh()
+    if instanced:
+        return L.host_scene_instanced(kind, verts, faces, grid=grid)
     return L.host_scene(kind, verts, faces, grid=grid)
 
 
@@ -231,7 +238,8 @@ def main():
     strong = args.workload in STRONG
     L = capi.Lib()
     ctx = L.context(local_rank)
-    hs = load_scene(L, capi, kind, grid)
+    instanced = args.workload in INSTANCED
+    hs = load_scene(L, capi, kind, grid, instanced)
     cam = hs.camera(W / H)
     if strong:
         if spp % world:
@@ -248,6 +256,12 @@ def main():
     C.memmove(C.byref(pdesc), C.byref(hs.desc), C.sizeof(pdesc))
     pdesc.vertices = pin["vertices"].data_ptr(); pdesc.material_ids = pin["material_ids"].data_ptr(); pdesc.light_ids = pin["light_ids"].data_ptr()
     h2d = sum(t.numel() * t.element_size() for t in pin.values()) + hs.desc.num_materials * 20 + hs.desc.num_lights * 40
+    if instanced:  # the same pinned geometry, placed by the instance table
+        idesc = capi.InstancedSceneDesc()
+        C.memmove(C.byref(idesc), C.byref(hs.idesc), C.sizeof(idesc))
+        idesc.geometry = pdesc
+        h2d += hs.idesc.num_instances * C.sizeof(capi.Instance) + (hs.idesc.num_meshes + 1) * 8
+        pdesc = idesc
     nfl = 3 * W * H
     host_img = torch.empty(nfl, dtype=torch.float32).pin_memory()
 
@@ -439,7 +453,11 @@ def main():
                         "d2h_bytes_per_step": int(nfl * 4), "steps": n_e2e, "ms_per_step": e2e_t.item() / n_e2e * 1e3,
                         "note": "rtb_scene_create (pinned H2D + GPU BVH build) + render + device->host framebuffer, every step"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
-        if world == 1 and not args.no_cpu_baseline:
+        if instanced:
+            line["config"]["instances"] = int(bst.num_instances)
+            line["config"]["stored_triangles"] = int(bst.num_triangles)
+            line["config"]["flattened_triangles"] = int(bst.num_flat_triangles)
+        if world == 1 and not args.no_cpu_baseline and not instanced:  # (the oracle would need the 10 M flattened triangles)
             cb = cpu_baseline_port(capi, L, hs, cam, capi.render_params(L, width=W, height=H, spp=spp, max_bounces=depth))
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))

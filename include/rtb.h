@@ -100,6 +100,33 @@ typedef struct rtb_scene_desc {
     const rtb_light *lights;
 } rtb_scene_desc;
 
+/* ---- instanced scenes: a two-level BVH (SURVEY 8f-2 "instancing: two-level BVH instead of flattening").  The
+ * reference has no instancing — main.cu:67-86 transforms every vertex on the host and Bvh::Bvh takes the flat list —
+ * so this is a second INPUT FORMAT for the same path: `geometry` holds the triangles of all meshes in object space,
+ * mesh m = triangles [mesh_first[m], mesh_first[m+1]), and every instance places one mesh with an affine transform.
+ * One 8-wide BVH is built per mesh, one over the instances' world boxes; a ray is taken into object space when it
+ * enters an instance (same parameter t, so hit distances compare directly).  A 10 M-triangle field of 144 bunnies is
+ * then 4 MB of nodes + triangles (L2-resident) instead of 600 MB.
+ * Results are those of the flattened scene (rtb_instanced_flatten) up to the rounding of the ray transform:
+ * hit ids equal except on near-ties, t within 1e-5 relative (tests/test_instancing.py).
+ * Hit ids (rtb_hit.prim, rtb_trace_any's excluded, AOV prim) number the triangles of the FLATTENED scene: instance
+ * i owns [sum of the mesh sizes of instances 0..i-1, ... + its own mesh size).
+ * Restriction: a triangle with light_ids >= 0 must belong to a mesh that is instanced exactly once, with the
+ * identity transform (emitters live in the static part of the scene). */
+typedef struct rtb_instance {
+    int32_t mesh;      /* index into the mesh table */
+    int32_t material;  /* material of every triangle of this instance, or -1: the triangles' own material_ids */
+    float xform[12];   /* object -> world, row-major 3x4: world = xform[:, :3] * p + xform[:, 3]; must be invertible */
+} rtb_instance;
+
+typedef struct rtb_instanced_scene_desc {
+    rtb_scene_desc geometry;    /* all meshes, object space; materials; lights (triangle = index into geometry) */
+    int32_t num_meshes;
+    const int64_t *mesh_first;  /* [num_meshes + 1], ascending, mesh_first[0] = 0, mesh_first[num_meshes] = num_triangles */
+    int32_t num_instances;
+    const rtb_instance *instances;
+} rtb_instanced_scene_desc;
+
 /* BVH builder selection (rtb_build_params.builder) */
 enum { RTB_BUILDER_PLOC = 0 }; /* the only builder so far; other values are rejected */
 
@@ -129,6 +156,11 @@ typedef struct rtb_bvh_stats {
     int32_t ploc_iterations;
     int32_t collapse_levels;
     float scene_bounds[6];    /* xmin xmax ymin ymax zmin zmax */
+    /* instanced scenes (0 otherwise): num_triangles / num_nodes above count what is STORED (all mesh trees + the
+     * tree over the instances) */
+    int64_t num_instances;
+    int64_t num_flat_triangles; /* triangles of the flattened scene the description stands for */
+    int64_t num_top_nodes;      /* 8-wide nodes of the tree over the instances (the first nodes of the array) */
 } rtb_bvh_stats;
 
 /* Runtime replacement of the reference's compile-time constants
@@ -212,6 +244,10 @@ RTB_API int rtb_scene_create_from_primitives(rtb_context *ctx, const void *h_pri
                                              const void *d_materials, int32_t num_materials,
                                              const void *d_lights, int32_t num_lights,
                                              const rtb_build_params *bp, rtb_scene **out);
+/* two-level BVH over meshes + instances (see rtb_instanced_scene_desc); every query / render entry point below
+ * works on the result like on a flat scene */
+RTB_API int rtb_scene_create_instanced(rtb_context *ctx, const rtb_instanced_scene_desc *desc,
+                                       const rtb_build_params *bp, rtb_scene **out);
 RTB_API int rtb_scene_destroy(rtb_scene *scene);
 RTB_API int rtb_scene_stats(const rtb_scene *scene, rtb_bvh_stats *out);
 
@@ -289,6 +325,16 @@ RTB_API int rtb_host_scene_build(int32_t kind, const float *mesh_verts, int64_t 
                                  uint32_t seed, rtb_host_scene **out);
 RTB_API int rtb_host_scene_desc(const rtb_host_scene *hs, rtb_scene_desc *out);
 RTB_API int rtb_host_scene_camera(const rtb_host_scene *hs, float aspect, rtb_camera *out);
+/* instanced form of a procedural scene (host C++, no GPU work).  RTB_SCENE_S2: mesh 0 = the bunny as loaded, placed
+ * grid x grid times by the very transforms rtb_host_scene_build applies to its vertices, mesh 1 = the Cornell shell
+ * with its two emitters (identity); flattening it gives the triangles of the flat RTB_SCENE_S2 in the same order. */
+RTB_API int rtb_host_scene_build_instanced(int32_t kind, const float *mesh_verts, int64_t num_verts,
+                                           const int32_t *mesh_faces, int64_t num_faces, int32_t grid,
+                                           uint32_t seed, rtb_host_scene **out);
+RTB_API int rtb_host_scene_instanced_desc(const rtb_host_scene *hs, rtb_instanced_scene_desc *out);
+/* the flat scene an instanced description stands for: every instance's triangles transformed on the host
+ * (Transform::apply, transform.hpp:26-33: double arithmetic on the float matrix), instance after instance */
+RTB_API int rtb_instanced_flatten(const rtb_instanced_scene_desc *desc, rtb_host_scene **out);
 RTB_API int rtb_host_scene_destroy(rtb_host_scene *hs);
 /* scene file shared with the reference harness: see csrc/host/scene_io.cpp */
 RTB_API int rtb_scene_desc_save(const char *path, const rtb_scene_desc *desc);

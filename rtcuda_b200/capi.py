@@ -41,6 +41,15 @@ class SceneDesc(C.Structure):
                 ("num_lights", C.c_int32), ("lights", C.c_void_p)]
 
 
+class Instance(C.Structure):
+    _fields_ = [("mesh", C.c_int32), ("material", C.c_int32), ("xform", C.c_float * 12)]
+
+
+class InstancedSceneDesc(C.Structure):
+    _fields_ = [("geometry", SceneDesc), ("num_meshes", C.c_int32), ("mesh_first", C.c_void_p),
+                ("num_instances", C.c_int32), ("instances", C.c_void_p)]
+
+
 class BuildParams(C.Structure):
     _fields_ = [("builder", C.c_int32), ("ploc_radius", C.c_int32), ("max_leaf_tris", C.c_int32),
                 ("collapse", C.c_int32)]
@@ -50,7 +59,8 @@ class BvhStats(C.Structure):
     _fields_ = [("num_triangles", C.c_int64), ("num_bvh2_nodes", C.c_int64), ("num_nodes", C.c_int64),
                 ("node_bytes", C.c_int64), ("triangle_bytes", C.c_int64), ("sah_cost", C.c_float),
                 ("build_ms", C.c_float), ("ploc_iterations", C.c_int32), ("collapse_levels", C.c_int32),
-                ("scene_bounds", C.c_float * 6)]
+                ("scene_bounds", C.c_float * 6), ("num_instances", C.c_int64), ("num_flat_triangles", C.c_int64),
+                ("num_top_nodes", C.c_int64)]
 
 
 class RenderParams(C.Structure):
@@ -81,6 +91,7 @@ SYMBOLS = [
     "rtb_render", "rtb_render_accumulate", "rtb_tonemap_device", "rtb_mesh_load_ply", "rtb_mesh_load_bin",
     "rtb_mesh_save_bin", "rtb_free", "rtb_host_scene_build", "rtb_host_scene_desc", "rtb_host_scene_camera",
     "rtb_host_scene_destroy", "rtb_scene_desc_save", "rtb_host_scene_load", "rtb_write_ppm",
+    "rtb_scene_create_instanced", "rtb_host_scene_build_instanced", "rtb_host_scene_instanced_desc", "rtb_instanced_flatten",
 ]
 
 
@@ -125,6 +136,16 @@ class Lib:
     def host_scene(self, kind, verts, faces, grid=0, seed=1234):
         return HostScene(self, kind, verts, faces, grid, seed)
 
+    def host_scene_instanced(self, kind, verts, faces, grid=0, seed=1234):
+        """instanced form of a procedural scene: .idesc is the rtb_instanced_scene_desc"""
+        return HostScene(self, kind, verts, faces, grid, seed, instanced=True)
+
+    def flatten(self, idesc):
+        """the flat HostScene an instanced description stands for"""
+        h = C.c_void_p()
+        self.check(self.lib.rtb_instanced_flatten(C.byref(idesc), C.byref(h)))
+        return HostScene(self, handle=h)
+
     def camera_look_at(self, lookfrom, lookat, up, vfov, aspect):
         cam = Camera()
         a = (C.c_float * 3)(*lookfrom); b = (C.c_float * 3)(*lookat); c = (C.c_float * 3)(*up)
@@ -146,16 +167,21 @@ class Lib:
 
 
 class HostScene:
-    def __init__(self, L, kind, verts, faces, grid, seed):
+    def __init__(self, L, kind=None, verts=None, faces=None, grid=0, seed=1234, instanced=False, handle=None):
         self.L = L
-        self.h = C.c_void_p()
-        verts = np.ascontiguousarray(verts, dtype=np.float32)
-        faces = np.ascontiguousarray(faces, dtype=np.int32)
-        L.check(L.lib.rtb_host_scene_build(kind, verts.ctypes.data_as(C.c_void_p), C.c_int64(len(verts)),
-                                           faces.ctypes.data_as(C.c_void_p), C.c_int64(len(faces)), grid,
-                                           C.c_uint32(seed), C.byref(self.h)))
+        self.h = handle if handle is not None else C.c_void_p()
+        if handle is None:
+            verts = np.ascontiguousarray(verts, dtype=np.float32)
+            faces = np.ascontiguousarray(faces, dtype=np.int32)
+            fn = L.lib.rtb_host_scene_build_instanced if instanced else L.lib.rtb_host_scene_build
+            L.check(fn(kind, verts.ctypes.data_as(C.c_void_p), C.c_int64(len(verts)), faces.ctypes.data_as(C.c_void_p),
+                       C.c_int64(len(faces)), grid, C.c_uint32(seed), C.byref(self.h)))
         self.desc = SceneDesc()
         L.check(L.lib.rtb_host_scene_desc(self.h, C.byref(self.desc)))
+        self.idesc = None
+        if instanced:
+            self.idesc = InstancedSceneDesc()
+            L.check(L.lib.rtb_host_scene_instanced_desc(self.h, C.byref(self.idesc)))
 
     def arrays(self):
         """numpy views of the description (valid while this object lives)."""
@@ -192,6 +218,7 @@ class Context:
         L.check(L.lib.rtb_context_create(device, C.byref(self.h)))
 
     def scene(self, desc, build_params=None):
+        """desc: SceneDesc (flat) or InstancedSceneDesc (two-level BVH)"""
         return Scene(self, desc, build_params)
 
     def tonemap_device(self, d_accum_ptr, num_floats, total_spp, d_out_ptr):
@@ -222,7 +249,8 @@ class Scene:
         self.ctx, self.L = ctx, ctx.L
         self.h = C.c_void_p()
         bp = C.byref(build_params) if build_params is not None else None
-        self.L.check(self.L.lib.rtb_scene_create(ctx.h, C.byref(desc), bp, C.byref(self.h)))
+        create = self.L.lib.rtb_scene_create_instanced if isinstance(desc, InstancedSceneDesc) else self.L.lib.rtb_scene_create
+        self.L.check(create(ctx.h, C.byref(desc), bp, C.byref(self.h)))
 
     def stats(self):
         s = BvhStats()

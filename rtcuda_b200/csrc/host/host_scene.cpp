@@ -125,7 +125,38 @@ float lcg01(uint32_t &s) { return (float)(lcg(s) >> 8) * (1.0f / 16777216.0f); }
 struct rtb_host_scene {
     Builder b;
     float lookfrom[3], lookat[3], up[3], vfov;
+    // instanced form (rtb_host_scene_build_instanced): b holds the meshes in object space
+    std::vector<int64_t> mesh_first;
+    std::vector<rtb_instance> instances;
 };
+
+namespace {
+void default_camera(rtb_host_scene *hs) {  // main.cu:162-166
+    hs->lookfrom[0] = 0.5f; hs->lookfrom[1] = 0.5f; hs->lookfrom[2] = 1.5f;
+    hs->lookat[0] = 0.5f; hs->lookat[1] = 0.5f; hs->lookat[2] = 0.f;
+    hs->up[0] = 0.f; hs->up[1] = 1.f; hs->up[2] = 0.f;
+    hs->vfov = 37.8f;
+}
+rtb_instance make_instance(int mesh, int material, const M4 &t) {
+    rtb_instance in;
+    in.mesh = mesh; in.material = material;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) in.xform[4 * r + c] = t.m[r][c];
+    return in;
+}
+// the placement of bunny (gx, gz) of RTB_SCENE_S2: shared by the flat and the instanced generator
+M4 s2_placement(const M4 &base, uint32_t &s, int gx, int gz, int grid) {
+    const float cx = 0.1557f, cz = -0.12065f, foot = 0.3114f;
+    const float cell = 1.f / (float)grid;
+    const float ang = 6.2831853f * lcg01(s);
+    const float sc = (0.70f + 0.25f * lcg01(s)) * cell / foot;
+    const float jx = (lcg01(s) - 0.5f) * 0.15f * cell, jz = (lcg01(s) - 0.5f) * 0.15f * cell;
+    M4 t = composite(base, translate(-cx, 0.f, -cz));
+    t = composite(t, rotate_y(ang));
+    t = composite(t, scale(sc, sc, sc));
+    t = composite(t, translate(((float)gx + 0.5f) * cell + jx, 0.f, -((float)gz + 0.5f) * cell + jz));
+    return t;
+}
+}  // namespace
 
 extern "C" {
 
@@ -169,29 +200,95 @@ int rtb_host_scene_build(int32_t kind, const float *mv, int64_t nv, const int32_
         // each instance is rotated about Y around its footprint centre, scaled
         // into its floor cell and dropped on a jittered grid over the floor.
         uint32_t s = seed ? seed : 1234u;
-        const float cx = 0.1557f, cz = -0.12065f, foot = 0.3114f;
-        const float cell = 1.f / (float)grid;
         for (int gz = 0; gz < grid; ++gz)
-            for (int gx = 0; gx < grid; ++gx) {
-                const float ang = 6.2831853f * lcg01(s);
-                const float sc = (0.70f + 0.25f * lcg01(s)) * cell / foot;
-                const float jx = (lcg01(s) - 0.5f) * 0.15f * cell, jz = (lcg01(s) - 0.5f) * 0.15f * cell;
-                M4 t = composite(base, translate(-cx, 0.f, -cz));
-                t = composite(t, rotate_y(ang));
-                t = composite(t, scale(sc, sc, sc));
-                t = composite(t, translate(((float)gx + 0.5f) * cell + jx, 0.f, -((float)gz + 0.5f) * cell + jz));
-                add_mesh(b, t, mv, nv, mf, nf, brown);
-            }
+            for (int gx = 0; gx < grid; ++gx) add_mesh(b, s2_placement(base, s, gx, gz, grid), mv, nv, mf, nf, brown);
         cornell_shell(b, red, green, white);
     } else {
         delete hs;
         return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_build: unknown scene kind");
     }
-    // camera, main.cu:162-166
-    hs->lookfrom[0] = 0.5f; hs->lookfrom[1] = 0.5f; hs->lookfrom[2] = 1.5f;
-    hs->lookat[0] = 0.5f; hs->lookat[1] = 0.5f; hs->lookat[2] = 0.f;
-    hs->up[0] = 0.f; hs->up[1] = 1.f; hs->up[2] = 0.f;
-    hs->vfov = 37.8f;
+    default_camera(hs);
+    *out = hs;
+    return RTB_OK;
+}
+
+// Instanced form: the meshes stay in object space, the placements become instance transforms.
+int rtb_host_scene_build_instanced(int32_t kind, const float *mv, int64_t nv, const int32_t *mf, int64_t nf, int32_t grid,
+                                   uint32_t seed, rtb_host_scene **out) {
+    if (!out || !mv || !mf || nv <= 0 || nf <= 0) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_build_instanced: null mesh");
+    if (kind != RTB_SCENE_S2 && kind != RTB_SCENE_S1) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_build_instanced: RTB_SCENE_S1 or RTB_SCENE_S2");
+    rtb_host_scene *hs = new rtb_host_scene();
+    Builder &b = hs->b;
+    const int red = b.add_material(RTB_MATTE, 0.65f, 0.05f, 0.05f, 0.f);
+    const int green = b.add_material(RTB_MATTE, 0.12f, 0.45f, 0.15f, 0.f);
+    const int white = b.add_material(RTB_MATTE, 0.73f, 0.73f, 0.73f, 0.f);
+    const int brown = b.add_material(RTB_MATTE, 0.62f, 0.57f, 0.54f, 0.f);
+    // mesh 0: the bunny as loaded
+    for (int64_t f = 0; f < nf; ++f) b.tri(&mv[3 * (size_t)mf[3 * f]], &mv[3 * (size_t)mf[3 * f + 1]], &mv[3 * (size_t)mf[3 * f + 2]], brown);
+    hs->mesh_first.push_back(0);
+    hs->mesh_first.push_back((int64_t)b.mat.size());
+    // mesh 1: walls + emitters
+    cornell_shell(b, red, green, white);
+    hs->mesh_first.push_back((int64_t)b.mat.size());
+    M4 base = translate(0.0946899f, -0.0329874f, -0.0587997f);
+    base = composite(base, scale(2.f, 2.f, 2.f));
+    if (kind == RTB_SCENE_S1) {
+        hs->instances.push_back(make_instance(0, -1, composite(base, translate(0.3f, 0.f, -0.5f))));
+    } else {
+        if (grid <= 0) grid = 12;
+        uint32_t s = seed ? seed : 1234u;
+        for (int gz = 0; gz < grid; ++gz)
+            for (int gx = 0; gx < grid; ++gx) hs->instances.push_back(make_instance(0, -1, s2_placement(base, s, gx, gz, grid)));
+    }
+    hs->instances.push_back(make_instance(1, -1, translate(0.f, 0.f, 0.f)));
+    default_camera(hs);
+    *out = hs;
+    return RTB_OK;
+}
+
+int rtb_host_scene_instanced_desc(const rtb_host_scene *hs, rtb_instanced_scene_desc *d) {
+    if (!hs || !d) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_instanced_desc: null");
+    if (hs->instances.empty()) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_instanced_desc: not an instanced scene");
+    rtb_host_scene_desc(hs, &d->geometry);
+    d->num_meshes = (int32_t)hs->mesh_first.size() - 1;
+    d->mesh_first = hs->mesh_first.data();
+    d->num_instances = (int32_t)hs->instances.size();
+    d->instances = hs->instances.data();
+    return RTB_OK;
+}
+
+// Every instance's triangles through its transform with the reference's vertex arithmetic (Transform::apply,
+// transform.hpp:26-33), instance after instance; lights follow their triangles.
+int rtb_instanced_flatten(const rtb_instanced_scene_desc *D, rtb_host_scene **out) {
+    if (!D || !out || !D->mesh_first || !D->instances || D->num_meshes <= 0 || D->num_instances <= 0 || !D->geometry.vertices ||
+        !D->geometry.material_ids)
+        return rtb::set_error(RTB_ERR_INVALID, "rtb_instanced_flatten: incomplete description");
+    const rtb_scene_desc &g = D->geometry;
+    rtb_host_scene *hs = new rtb_host_scene();
+    Builder &b = hs->b;
+    b.materials.assign(g.materials, g.materials + g.num_materials);
+    if (g.num_lights) b.lights.assign(g.lights, g.lights + g.num_lights);
+    for (int i = 0; i < D->num_instances; ++i) {
+        const rtb_instance &in = D->instances[i];
+        if (in.mesh < 0 || in.mesh >= D->num_meshes) { delete hs; return rtb::set_error(RTB_ERR_INVALID, "rtb_instanced_flatten: mesh out of range"); }
+        M4 t = translate(0.f, 0.f, 0.f);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) t.m[r][c] = in.xform[4 * r + c];
+        for (int64_t k = D->mesh_first[in.mesh]; k < D->mesh_first[in.mesh + 1]; ++k) {
+            float p[3][3];
+            for (int v = 0; v < 3; ++v) {
+                double w[3] = {g.vertices[9 * k + 3 * v], g.vertices[9 * k + 3 * v + 1], g.vertices[9 * k + 3 * v + 2]};
+                apply(t, w);
+                p[v][0] = (float)w[0]; p[v][1] = (float)w[1]; p[v][2] = (float)w[2];
+            }
+            b.tri(p[0], p[1], p[2], in.material >= 0 ? in.material : g.material_ids[k]);
+            const int l = g.light_ids ? g.light_ids[k] : -1;
+            if (l >= 0) {
+                b.light.back() = l;
+                if (l < g.num_lights && b.lights[(size_t)l].type == RTB_AREA_LIGHT) b.lights[(size_t)l].triangle = (int64_t)b.mat.size() - 1;
+            }
+        }
+    }
+    default_camera(hs);
     *out = hs;
     return RTB_OK;
 }
@@ -362,10 +459,7 @@ int rtb_host_scene_load(const char *path, rtb_host_scene **out) {
          fread(b.lights.data(), sizeof(rtb_light), (size_t)nl, f) == (size_t)nl;
     fclose(f);
     if (!ok) { delete hs; return rtb::set_error(RTB_ERR_IO, "truncated scene file"); }
-    hs->lookfrom[0] = 0.5f; hs->lookfrom[1] = 0.5f; hs->lookfrom[2] = 1.5f;
-    hs->lookat[0] = 0.5f; hs->lookat[1] = 0.5f; hs->lookat[2] = 0.f;
-    hs->up[0] = 0.f; hs->up[1] = 1.f; hs->up[2] = 0.f;
-    hs->vfov = 37.8f;
+    default_camera(hs);
     *out = hs;
     return RTB_OK;
 }

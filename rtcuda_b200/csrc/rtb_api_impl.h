@@ -85,6 +85,16 @@ int rtb_scene_create_from_primitives(rtb_context *ctx, const void *h_primitives,
         *out = new rtb_scene{ctx, impl};
     });
 }
+int rtb_scene_create_instanced(rtb_context *ctx, const rtb_instanced_scene_desc *desc, const rtb_build_params *bp, rtb_scene **out) {
+    if (!ctx || !desc || !out) return rtb::set_error(RTB_ERR_INVALID, "rtb_scene_create_instanced: null argument");
+    *out = nullptr;
+    return rtb::guarded([&] {
+        ctx->be.make_current();
+        rtb_build_params p = bp ? *bp : rtb::build_defaults();
+        auto *impl = rtb::scene_from_instanced(ctx->be, *desc, p);
+        *out = new rtb_scene{ctx, impl};
+    });
+}
 int rtb_scene_destroy(rtb_scene *s) {
     return rtb::guarded([&] {
         if (!s) return;
@@ -151,7 +161,7 @@ int rtb_trace_any(rtb_scene *s, const rtb_ray *h_rays, const int32_t *h_excluded
         be.upload(dr, h_rays, (size_t)n);
         if (h_excluded) {
             for (int64_t i = 0; i < n; ++i)
-                if (h_excluded[i] >= s->impl->n) { be.free(dr); be.free(dout); throw rtb::Error(RTB_ERR_INVALID, "excluded triangle out of range"); }
+                if (h_excluded[i] >= s->impl->n_flat) { be.free(dr); be.free(dout); throw rtb::Error(RTB_ERR_INVALID, "excluded triangle out of range"); }
             dex = be.template alloc<int32_t>((size_t)n);
             be.upload(dex, h_excluded, (size_t)n);
         }

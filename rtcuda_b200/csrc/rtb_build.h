@@ -388,8 +388,10 @@ RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
                 const B2Node x = a.nodes[ni];
                 if (x.right < 0) {
                     const int dst = tri_base + tri_off;
-                    a.tris_out[dst] = a.tri_in[x.left];
-                    a.meta_out[dst] = a.meta_in[x.left];
+                    if (a.tri_in) {  // (null: the tree over the instances of a two-level scene, whose leaves are boxes)
+                        a.tris_out[dst] = a.tri_in[x.left];
+                        a.meta_out[dst] = a.meta_in[x.left];
+                    }
                     a.prim_out[dst] = x.left;
                     a.leaf_of_prim[x.left] = dst;
                     tri_off++;
@@ -413,6 +415,29 @@ RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
 #undef RTB_PACK4
     Q4 *dst = a.nodes8 + (size_t)item.wide * kNodeWords;
     dst[0] = w0; dst[1] = w1; dst[2] = w2; dst[3] = w3; dst[4] = w4;
+}
+
+// ------------------------------------------------------------ two-level scenes
+// bounds of pre-computed boxes (the instances' world boxes) instead of prim_setup
+RTB_HD void box_bounds_body(const F4 *lo, const F4 *hi, int32_t *scene_bounds, int n, int i) {
+    if (i >= n) return;
+    const F4 l = lo[i], h = hi[i];
+    atomic_min_i(scene_bounds + 0, float_to_ordered(l.x));
+    atomic_min_i(scene_bounds + 1, float_to_ordered(l.y));
+    atomic_min_i(scene_bounds + 2, float_to_ordered(l.z));
+    atomic_max_i(scene_bounds + 3, float_to_ordered(h.x));
+    atomic_max_i(scene_bounds + 4, float_to_ordered(h.y));
+    atomic_max_i(scene_bounds + 5, float_to_ordered(h.z));
+}
+// a mesh's tree is built with indices relative to itself; in the scene's arrays its nodes start at node_off and its
+// triangles at tri_off
+RTB_HD void rebase_node_body(const Q4 *src, Q4 *dst, uint32_t node_off, uint32_t tri_off, int n, int i) {
+    if (i >= n) return;
+    const Q4 *s = src + (size_t)i * kNodeWords;
+    Q4 *d = dst + (size_t)i * kNodeWords;
+    Q4 w1 = s[1];
+    w1.x += node_off; w1.y += tri_off;
+    d[0] = s[0]; d[1] = w1; d[2] = s[2]; d[3] = s[3]; d[4] = s[4];
 }
 
 // area lights refer to their triangle by leaf-order index after the build

@@ -36,7 +36,35 @@ struct Bvh8View {
     const int32_t *prim; // leaf order -> caller's triangle index
     int32_t num_nodes;
     int32_t num_tris;
+    // two-level scenes (rtb_scene_create_instanced), null / 0 otherwise: the tree rooted at node 0 is then the one
+    // over the INSTANCES (its leaf entries index `top_inst`), every mesh has its own tree further up the same node
+    // array (object space, indices already absolute), and `inst` holds kInstWords words per instance
+    const F4 *inst;
+    const int32_t *top_inst;  // leaf order of the top tree -> instance
+    int32_t num_inst;
 };
+
+// Instance record, 8 x 16 bytes: rows of the world->object matrix (w = translation), rows of the object->world
+// matrix, {root node of the mesh's tree, material word (index | type << 24) or -1, first id of the instance in the
+// flattened numbering, first caller index of the mesh} as raw ints, one spare word.
+constexpr int kInstWords = 8;
+struct InstInfo {
+    int32_t root, material, flat_first, mesh_first;
+};
+RTB_HD InstInfo inst_info(const F4 *inst, int i) {
+    const F4 w = ldg(inst + (size_t)i * kInstWords + 6);
+    InstInfo r;
+    r.root = f2i(w.x); r.material = f2i(w.y); r.flat_first = f2i(w.z); r.mesh_first = f2i(w.w);
+    return r;
+}
+RTB_HD V3 xform_point(const F4 &r0, const F4 &r1, const F4 &r2, V3 p) {
+    return v3(ffma(r0.z, p.z, ffma(r0.y, p.y, ffma(r0.x, p.x, r0.w))), ffma(r1.z, p.z, ffma(r1.y, p.y, ffma(r1.x, p.x, r1.w))),
+              ffma(r2.z, p.z, ffma(r2.y, p.y, ffma(r2.x, p.x, r2.w))));
+}
+RTB_HD V3 xform_vector(const F4 &r0, const F4 &r1, const F4 &r2, V3 d) {
+    return v3(ffma(r0.z, d.z, ffma(r0.y, d.y, fmul(r0.x, d.x))), ffma(r1.z, d.z, ffma(r1.y, d.y, fmul(r1.x, d.x))),
+              ffma(r2.z, d.z, ffma(r2.y, d.y, fmul(r2.x, d.x))));
+}
 
 struct HitRec {
     float t, u, v;
@@ -54,6 +82,26 @@ RTB_HD Tri48 load_tri(const F4 *tris, int idx) {
     t.e1y = b.x; t.e1z = b.y; t.e2x = b.z; t.e2y = b.w;
     t.e2z = c.x; t.nx = c.y; t.ny = c.z; t.nz = c.w;
     return t;
+}
+
+// id of a hit in the caller's numbering: the triangle list of a flat scene, the flattened list of an instanced one
+RTB_HD int hit_prim(const Bvh8View &B, int tri, int inst) {
+    const int p = B.prim[tri];
+    if (inst < 0) return p;
+    const InstInfo in = inst_info(B.inst, inst);
+    return in.flat_first + (p - in.mesh_first);
+}
+// A triangle of an instance in WORLD space: its vertices through the object->world matrix, then the record the
+// reference's host constructor derives from vertices (triangle.cuh:6-7) — what the flattened scene stores, up to the
+// rounding of the transform.  inst < 0: the stored record.
+RTB_HD Tri48 load_tri_world(const Bvh8View &B, int idx, int inst) {
+    const Tri48 t = load_tri(B.tris, idx);
+    if (inst < 0) return t;
+    const F4 *m = B.inst + (size_t)inst * kInstWords + 3;
+    const F4 r0 = ldg(m), r1 = ldg(m + 1), r2 = ldg(m + 2);
+    const V3 p0 = tri_p0(t);
+    return tri_from_vertices(xform_point(r0, r1, r2, p0), xform_point(r0, r1, r2, vsub(p0, tri_e1(t))),
+                             xform_point(r0, r1, r2, vadd(p0, tri_e2(t))));
 }
 
 // ------------------------------------------------------------ quantisation
@@ -203,7 +251,15 @@ constexpr int kStackSize = 48;
 // leaf-order index differs from `excluded` (the light's own triangle,
 // bvh.cuh:239-248).  Otherwise find the closest hit with the reference's
 // accept rule 0 < t <= tmax, tmax shrinking (bvh.cuh:222-236).
-template <bool ANY, bool COUNT>
+//
+// INST (two-level scenes): the tree at node 0 is the one over the instances.  The leaf lists of that tree name
+// instances instead of triangles; entering one takes the ray into the mesh's object space (origin through the
+// world->object matrix, direction through its linear part WITHOUT renormalising, so t means the same in both spaces
+// and tmax / the accept rule carry over) and continues at the root of the mesh's own tree on the same stack.  The
+// instance is left when the stack is back at the height it was entered at; the world ray is then set up again from
+// the (o, d) the caller still holds.  What is left of a leaf list waits on the stack as an entry whose top byte is 0
+// (node groups always have hit bits there).
+template <bool ANY, bool COUNT, bool INST = false>
 struct Traversal {
     RaySetup r;
     float tmax;
@@ -212,6 +268,11 @@ struct Traversal {
     HitRec hit;
     bool found;
     TraceCounters cnt;
+    // INST only (dead otherwise)
+    int32_t cur;            // instance being traversed, -1 = the tree over the instances
+    int32_t sp_enter;       // stack height at which it was entered
+    int32_t hit_inst;       // instance of `hit`
+    int32_t excluded_inst;  // ANY: instance `excluded` belongs to, -1 = whichever
     // the stack lives OUTSIDE the struct (caller-provided arrays) so that the
     // scalar state above stays in registers instead of following the
     // dynamically indexed arrays into local memory
@@ -223,6 +284,7 @@ struct Traversal {
         hit.t = 0.f; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
         found = false;
         cnt.nodes = 0; cnt.tris = 0;
+        cur = -1; sp_enter = 0; hit_inst = -1; excluded_inst = -1;
     }
     // The three parts of one traversal step.  The persistent kernels call them separately so that
     // the triangle tests of a whole warp can be pooled (rtb_cuda.cu, coop_triangles); step() below
@@ -258,9 +320,10 @@ struct Traversal {
         (void)B;
         if (0.0f < t && t <= tmax) {
             if (ANY) {
-                if (idx != excluded) { found = true; return true; }
+                if (idx != excluded || (INST && excluded_inst >= 0 && cur != excluded_inst)) { found = true; return true; }
             } else {
                 tmax = t; hit.t = t; hit.u = u; hit.v = v; hit.tri = idx; found = true;
+                if (INST) hit_inst = cur;
             }
         }
         return false;
@@ -272,6 +335,52 @@ struct Traversal {
             --sp; gx = stack_x[sp]; gy = stack_y[sp];
         }
         return true;
+    }
+    // ---- INST ----
+    // (tx, ty) is a leaf list of the top tree: enter the instance of its highest entry.  The node group still pending
+    // and the rest of the list go on the stack first, so they are resumed when the instance has been left.
+    RTB_HD void enter_instance(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y, uint32_t tx, uint32_t &ty, V3 o, V3 d) {
+        const int bit = bfind(ty);
+        ty &= ~(1u << bit);
+        if (gy & 0xff000000u) { stack_x[sp] = gx; stack_y[sp] = gy; ++sp; }
+        if (ty) { stack_x[sp] = tx; stack_y[sp] = ty; ++sp; ty = 0u; }
+        cur = B.top_inst[tx + (uint32_t)bit];
+        sp_enter = sp;
+        const F4 *m = B.inst + (size_t)cur * kInstWords;
+        const F4 r0 = ldg(m), r1 = ldg(m + 1), r2 = ldg(m + 2);
+        const int root = f2i(ldg(m + 6).x);
+        r = ray_setup(xform_point(r0, r1, r2, o), xform_vector(r0, r1, r2, d));
+        gx = (uint32_t)root; gy = 0x80000000u;
+    }
+    // next pending node group or leaf list; (o, d) = the world ray, set up again when an instance is left
+    RTB_HD bool advance_inst(const uint32_t *stack_x, const uint32_t *stack_y, uint32_t &tx, uint32_t &ty, V3 o, V3 d) {
+        if ((gy & 0xff000000u) == 0) {
+            if (cur >= 0 && sp == sp_enter) { cur = -1; r = ray_setup(o, d); }
+            if (sp == 0) return false;
+            --sp;
+            const uint32_t x = stack_x[sp], y = stack_y[sp];
+            if (y & 0xff000000u) { gx = x; gy = y; }
+            else { tx = x; ty = y; gx = 0u; gy = 0u; }  // the rest of a leaf list of the top tree
+        }
+        return true;
+    }
+    RTB_HD bool step_inst(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y, uint32_t &tx, uint32_t &ty, V3 o, V3 d) {
+        if (ty == 0u) node_part(B, stack_x, stack_y, tx, ty);
+        if (cur < 0) {
+            if (ty) enter_instance(B, stack_x, stack_y, tx, ty, o, d);
+        } else {
+            while (ty) {
+                const int bit = bfind(ty);
+                ty &= ~(1u << bit);
+                const int idx = (int)(tx + (uint32_t)bit);
+                const Tri48 tr = load_tri(B.tris, idx);
+                if (COUNT) cnt.tris++;
+                float u, v;
+                const float t = tri_candidate(tr, r.o, r.d, u, v);
+                if (accept(B, idx, t, u, v)) return false;
+            }
+        }
+        return advance_inst(stack_x, stack_y, tx, ty, o, d);
     }
     // one node (its 8 child boxes) plus the triangles it exposes; false when the ray is finished
     RTB_HD bool step(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y) {
@@ -301,6 +410,29 @@ RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t exclud
     hit = T.hit;
     if (COUNT) { cnt->nodes = T.cnt.nodes; cnt->tris = T.cnt.tris; }
     return T.found;
+}
+// the same through a two-level scene; hit_inst = instance of the hit (-1: miss), excluded_inst = instance of
+// `excluded` or -1 (whichever instance)
+template <bool ANY, bool COUNT>
+RTB_HD bool bvh8_trace_inst(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, int32_t excluded_inst, HitRec &hit,
+                            int32_t &hit_inst, TraceCounters *cnt) {
+    Traversal<ANY, COUNT, true> T;
+    uint32_t stack_x[kStackSize], stack_y[kStackSize];
+    T.init(o, d, tmax, excluded);
+    T.excluded_inst = excluded_inst;
+    uint32_t tx = 0u, ty = 0u;
+    while (T.step_inst(B, stack_x, stack_y, tx, ty, o, d)) {}
+    hit = T.hit; hit_inst = T.hit_inst;
+    if (COUNT) { cnt->nodes = T.cnt.nodes; cnt->tris = T.cnt.tris; }
+    return T.found;
+}
+// whichever the scene is
+template <bool ANY, bool COUNT>
+RTB_HD bool scene_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, int32_t excluded_inst, HitRec &hit,
+                        int32_t &hit_inst, TraceCounters *cnt) {
+    if (B.inst) return bvh8_trace_inst<ANY, COUNT>(B, o, d, tmax, excluded, excluded_inst, hit, hit_inst, cnt);
+    hit_inst = -1;
+    return bvh8_trace<ANY, COUNT>(B, o, d, tmax, excluded, hit, cnt);
 }
 
 }  // namespace rtb

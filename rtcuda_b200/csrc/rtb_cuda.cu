@@ -185,13 +185,15 @@ __device__ __forceinline__ void own_triangles(const Bvh8View &B, Traversal<ANY, 
     }
 }
 
-template <bool ANY, bool POOL>
+// INST: two-level scenes (rtb_bvh8.h, Traversal<.., INST>): stepped schedule only; the world ray a lane needs when it
+// enters or leaves an instance is the one in its shared-memory slot (ws.ro / ws.rd).
+template <bool ANY, bool POOL, bool INST = false>
 __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveState &W, const SceneView &S, FetchTuning tune) {
     const int n = ANY ? W.c->n_shadow : W.c->n_extend;
     int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanes_below = (1u << lane) - 1u;
-    Traversal<ANY, false> T;
+    Traversal<ANY, false, INST> T;
     uint32_t stack_x[kStackSize], stack_y[kStackSize];
     bool has = false, exhausted = false, pending = false;
     int qi = 0;
@@ -211,9 +213,10 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
             } else if (T.hit.tri < 0) {
                 if (W.has_env) extend_miss(W, __float_as_uint(ws.ro[lane].w), v3(fw.x, fw.y, fw.z));
             } else {
-                const int mat = S.tri_meta[T.hit.tri].material;
+                const int mat = INST ? hit_material(S, T.hit.tri, T.hit_inst) : S.tri_meta[T.hit.tri].material;
                 const int type = mat >> 24;
                 const int j = hit_queue_push(W, type);
+                if (INST) W.hit_inst[j] = T.hit_inst;
                 F4 beta; beta.x = fw.x; beta.y = fw.y; beta.z = fw.z; beta.w = fw.w;
                 const float4 o = ws.ro[lane], d = ws.rd[lane];
                 F4 ma; ma.x = d.x; ma.y = d.y; ma.z = d.z; ma.w = o.w;
@@ -275,7 +278,36 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
         }
         const int keep_going = exhausted ? 1 : tune.refill;
         do {
-            if (!POOL && tune.tri_step > 0) {
+            if constexpr (INST) {
+                if (has && ty == 0u) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+                if (has && T.cur < 0) {  // (tx, ty) is a leaf list of the top tree: enter its nearest instance
+                    if (ty != 0u) {
+                        const float4 o = ws.ro[lane], d = ws.rd[lane];
+                        T.enter_instance(S.bvh, stack_x, stack_y, tx, ty, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
+                    }
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < tune.tri_step && ty != 0u; ++k) {
+                        const int bit = 31 - __clz(ty);
+                        ty &= ~(1u << bit);
+                        const int idx = (int)(tx + (uint32_t)bit);
+                        const Tri48 tr = load_tri(S.bvh.tris, idx);
+                        float u, v;
+                        const float t = tri_candidate(tr, T.r.o, T.r.d, u, v);
+                        if (T.accept(S.bvh, idx, t, u, v)) { has = false; pending = true; ty = 0u; }
+                    }
+                }
+                if (has && ty == 0u) {
+                    const float4 o = ws.ro[lane], d = ws.rd[lane];
+                    if (!T.advance_inst(stack_x, stack_y, tx, ty, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z))) { has = false; pending = true; }
+                }
+            } else if constexpr (POOL) {
+                tx = 0u; ty = 0u;
+                if (has) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+                pooled_triangles<ANY>(ws, S.bvh, T, tx, ty, has, pending, lane, lanes_below);
+                ty = 0u;
+                if (has && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
+            } else if (tune.tri_step > 0) {
                 // stepped: at most tri_step triangle tests per lane and step; a lane with more keeps them for
                 // the next steps and sits out the node phase meanwhile (its own order of events is unchanged:
                 // the next node is fetched only once all triangles of the current one are tested), so one
@@ -295,8 +327,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
             } else {
                 tx = 0u; ty = 0u;
                 if (has) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
-                if (POOL) pooled_triangles<ANY>(ws, S.bvh, T, tx, ty, has, pending, lane, lanes_below);
-                else own_triangles<ANY>(S.bvh, T, tx, ty, has, pending);
+                own_triangles<ANY>(S.bvh, T, tx, ty, has, pending);
                 ty = 0u;
                 if (has && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
             }
@@ -311,17 +342,21 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
 // (tri_step 0); at most tri_step per step, the rest carried over (default, 2: C2 39.5 -> 39.1 ms, C3 116.5 ->
 // 108.9 ms); pooled per warp in shared memory (POOL, RTB_POOLED=1: C3 113.5 ms, C2 47.9 ms).
 // Tried and dropped: prefetching the next node into L2 during the triangle tests (C3 116 -> 140 ms, C2 40 -> 49 ms).
-template <int WHICH, bool POOL>
+template <int WHICH, bool POOL, bool INST = false>
 __global__ void __launch_bounds__(kBlock, 4) k_trace(WaveState W, SceneView S, FetchTuning tune) {
     __shared__ WarpScratch scratch[kBlock / 32];
     WarpScratch &ws = scratch[threadIdx.x >> 5];
-    if (WHICH & 1) persistent_trace<false, POOL>(ws, W, S, tune);
+    if (WHICH & 1) persistent_trace<false, POOL, INST>(ws, W, S, tune);
     if (WHICH == 3) __syncwarp();
-    if (WHICH & 2) persistent_trace<true, POOL>(ws, W, S, tune);
+    if (WHICH & 2) persistent_trace<true, POOL, INST>(ws, W, S, tune);
 }
 template <int WHICH>
 static void launch_trace_kernel(int grid, cudaStream_t st, bool pooled, const WaveState &W, const SceneView &S, const FetchTuning &tune) {
-    if (pooled) k_trace<WHICH, true><<<grid, kBlock, 0, st>>>(W, S, tune);
+    if (S.bvh.inst) {  // two-level scene: stepped schedule
+        FetchTuning t = tune;
+        if (t.tri_step < 1) t.tri_step = 2;
+        k_trace<WHICH, false, true><<<grid, kBlock, 0, st>>>(W, S, t);
+    } else if (pooled) k_trace<WHICH, true><<<grid, kBlock, 0, st>>>(W, S, tune);
     else k_trace<WHICH, false><<<grid, kBlock, 0, st>>>(W, S, tune);
 }
 // one thread per queue entry (A/B against the persistent kernels; COUNT = work counters)
@@ -448,7 +483,7 @@ struct CudaBackend {
     }
     void shade(const ShadeK &k) {
         const int grid = num_sms_ * shade_blocks_per_sm(k.type);  // one resident wave: the kernels are grid-stride loops
-        if (k.rc.flags & (RTB_RENDER_TRUE_MIS | RTB_RENDER_RR_TERMINATE)) {  // beyond-the-reference estimator
+        if ((k.rc.flags & (RTB_RENDER_TRUE_MIS | RTB_RENDER_RR_TERMINATE)) || k.S.bvh.inst) {  // beyond-the-reference estimator, instanced scenes
             if (k.type == 0) k_shade<0, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else if (k.type == 1) k_shade<1, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
             else if (k.type == 2) k_shade<2, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);

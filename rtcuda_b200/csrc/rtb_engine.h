@@ -11,6 +11,7 @@
 // blocking 4-byte device->host copies per iteration); here an iteration is 4
 // launches (shade, generate, control, trace), and the host looks at one `done` word every few iterations.
 #pragma once
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -76,6 +77,7 @@ struct TraceClosestK {
         if (i >= n) return;
         const rtb_ray r = rays[i];
         HitRec h;
+        int32_t hi = -1;
         if (!ray_is_finite(r)) {  // can hit nothing, would walk the whole tree
             rtb_hit o; o.t = 0.f; o.u = 0.f; o.v = 0.f; o.prim = -1;
             hits[i] = o;
@@ -83,17 +85,17 @@ struct TraceClosestK {
         }
         if (counts) {
             TraceCounters c; c.nodes = 0; c.tris = 0;
-            bvh8_trace<false, true>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, -1, h, &c);
+            scene_trace<false, true>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, -1, -1, h, hi, &c);
 #if defined(__CUDA_ARCH__)
             atomicAdd(counts, (unsigned long long)c.nodes); atomicAdd(counts + 1, (unsigned long long)c.tris);
 #else
             counts[0] += c.nodes; counts[1] += c.tris;
 #endif
         } else {
-            bvh8_trace<false, false>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, -1, h, nullptr);
+            scene_trace<false, false>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, -1, -1, h, hi, nullptr);
         }
         rtb_hit o;
-        o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.tri >= 0 ? B.prim[h.tri] : -1;
+        o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.tri >= 0 ? hit_prim(B, h.tri, hi) : -1;
         hits[i] = o;
     }
 };
@@ -103,10 +105,21 @@ struct TraceAnyK {
         if (i >= n) return;
         const rtb_ray r = rays[i];
         if (!ray_is_finite(r)) { occluded[i] = 0; return; }
-        int ex = excluded ? excluded[i] : -1;
+        int ex = excluded ? excluded[i] : -1, ex_inst = -1;
+        if (ex >= 0 && B.inst) {  // id in the flattened numbering -> (instance, triangle of its mesh)
+            int lo = 0, hi = B.num_inst - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (inst_info(B.inst, mid).flat_first <= ex) lo = mid; else hi = mid - 1;
+            }
+            const InstInfo in = inst_info(B.inst, lo);
+            ex_inst = lo;
+            ex = ex - in.flat_first + in.mesh_first;
+        }
         if (ex >= 0) ex = leaf_of_prim[ex];
         HitRec h;
-        occluded[i] = bvh8_trace<true, false>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, ex, h, nullptr) ? 1 : 0;
+        int32_t hi_ = -1;
+        occluded[i] = scene_trace<true, false>(B, v3(r.origin[0], r.origin[1], r.origin[2]), v3(r.dir[0], r.dir[1], r.dir[2]), r.tmax, ex, ex_inst, h, hi_, nullptr) ? 1 : 0;
     }
 };
 
@@ -119,18 +132,19 @@ struct AovK {
         V3 o, d;
         camera_ray(cam, fdiv(fadd((float)(i % width), 0.5f), (float)width), fdiv(fadd((float)(i / width), 0.5f), (float)height), o, d);
         HitRec h;
-        bvh8_trace<false, false>(S.bvh, o, d, FLT_MAX, -1, h, nullptr);
+        int32_t hi = -1;
+        scene_trace<false, false>(S.bvh, o, d, FLT_MAX, -1, -1, h, hi, nullptr);
         V3 al = v3(0.f), n = v3(0.f);
         if (h.tri >= 0) {
-            const rtb_material m = S.materials[S.tri_meta[h.tri].material & 0xffffff];
+            const rtb_material m = S.materials[hit_material(S, h.tri, hi) & 0xffffff];
             al = v3(m.albedo[0], m.albedo[1], m.albedo[2]);
-            n = vneg(vnormalize(tri_n(load_tri(S.bvh.tris, h.tri))));  // the shading normal of render.cuh:153
+            n = vneg(vnormalize(tri_n(load_tri_world(S.bvh, h.tri, hi))));  // the shading normal of render.cuh:153
             if (vdot(n, d) > 0.f) n = vneg(n);
         }
         if (albedo) { albedo[3 * (size_t)i] = al.x; albedo[3 * (size_t)i + 1] = al.y; albedo[3 * (size_t)i + 2] = al.z; }
         if (normal) { normal[3 * (size_t)i] = n.x; normal[3 * (size_t)i + 1] = n.y; normal[3 * (size_t)i + 2] = n.z; }
         if (depth) depth[i] = h.tri >= 0 ? h.t : 0.f;
-        if (prim) prim[i] = h.tri >= 0 ? S.bvh.prim[h.tri] : -1;
+        if (prim) prim[i] = h.tri >= 0 ? hit_prim(S.bvh, h.tri, hi) : -1;
     }
 };
 
@@ -139,7 +153,10 @@ constexpr int kMaxPipelines = 2;
 template <class BE>
 struct SceneT {
     BE *be = nullptr;
-    int64_t n = 0;
+    int64_t n = 0;       // triangles stored
+    int64_t n_flat = 0;  // triangles of the flattened scene (= n unless the scene is instanced): range of the hit ids
+    // two-level scenes (scene_from_instanced): instance records, leaf order of the top tree -> instance
+    F4 *inst = nullptr; int32_t *top_inst = nullptr; int32_t num_inst = 0;
     Q4 *nodes8 = nullptr;
     F4 *tris = nullptr;
     TriMeta *meta = nullptr;
@@ -159,6 +176,7 @@ struct SceneT {
         SceneView S;
         S.bvh.nodes = nodes8; S.bvh.tris = tris; S.bvh.prim = prim;
         S.bvh.num_nodes = num_nodes; S.bvh.num_tris = (int32_t)n;
+        S.bvh.inst = inst; S.bvh.top_inst = top_inst; S.bvh.num_inst = num_inst;
         S.tri_meta = meta; S.materials = materials; S.lights = lights;
         S.num_lights = num_lights; S.num_materials = num_materials;
         return S;
@@ -167,8 +185,8 @@ struct SceneT {
         for (int k = 0; k < pipes; ++k) {
             WaveState &w = W[k];
             be->free(w.ea); be->free(w.eb); be->free(w.ec); be->free(w.ma); be->free(w.mb); be->free(w.mc);
-            be->free(w.sh_o); be->free(w.sh_d); be->free(w.sh_L); be->free(w.c); be->free(w.mis);
-            w.mis = nullptr;
+            be->free(w.sh_o); be->free(w.sh_d); be->free(w.sh_L); be->free(w.c); be->free(w.mis); be->free(w.hit_inst);
+            w.mis = nullptr; w.hit_inst = nullptr;
         }
         pool = 0; pipes = 0;
     }
@@ -184,6 +202,7 @@ struct SceneT {
             w.c = be->template alloc<Counters>(1);
             w.pool = p;
             w.mis = nullptr;
+            w.hit_inst = inst ? be->template alloc<int32_t>(kNumMaterialTypes * (size_t)p) : nullptr;
         }
         pool = p; pipes = np;
     }
@@ -192,42 +211,41 @@ struct SceneT {
         free_wave();
         be->free(own_accum);
         be->free(nodes8); be->free(tris); be->free(meta); be->free(prim); be->free(leaf_of_prim);
-        be->free(materials); be->free(lights);
+        be->free(materials); be->free(lights); be->free(inst); be->free(top_inst);
     }
 };
 
 // ---- builder ----
-// tri_in / meta_in / light_tri are device arrays in caller order; vertices may
-// be null when tri_in is already filled (reference-pointer ingest).
+// One 8-wide tree over n primitives.  Triangles: d_vertices (may be null when tri_in is already filled —
+// reference-pointer ingest), tri_in / meta_in device arrays in caller order.  Boxes (box_lo != null: the tree over the
+// instances of a two-level scene): tri_in / meta_in null.  Leaf-order outputs go to caller-allocated arrays of n entries
+// (tris / meta unused for boxes); the nodes come back in an array of their own (indices relative to this tree).
+struct BuiltTree {
+    Q4 *nodes8 = nullptr;
+    int32_t num_nodes = 0;
+    int levels = 0, ploc_iterations = 0;
+    float sah_cost = 0.f;
+    float bounds[6] = {0, 0, 0, 0, 0, 0};  // xmin xmax ymin ymax zmin zmax
+};
+struct BoxBoundsK {
+    const F4 *lo, *hi; int32_t *bounds; int n;
+    RTB_HD void operator()(int i) const { box_bounds_body(lo, hi, bounds, n, i); }
+};
+struct RebaseK {
+    const Q4 *src; Q4 *dst; uint32_t node_off, tri_off; int n;
+    RTB_HD void operator()(int i) const { rebase_node_body(src, dst, node_off, tri_off, n, i); }
+};
+struct AddK {
+    int32_t *p; int32_t v; int n;
+    RTB_HD void operator()(int i) const { if (i < n) p[i] += v; }
+};
 template <class BE>
-void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, TriMeta *meta_in,
-               const int64_t *d_light_tri, const rtb_build_params &bp) {
-    const int64_t n64 = sc.n;
-    if (n64 > 0x3fffffff) throw Error(RTB_ERR_INVALID, "too many triangles (max 2^30-1)");
-    const int n = (int)n64;
+BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriMeta *meta_in, const F4 *box_lo, const F4 *box_hi,
+                     const rtb_build_params &bp, int max_leaf, Tri48 *tris_out, TriMeta *meta_out, int32_t *prim_out,
+                     int32_t *leaf_of_prim) {
+    BuiltTree out;
     if (bp.builder != RTB_BUILDER_PLOC) throw Error(RTB_ERR_INVALID, "unknown BVH builder");
-    const int max_leaf = bp.max_leaf_tris >= 1 && bp.max_leaf_tris <= 3 ? bp.max_leaf_tris : 3;
     const int radius = bp.ploc_radius > 0 ? bp.ploc_radius : 16;
-    auto t0 = be.now();
-    sc.stats = rtb_bvh_stats{};
-    sc.stats.num_triangles = n;
-    sc.tris = (F4 *)be.template alloc<Tri48>(n > 0 ? n : 1);
-    sc.meta = be.template alloc<TriMeta>(n > 0 ? n : 1);
-    sc.prim = be.template alloc<int32_t>(n > 0 ? n : 1);
-    sc.leaf_of_prim = be.template alloc<int32_t>(n > 0 ? n : 1);
-    if (n == 0) {  // empty scene: one node with eight empty slots
-        std::vector<Q4> root(kNodeWords);
-        memset(root.data(), 0, sizeof(Q4) * kNodeWords);
-        root[2].x = root[2].y = root[2].z = root[2].w = 0xffffffffu;  // qlo = 255 > qhi = 0
-        root[3].x = root[3].y = 0xffffffffu;
-        root[0].w = 127u | (127u << 8) | (127u << 16);
-        sc.nodes8 = be.template alloc<Q4>(kNodeWords);
-        be.upload(sc.nodes8, root.data(), kNodeWords);
-        sc.num_nodes = 1;
-        sc.stats.num_nodes = 1;
-        sc.stats.node_bytes = 80;
-        return;
-    }
     // 1. per-triangle records, bounds
     F4 *prim_lo = be.template alloc<F4>(n), *prim_hi = be.template alloc<F4>(n);
     int32_t *bounds = be.template alloc<int32_t>(6);
@@ -235,9 +253,15 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
         int32_t init[6];
         for (int k = 0; k < 3; ++k) { init[k] = float_to_ordered(FLT_MAX); init[3 + k] = float_to_ordered(-FLT_MAX); }
         be.upload(bounds, init, 6);
-        PrimSetupK k; k.a.vertices = d_vertices; k.a.tri_in = tri_in; k.a.prim_lo = prim_lo; k.a.prim_hi = prim_hi;
-        k.a.scene_bounds = bounds; k.a.n = n;
-        be.launch(n, k);
+        if (box_lo) {
+            be.copy(prim_lo, box_lo, (size_t)n); be.copy(prim_hi, box_hi, (size_t)n);
+            BoxBoundsK k; k.lo = box_lo; k.hi = box_hi; k.bounds = bounds; k.n = n;
+            be.launch(n, k);
+        } else {
+            PrimSetupK k; k.a.vertices = d_vertices; k.a.tri_in = tri_in; k.a.prim_lo = prim_lo; k.a.prim_hi = prim_hi;
+            k.a.scene_bounds = bounds; k.a.n = n;
+            be.launch(n, k);
+        }
     }
     // 2. Morton codes + sort
     uint64_t *keys = be.template alloc<uint64_t>(n);
@@ -274,8 +298,7 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
     }
     int32_t root_b2 = 0;
     be.download(&root_b2, ca, 1);
-    sc.stats.ploc_iterations = iters;
-    sc.stats.num_bvh2_nodes = n_b2;
+    out.ploc_iterations = iters;
     be.free(prim_lo); be.free(prim_hi); be.free(keys); be.free(sorted); be.free(cb); be.free(nn); be.free(ca);
     // 4. collapse plan: bottom-up over the binary tree, one launch per PLOC round (a round's nodes only have older children)
     float *plan_cost = nullptr; uint8_t *plan = nullptr;
@@ -304,8 +327,8 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
         be.upload(ctr + 3, &zero, 1);
         CollapseK k;
         k.a.nodes = b2; k.a.count = count; k.a.plan = plan; k.a.tri_in = tri_in; k.a.meta_in = meta_in;
-        k.a.nodes8 = nodes_tmp; k.a.tris_out = (Tri48 *)sc.tris; k.a.meta_out = sc.meta; k.a.prim_out = sc.prim;
-        k.a.leaf_of_prim = sc.leaf_of_prim; k.a.node_counter = ctr + 1; k.a.tri_counter = ctr + 2;
+        k.a.nodes8 = nodes_tmp; k.a.tris_out = tris_out; k.a.meta_out = meta_out; k.a.prim_out = prim_out;
+        k.a.leaf_of_prim = leaf_of_prim; k.a.node_counter = ctr + 1; k.a.tri_counter = ctr + 2;
         k.a.work_in = wa; k.a.n_in = n_in; k.a.work_out = wb; k.a.n_out = ctr + 3; k.a.sah = sah; k.a.max_leaf = max_leaf;
         be.launch(n_in, k);
         int32_t n_out = 0;
@@ -314,19 +337,14 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
         WorkItem *t = wa; wa = wb; wb = t;
         ++levels;
     }
-    if (levels >= kStackSize) throw Error(RTB_ERR_INVALID, "BVH too deep for the traversal stack");
     int32_t c4[4];
     be.download(c4, ctr, 4);
-    sc.num_nodes = c4[1];
+    out.num_nodes = c4[1];
+    out.levels = levels;
     if (c4[2] != n) throw Error(RTB_ERR_INVALID, "internal: collapse lost triangles");
-    sc.nodes8 = be.template alloc<Q4>((size_t)sc.num_nodes * kNodeWords);
-    be.copy(sc.nodes8, nodes_tmp, (size_t)sc.num_nodes * kNodeWords);
+    out.nodes8 = be.template alloc<Q4>((size_t)out.num_nodes * kNodeWords);
+    be.copy(out.nodes8, nodes_tmp, (size_t)out.num_nodes * kNodeWords);
     be.free(nodes_tmp); be.free(wa); be.free(wb); be.free(plan_cost); be.free(plan);
-    if (sc.num_lights > 0) {
-        LightFixK k; k.lights = sc.lights; k.light_tri = d_light_tri; k.leaf_of_prim = sc.leaf_of_prim; k.n = sc.num_lights;
-        be.launch(sc.num_lights, k);
-    }
-    // stats
     float sah_h = 0.f;
     be.download(&sah_h, sah, 1);
     int32_t bnd[6];
@@ -334,14 +352,60 @@ void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, T
     float lo[3], hi[3];
     for (int k = 0; k < 3; ++k) { lo[k] = ordered_to_float(bnd[k]); hi[k] = ordered_to_float(bnd[3 + k]); }
     const float root_area = half_area(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
-    sc.stats.sah_cost = root_area > 0.f ? sah_h / root_area : 0.f;
+    out.sah_cost = root_area > 0.f ? sah_h / root_area : 0.f;
+    for (int k = 0; k < 3; ++k) { out.bounds[2 * k] = lo[k]; out.bounds[2 * k + 1] = hi[k]; }
+    be.free(b2); be.free(count); be.free(ctr); be.free(sah); be.free(bounds);
+    return out;
+}
+
+// tri_in / meta_in / light_tri are device arrays in caller order; vertices may
+// be null when tri_in is already filled (reference-pointer ingest).
+template <class BE>
+void build_bvh(BE &be, SceneT<BE> &sc, const float *d_vertices, Tri48 *tri_in, TriMeta *meta_in,
+               const int64_t *d_light_tri, const rtb_build_params &bp) {
+    const int64_t n64 = sc.n;
+    if (n64 > 0x3fffffff) throw Error(RTB_ERR_INVALID, "too many triangles (max 2^30-1)");
+    const int n = (int)n64;
+    if (bp.builder != RTB_BUILDER_PLOC) throw Error(RTB_ERR_INVALID, "unknown BVH builder");
+    const int max_leaf = bp.max_leaf_tris >= 1 && bp.max_leaf_tris <= 3 ? bp.max_leaf_tris : 3;
+    auto t0 = be.now();
+    sc.stats = rtb_bvh_stats{};
+    sc.stats.num_triangles = n;
+    sc.n_flat = n;
+    sc.tris = (F4 *)be.template alloc<Tri48>(n > 0 ? n : 1);
+    sc.meta = be.template alloc<TriMeta>(n > 0 ? n : 1);
+    sc.prim = be.template alloc<int32_t>(n > 0 ? n : 1);
+    sc.leaf_of_prim = be.template alloc<int32_t>(n > 0 ? n : 1);
+    if (n == 0) {  // empty scene: one node with eight empty slots
+        std::vector<Q4> root(kNodeWords);
+        memset(root.data(), 0, sizeof(Q4) * kNodeWords);
+        root[2].x = root[2].y = root[2].z = root[2].w = 0xffffffffu;  // qlo = 255 > qhi = 0
+        root[3].x = root[3].y = 0xffffffffu;
+        root[0].w = 127u | (127u << 8) | (127u << 16);
+        sc.nodes8 = be.template alloc<Q4>(kNodeWords);
+        be.upload(sc.nodes8, root.data(), kNodeWords);
+        sc.num_nodes = 1;
+        sc.stats.num_nodes = 1;
+        sc.stats.node_bytes = 80;
+        return;
+    }
+    const BuiltTree bt = build_tree(be, n, d_vertices, tri_in, meta_in, nullptr, nullptr, bp, max_leaf, (Tri48 *)sc.tris, sc.meta, sc.prim,
+                                    sc.leaf_of_prim);
+    sc.nodes8 = bt.nodes8;
+    sc.num_nodes = bt.num_nodes;
+    if (bt.levels >= kStackSize) throw Error(RTB_ERR_INVALID, "BVH too deep for the traversal stack");
+    if (sc.num_lights > 0) {
+        LightFixK k; k.lights = sc.lights; k.light_tri = d_light_tri; k.leaf_of_prim = sc.leaf_of_prim; k.n = sc.num_lights;
+        be.launch(sc.num_lights, k);
+    }
+    sc.stats.ploc_iterations = bt.ploc_iterations;
+    sc.stats.num_bvh2_nodes = 2 * (int64_t)n - 1;
+    sc.stats.sah_cost = bt.sah_cost;
     sc.stats.num_nodes = sc.num_nodes;
     sc.stats.node_bytes = (int64_t)sc.num_nodes * 80;
     sc.stats.triangle_bytes = (int64_t)n * 48;
-    sc.stats.collapse_levels = levels;
-    sc.stats.scene_bounds[0] = lo[0]; sc.stats.scene_bounds[1] = hi[0]; sc.stats.scene_bounds[2] = lo[1];
-    sc.stats.scene_bounds[3] = hi[1]; sc.stats.scene_bounds[4] = lo[2]; sc.stats.scene_bounds[5] = hi[2];
-    be.free(b2); be.free(count); be.free(ctr); be.free(sah); be.free(bounds);
+    sc.stats.collapse_levels = bt.levels;
+    for (int k = 0; k < 6; ++k) sc.stats.scene_bounds[k] = bt.bounds[k];
     sc.stats.build_ms = be.elapsed_ms(t0, be.now());
 }
 
@@ -450,6 +514,221 @@ SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const 
         build_bvh(be, *sc, nullptr, tri_in, meta_in, d_light_tri, bp);
         be.free(d_prims); be.free(tri_in); be.free(meta_in); be.free(d_light_tri);
     } catch (...) {
+        delete sc;
+        throw;
+    }
+    return sc;
+}
+
+// ---- two-level scenes (rtb_scene_create_instanced) ----
+// One tree per mesh (object space), one over the instances' world boxes; all nodes in one array: the top tree first
+// (traversal starts at node 0), then the meshes' trees with their indices rebased.  Triangles, meta, prim and
+// leaf_of_prim keep mesh m in [mesh_first[m], mesh_first[m+1]) — leaf order permutes within a mesh only.
+inline bool invert3x4(const float *m, double *inv) {  // rows of [A | b] -> rows of [A^-1 | -A^-1 b]
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (!(fabs(det) > 0.0) || !std::isfinite(det)) return false;
+    const double r = 1.0 / det;
+    const double A[9] = {(e * i - f * h) * r, (c * h - b * i) * r, (b * f - c * e) * r, (f * g - d * i) * r, (a * i - c * g) * r,
+                         (c * d - a * f) * r, (d * h - e * g) * r, (b * g - a * h) * r, (a * e - b * d) * r};
+    for (int k = 0; k < 3; ++k) {
+        inv[4 * k] = A[3 * k]; inv[4 * k + 1] = A[3 * k + 1]; inv[4 * k + 2] = A[3 * k + 2];
+        inv[4 * k + 3] = -(A[3 * k] * m[3] + A[3 * k + 1] * m[7] + A[3 * k + 2] * m[11]);
+    }
+    return true;
+}
+inline bool is_identity3x4(const float *m) {
+    static const float id[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    for (int k = 0; k < 12; ++k) if (m[k] != id[k]) return false;
+    return true;
+}
+template <class BE>
+SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, const rtb_build_params &bp) {
+    const rtb_scene_desc &d = D.geometry;
+    if (d.num_triangles <= 0 || !d.vertices || !d.material_ids || d.num_materials <= 0 || !d.materials)
+        throw Error(RTB_ERR_INVALID, "rtb_scene_create_instanced: incomplete geometry");
+    if (d.num_lights > 0 && !d.lights) throw Error(RTB_ERR_INVALID, "rtb_scene_create_instanced: lights missing");
+    if (D.num_meshes <= 0 || !D.mesh_first || D.num_instances <= 0 || !D.instances)
+        throw Error(RTB_ERR_INVALID, "rtb_scene_create_instanced: meshes / instances missing");
+    if (d.num_triangles > 0x3fffffff) throw Error(RTB_ERR_INVALID, "too many triangles (max 2^30-1)");
+    const int n = (int)d.num_triangles, nm = D.num_meshes, ni = D.num_instances;
+    if (D.mesh_first[0] != 0 || D.mesh_first[nm] != n) throw Error(RTB_ERR_INVALID, "mesh_first must run from 0 to num_triangles");
+    for (int m = 0; m < nm; ++m)
+        if (D.mesh_first[m + 1] <= D.mesh_first[m]) throw Error(RTB_ERR_INVALID, "mesh_first must ascend strictly (no empty meshes)");
+    for (int i = 0; i < d.num_materials; ++i)
+        if (d.materials[i].type < 0 || d.materials[i].type >= kNumMaterialTypes) throw Error(RTB_ERR_INVALID, "unknown material type");
+    std::vector<int> uses((size_t)nm, 0), ident((size_t)nm, 1);
+    std::vector<long long> flat_first((size_t)ni + 1, 0);
+    for (int i = 0; i < ni; ++i) {
+        const rtb_instance &in = D.instances[i];
+        if (in.mesh < 0 || in.mesh >= nm) throw Error(RTB_ERR_INVALID, "instance: mesh out of range");
+        if (in.material < -1 || in.material >= d.num_materials) throw Error(RTB_ERR_INVALID, "instance: material out of range");
+        for (int k = 0; k < 12; ++k) if (!std::isfinite(in.xform[k])) throw Error(RTB_ERR_INVALID, "instance: transform not finite");
+        uses[(size_t)in.mesh]++;
+        if (!is_identity3x4(in.xform)) ident[(size_t)in.mesh] = 0;
+        flat_first[(size_t)i + 1] = flat_first[(size_t)i] + (D.mesh_first[in.mesh + 1] - D.mesh_first[in.mesh]);
+    }
+    if (flat_first[(size_t)ni] > 0x7fffffffll) throw Error(RTB_ERR_INVALID, "flattened scene beyond 2^31-1 triangles");
+    std::vector<int> mesh_of((size_t)n);
+    for (int m = 0; m < nm; ++m) for (long long t = D.mesh_first[m]; t < D.mesh_first[m + 1]; ++t) mesh_of[(size_t)t] = m;
+    std::vector<TriMeta> meta((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const int m = d.material_ids[i];
+        if (m < 0 || m >= d.num_materials) throw Error(RTB_ERR_INVALID, "material id out of range");
+        const int l = d.light_ids ? d.light_ids[i] : -1;
+        if (l >= d.num_lights) throw Error(RTB_ERR_INVALID, "light id out of range");
+        if (l >= 0 && !(uses[(size_t)mesh_of[(size_t)i]] == 1 && ident[(size_t)mesh_of[(size_t)i]]))
+            throw Error(RTB_ERR_INVALID, "an emissive triangle must belong to a mesh instanced exactly once with the identity transform");
+        meta[(size_t)i].material = m | (d.materials[m].type << 24);
+        meta[(size_t)i].light = l;
+    }
+    std::vector<LightDev> lights((size_t)d.num_lights);
+    std::vector<int64_t> light_tri((size_t)d.num_lights);
+    for (int i = 0; i < d.num_lights; ++i) {
+        const rtb_light &l = d.lights[i];
+        if (l.type == RTB_AREA_LIGHT) {
+            if (l.triangle < 0 || l.triangle >= n) throw Error(RTB_ERR_INVALID, "area light triangle out of range");
+            const int m = mesh_of[(size_t)l.triangle];
+            if (!(uses[(size_t)m] == 1 && ident[(size_t)m]))
+                throw Error(RTB_ERR_INVALID, "an area light's triangle must belong to a mesh instanced exactly once with the identity transform");
+        }
+        LightDev &o = lights[(size_t)i];
+        o.type = l.type; o.px = l.pos[0]; o.py = l.pos[1]; o.pz = l.pos[2]; o.tri = -1;
+        o.Lx = l.L[0]; o.Ly = l.L[1]; o.Lz = l.L[2];
+        light_tri[(size_t)i] = l.type == RTB_AREA_LIGHT ? l.triangle : 0;
+    }
+    if (bp.builder != RTB_BUILDER_PLOC) throw Error(RTB_ERR_INVALID, "unknown BVH builder");
+    const int max_leaf = bp.max_leaf_tris >= 1 && bp.max_leaf_tris <= 3 ? bp.max_leaf_tris : 3;
+    SceneT<BE> *sc = new SceneT<BE>();
+    std::vector<BuiltTree> trees((size_t)nm);
+    BuiltTree top;
+    try {
+        sc->be = &be;
+        sc->n = n;
+        sc->n_flat = flat_first[(size_t)ni];
+        sc->num_materials = d.num_materials;
+        sc->num_lights = d.num_lights;
+        auto t0 = be.now();
+        sc->materials = be.template alloc<rtb_material>(d.num_materials);
+        be.upload(sc->materials, d.materials, d.num_materials);
+        for (int i = 0; i < d.num_materials; ++i) sc->type_mask |= 1u << d.materials[i].type;
+        sc->lights = be.template alloc<LightDev>(d.num_lights > 0 ? d.num_lights : 1);
+        int64_t *d_light_tri = be.template alloc<int64_t>(d.num_lights > 0 ? d.num_lights : 1);
+        if (d.num_lights) { be.upload(sc->lights, lights.data(), d.num_lights); be.upload(d_light_tri, light_tri.data(), d.num_lights); }
+        float *d_vertices = be.template alloc<float>(9 * (size_t)n);
+        Tri48 *tri_in = be.template alloc<Tri48>(n);
+        TriMeta *meta_in = be.template alloc<TriMeta>(n);
+        be.upload(d_vertices, d.vertices, 9 * (size_t)n);
+        be.upload(meta_in, meta.data(), (size_t)n);
+        sc->tris = (F4 *)be.template alloc<Tri48>(n);
+        sc->meta = be.template alloc<TriMeta>(n);
+        sc->prim = be.template alloc<int32_t>(n);
+        sc->leaf_of_prim = be.template alloc<int32_t>(n);
+        // the meshes' trees, each with indices relative to itself
+        int mesh_nodes = 0, mesh_levels = 0;
+        for (int m = 0; m < nm; ++m) {
+            const int first = (int)D.mesh_first[m], cnt = (int)(D.mesh_first[m + 1] - D.mesh_first[m]);
+            trees[(size_t)m] = build_tree(be, cnt, d_vertices + 9 * (size_t)first, tri_in + first, meta_in + first, nullptr, nullptr, bp,
+                                          max_leaf, (Tri48 *)sc->tris + first, sc->meta + first, sc->prim + first, sc->leaf_of_prim + first);
+            if (first) {
+                AddK k; k.p = sc->prim + first; k.v = first; k.n = cnt; be.launch(cnt, k);
+                k.p = sc->leaf_of_prim + first; be.launch(cnt, k);
+            }
+            mesh_nodes += trees[(size_t)m].num_nodes;
+            if (trees[(size_t)m].levels > mesh_levels) mesh_levels = trees[(size_t)m].levels;
+        }
+        be.free(d_vertices); be.free(tri_in); be.free(meta_in);
+        // the instances' world boxes: the eight corners of the mesh's box through the transform, padded by more than
+        // the rounding of the ray transform can move a hit point (1e-5 of the coordinates' magnitude)
+        std::vector<F4> blo((size_t)ni), bhi((size_t)ni);
+        for (int i = 0; i < ni; ++i) {
+            const rtb_instance &in = D.instances[i];
+            const float *b = trees[(size_t)in.mesh].bounds;
+            double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+            for (int c = 0; c < 8; ++c) {
+                const double x = b[c & 1], y = b[2 + ((c >> 1) & 1)], z = b[4 + ((c >> 2) & 1)];
+                for (int k = 0; k < 3; ++k) {
+                    const double w = (double)in.xform[4 * k] * x + (double)in.xform[4 * k + 1] * y + (double)in.xform[4 * k + 2] * z + (double)in.xform[4 * k + 3];
+                    if (w < lo[k]) lo[k] = w;
+                    if (w > hi[k]) hi[k] = w;
+                }
+            }
+            double mag = 0.0;
+            for (int k = 0; k < 3; ++k) { mag = fmax(mag, fabs(lo[k])); mag = fmax(mag, fabs(hi[k])); }
+            const double pad = 1e-5 * mag + 1e-30;
+            F4 l, h;
+            l.x = (float)(lo[0] - pad); l.y = (float)(lo[1] - pad); l.z = (float)(lo[2] - pad); l.w = 0.f;
+            h.x = (float)(hi[0] + pad); h.y = (float)(hi[1] + pad); h.z = (float)(hi[2] + pad); h.w = 0.f;
+            if (!(fabsf(l.x) <= FLT_MAX && fabsf(l.y) <= FLT_MAX && fabsf(l.z) <= FLT_MAX && fabsf(h.x) <= FLT_MAX && fabsf(h.y) <= FLT_MAX && fabsf(h.z) <= FLT_MAX))
+                throw Error(RTB_ERR_INVALID, "instance: world box not finite");
+            blo[(size_t)i] = l; bhi[(size_t)i] = h;
+        }
+        F4 *d_blo = be.template alloc<F4>(ni), *d_bhi = be.template alloc<F4>(ni);
+        be.upload(d_blo, blo.data(), (size_t)ni); be.upload(d_bhi, bhi.data(), (size_t)ni);
+        sc->top_inst = be.template alloc<int32_t>(ni);
+        int32_t *top_leaf_of = be.template alloc<int32_t>(ni);
+        // every instance gets a child box of its own in the top tree (leaf lists of one entry)
+        top = build_tree(be, ni, nullptr, nullptr, nullptr, d_blo, d_bhi, bp, 1, nullptr, nullptr, sc->top_inst, top_leaf_of);
+        be.free(d_blo); be.free(d_bhi); be.free(top_leaf_of);
+        // stack: a node group per level of both trees, plus the rest of a leaf list per level of the top tree
+        if (2 * top.levels + mesh_levels >= kStackSize) throw Error(RTB_ERR_INVALID, "BVH too deep for the traversal stack");
+        // one node array: the top tree, then the meshes' trees rebased
+        sc->num_nodes = top.num_nodes + mesh_nodes;
+        sc->nodes8 = be.template alloc<Q4>((size_t)sc->num_nodes * kNodeWords);
+        be.copy(sc->nodes8, top.nodes8, (size_t)top.num_nodes * kNodeWords);
+        std::vector<int> root_of((size_t)nm);
+        int off = top.num_nodes;
+        for (int m = 0; m < nm; ++m) {
+            RebaseK k; k.src = trees[(size_t)m].nodes8; k.dst = sc->nodes8 + (size_t)off * kNodeWords;
+            k.node_off = (uint32_t)off; k.tri_off = (uint32_t)D.mesh_first[m]; k.n = trees[(size_t)m].num_nodes;
+            be.launch(k.n, k);
+            root_of[(size_t)m] = off;
+            off += trees[(size_t)m].num_nodes;
+        }
+        be.sync();
+        for (int m = 0; m < nm; ++m) { be.free(trees[(size_t)m].nodes8); trees[(size_t)m].nodes8 = nullptr; }
+        be.free(top.nodes8); top.nodes8 = nullptr;
+        // instance records
+        std::vector<F4> rec((size_t)ni * kInstWords);
+        for (int i = 0; i < ni; ++i) {
+            const rtb_instance &in = D.instances[i];
+            double inv[12];
+            if (!invert3x4(in.xform, inv)) throw Error(RTB_ERR_INVALID, "instance: transform not invertible");
+            F4 *r = rec.data() + (size_t)i * kInstWords;
+            for (int k = 0; k < 3; ++k) {
+                r[k].x = (float)inv[4 * k]; r[k].y = (float)inv[4 * k + 1]; r[k].z = (float)inv[4 * k + 2]; r[k].w = (float)inv[4 * k + 3];
+                r[3 + k].x = in.xform[4 * k]; r[3 + k].y = in.xform[4 * k + 1]; r[3 + k].z = in.xform[4 * k + 2]; r[3 + k].w = in.xform[4 * k + 3];
+            }
+            const int mat = in.material >= 0 ? (in.material | (d.materials[in.material].type << 24)) : -1;
+            r[6].x = i2f(root_of[(size_t)in.mesh]); r[6].y = i2f(mat); r[6].z = i2f((int)flat_first[(size_t)i]); r[6].w = i2f((int)D.mesh_first[in.mesh]);
+            r[7].x = r[7].y = r[7].z = r[7].w = 0.f;
+        }
+        sc->inst = be.template alloc<F4>((size_t)ni * kInstWords);
+        be.upload(sc->inst, rec.data(), rec.size());
+        sc->num_inst = ni;
+        if (sc->num_lights > 0) {
+            LightFixK k; k.lights = sc->lights; k.light_tri = d_light_tri; k.leaf_of_prim = sc->leaf_of_prim; k.n = sc->num_lights;
+            be.launch(sc->num_lights, k);
+        }
+        be.sync();
+        be.free(d_light_tri);
+        sc->stats = rtb_bvh_stats{};
+        sc->stats.num_triangles = n;
+        sc->stats.num_bvh2_nodes = 2 * (int64_t)n - nm + 2 * (int64_t)ni - 1;
+        sc->stats.num_nodes = sc->num_nodes;
+        sc->stats.node_bytes = (int64_t)sc->num_nodes * 80;
+        sc->stats.triangle_bytes = (int64_t)n * 48;
+        sc->stats.sah_cost = top.sah_cost;
+        sc->stats.ploc_iterations = top.ploc_iterations;
+        sc->stats.collapse_levels = top.levels + mesh_levels;
+        for (int k = 0; k < 6; ++k) sc->stats.scene_bounds[k] = top.bounds[k];
+        sc->stats.num_instances = ni;
+        sc->stats.num_flat_triangles = sc->n_flat;
+        sc->stats.num_top_nodes = top.num_nodes;
+        sc->stats.build_ms = be.elapsed_ms(t0, be.now());
+    } catch (...) {
+        for (auto &t : trees) be.free(t.nodes8);
+        be.free(top.nodes8);
         delete sc;
         throw;
     }

@@ -40,6 +40,15 @@ struct SceneView {
     int32_t num_materials;
 };
 
+// material word (index | type << 24) of a hit: the instance's material if it has one, else the triangle's own
+RTB_HD int hit_material(const SceneView &S, int tri, int inst) {
+    if (inst >= 0) {
+        const int m = inst_info(S.bvh.inst, inst).material;
+        if (m >= 0) return m;
+    }
+    return S.tri_meta[tri].material;
+}
+
 struct RenderConsts {
     rtb_camera cam;
     int32_t width, height;
@@ -237,6 +246,7 @@ struct PathStepIn {
     int32_t material;  // TriMeta::material of the hit triangle (index | type << 24)
     float prev_pdf;    // RTB_RENDER_TRUE_MIS: solid-angle pdf of the BSDF sample that produced this ray (0 = delta)
     float t;           // RTB_RENDER_TRUE_MIS: hit distance
+    int32_t inst;      // two-level scenes: instance of the hit triangle (-1 otherwise); read by the EXT kernels only
 };
 struct PathStepOut {
     bool emit; V3 emission;
@@ -253,7 +263,8 @@ RTB_HD void path_step(const SceneView &S, const RenderConsts &rc, const PathStep
     out.emit = false; out.extend = false; out.shadow = false;
     // issue every load that only depends on the hit before the roulette logic: the shade kernel is
     // bound by memory latency (ncu r1: long-scoreboard stalls dominate), not by instruction count
-    const Tri48 tr = load_tri(S.bvh.tris, in.hit.tri);
+    // (two-level scenes run the EXT kernels: the hit triangle is taken to world space, everything below is unchanged)
+    const Tri48 tr = EXT ? load_tri_world(S.bvh, in.hit.tri, in.inst) : load_tri(S.bvh.tris, in.hit.tri);
     rtb_material m = S.materials[in.material & 0xffffff];  // type is packed in the top byte
     if (MT >= 0) m.type = MT;
     int b = in.bounces;

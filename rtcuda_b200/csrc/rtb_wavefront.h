@@ -62,6 +62,8 @@ struct WaveState {
     float *mis;
     float env[3];
     int32_t has_env;
+    // two-level scenes: instance of every hit ([kNumMaterialTypes][pool], null for flat scenes)
+    int32_t *hit_inst;
 };
 
 constexpr int kMaxBounces = 255;       // bounces share a word with the sample index
@@ -148,12 +150,12 @@ RTB_HD void extend_miss(const WaveState &W, uint32_t pixel, V3 beta) {  // envir
     const V3 L = vmul(beta, v3(W.env[0], W.env[1], W.env[2]));
     if (finite3(L)) accum_add(W.accum, pixel, L);
 }
-RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const HitRec &h) {
+RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const HitRec &h, int hit_inst = -1) {
     if (h.tri < 0) {
         if (W.has_env) extend_miss(W, f2u(ldg(W.ea + qi).w), xyz(ldg(W.ec + qi)));
         return;
     }
-    const int mat = S.tri_meta[h.tri].material;
+    const int mat = hit_material(S, h.tri, hit_inst);
     const int type = mat >> 24;
     const int j = hit_queue_push(W, type);
     // the shade kernel needs u, v and the triangle, not t: the slot carries the material word
@@ -164,6 +166,7 @@ RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const 
     W.mb[j] = f4(xyz(beta), b.w);
     W.mc[j] = hr;
     if (W.mis) { W.mis[2 * (size_t)j] = beta.w; W.mis[2 * (size_t)j + 1] = h.t; }
+    if (W.hit_inst) W.hit_inst[j] = hit_inst;
 }
 template <bool COUNT>
 RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
@@ -172,9 +175,10 @@ RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
     const F4 b = ldg(W.eb + qi);
     HitRec h;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    bvh8_trace<false, COUNT>(S.bvh, xyz(a), xyz(b), FLT_MAX, -1, h, &tc);
+    int32_t hi = -1;
+    scene_trace<false, COUNT>(S.bvh, xyz(a), xyz(b), FLT_MAX, -1, -1, h, hi, &tc);
     if (COUNT) { work_add(&W.c->work[0], tc.nodes); work_add(&W.c->work[1], tc.tris); }
-    extend_finish(W, S, qi, h);
+    extend_finish(W, S, qi, h, hi);
 }
 
 // ------------------------------------------------------------ shade
@@ -195,6 +199,7 @@ RTB_HD void shade_item(const WaveState &W, const SceneView &S, const RenderConst
     in.pixel = f2u(a.w);
     in.prev_pdf = 0.f; in.t = 0.f;
     if (EXT && W.mis) { in.prev_pdf = W.mis[2 * (size_t)q]; in.t = W.mis[2 * (size_t)q + 1]; }
+    in.inst = (EXT && W.hit_inst) ? W.hit_inst[q] : -1;
     PathStepOut out;
     path_step<TYPE, EXT>(S, rc, in, out);
     if (out.emit) accum_add(W.accum, in.pixel, out.emission);
@@ -252,7 +257,8 @@ RTB_HD void shadow_body(const WaveState &W, const SceneView &S, int si) {
     const F4 d = ldg(W.sh_d + si);
     HitRec h;
     TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    const bool occluded = bvh8_trace<true, COUNT>(S.bvh, xyz(o), xyz(d), o.w, f2i(d.w), h, &tc);
+    int32_t hi = -1;  // (the excluded triangle is an emitter: its mesh is instanced once, the triangle index identifies it)
+    const bool occluded = scene_trace<true, COUNT>(S.bvh, xyz(o), xyz(d), o.w, f2i(d.w), -1, h, hi, &tc);
     if (COUNT) { work_add(&W.c->work[2], tc.nodes); work_add(&W.c->work[3], tc.tris); }
     shadow_finish(W, si, occluded);
 }
