@@ -668,7 +668,11 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
         sc->top_inst = be.template alloc<int32_t>(ni);
         int32_t *top_leaf_of = be.template alloc<int32_t>(ni);
         // every instance gets a child box of its own in the top tree (leaf lists of one entry)
-        top = build_tree(be, ni, nullptr, nullptr, nullptr, d_blo, d_bhi, bp, 1, nullptr, nullptr, sc->top_inst, top_leaf_of);
+        // (the SAH-optimal collapse: its tie-breaking caveat concerns triangles, and it halves the top tree — S2: 57 -> 27
+        // nodes, 3.55 -> 3.38 nodes per primary ray; leaf lists of 2 or 3 instances were measured worse)
+        rtb_build_params tbp = bp;
+        tbp.collapse = RTB_COLLAPSE_SAH_OPTIMAL;
+        top = build_tree(be, ni, nullptr, nullptr, nullptr, d_blo, d_bhi, tbp, 1, nullptr, nullptr, sc->top_inst, top_leaf_of);
         be.free(d_blo); be.free(d_bhi); be.free(top_leaf_of);
         // stack: a node group per level of both trees, plus the rest of a leaf list per level of the top tree
         if (2 * top.levels + mesh_levels >= kStackSize) throw Error(RTB_ERR_INVALID, "BVH too deep for the traversal stack");
