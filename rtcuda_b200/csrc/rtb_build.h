@@ -429,6 +429,41 @@ RTB_HD void box_bounds_body(const F4 *lo, const F4 *hi, int32_t *scene_bounds, i
     atomic_max_i(scene_bounds + 4, float_to_ordered(h.y));
     atomic_max_i(scene_bounds + 5, float_to_ordered(h.z));
 }
+// world box of every instance from its mesh's transformed VERTICES (the box of the transformed mesh box is up to 40 %
+// wider for a rotated mesh, and every box a ray crosses costs a visit of that mesh's root): one thread per
+// (instance, run of kInstBoundsRun triangles)
+constexpr int kInstBoundsRun = 64;
+struct InstBoundsArgs {
+    const Tri48 *tris;          // leaf order; mesh m = [first, first + count)
+    const float *xforms;        // 12 floats per instance, object -> world
+    const int32_t *first, *count;  // per instance: its mesh's range
+    int32_t *bounds;            // 6 ordered ints per instance: min xyz, max xyz
+    int32_t num_inst, runs;     // runs = ceil(largest mesh / kInstBoundsRun)
+};
+RTB_HD void inst_bounds_body(const InstBoundsArgs &a, int tid) {
+    const int i = tid / a.runs, c = tid % a.runs;
+    if (i >= a.num_inst) return;
+    const int cnt = a.count[i], t0 = c * kInstBoundsRun;
+    if (t0 >= cnt) return;
+    const int t1 = t0 + kInstBoundsRun < cnt ? t0 + kInstBoundsRun : cnt;
+    const float *m = a.xforms + 12 * (size_t)i;
+    F4 r0, r1, r2;
+    r0.x = m[0]; r0.y = m[1]; r0.z = m[2]; r0.w = m[3]; r1.x = m[4]; r1.y = m[5]; r1.z = m[6]; r1.w = m[7];
+    r2.x = m[8]; r2.y = m[9]; r2.z = m[10]; r2.w = m[11];
+    V3 lo = v3(FLT_MAX), hi = v3(-FLT_MAX);
+    for (int t = t0; t < t1; ++t) {
+        const Tri48 tr = a.tris[a.first[i] + t];
+        const V3 p0 = tri_p0(tr);
+        const V3 q[3] = {xform_point(r0, r1, r2, p0), xform_point(r0, r1, r2, vsub(p0, tri_e1(tr))), xform_point(r0, r1, r2, vadd(p0, tri_e2(tr)))};
+        for (int k = 0; k < 3; ++k) {
+            lo = v3(fminf(lo.x, q[k].x), fminf(lo.y, q[k].y), fminf(lo.z, q[k].z));
+            hi = v3(fmaxf(hi.x, q[k].x), fmaxf(hi.y, q[k].y), fmaxf(hi.z, q[k].z));
+        }
+    }
+    int32_t *b = a.bounds + 6 * (size_t)i;
+    atomic_min_i(b + 0, float_to_ordered(lo.x)); atomic_min_i(b + 1, float_to_ordered(lo.y)); atomic_min_i(b + 2, float_to_ordered(lo.z));
+    atomic_max_i(b + 3, float_to_ordered(hi.x)); atomic_max_i(b + 4, float_to_ordered(hi.y)); atomic_max_i(b + 5, float_to_ordered(hi.z));
+}
 // a mesh's tree is built with indices relative to itself; in the scene's arrays its nodes start at node_off and its
 // triangles at tri_off
 RTB_HD void rebase_node_body(const Q4 *src, Q4 *dst, uint32_t node_off, uint32_t tri_off, int n, int i) {

@@ -235,6 +235,7 @@ struct RebaseK {
     const Q4 *src; Q4 *dst; uint32_t node_off, tri_off; int n;
     RTB_HD void operator()(int i) const { rebase_node_body(src, dst, node_off, tri_off, n, i); }
 };
+struct InstBoundsK { InstBoundsArgs a; RTB_HD void operator()(int i) const { inst_bounds_body(a, i); } };
 struct AddK {
     int32_t *p; int32_t v; int n;
     RTB_HD void operator()(int i) const { if (i < n) p[i] += v; }
@@ -638,30 +639,47 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
             if (trees[(size_t)m].levels > mesh_levels) mesh_levels = trees[(size_t)m].levels;
         }
         be.free(d_vertices); be.free(tri_in); be.free(meta_in);
-        // the instances' world boxes: the eight corners of the mesh's box through the transform, padded by more than
-        // the rounding of the ray transform can move a hit point (1e-5 of the coordinates' magnitude)
+        // the instances' world boxes, from the transformed vertices of their meshes, padded by more than the rounding of
+        // the ray transform can move a hit point (1e-5 of the coordinates' magnitude)
         std::vector<F4> blo((size_t)ni), bhi((size_t)ni);
-        for (int i = 0; i < ni; ++i) {
-            const rtb_instance &in = D.instances[i];
-            const float *b = trees[(size_t)in.mesh].bounds;
-            double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-            for (int c = 0; c < 8; ++c) {
-                const double x = b[c & 1], y = b[2 + ((c >> 1) & 1)], z = b[4 + ((c >> 2) & 1)];
-                for (int k = 0; k < 3; ++k) {
-                    const double w = (double)in.xform[4 * k] * x + (double)in.xform[4 * k + 1] * y + (double)in.xform[4 * k + 2] * z + (double)in.xform[4 * k + 3];
-                    if (w < lo[k]) lo[k] = w;
-                    if (w > hi[k]) hi[k] = w;
-                }
+        {
+            std::vector<float> xf(12 * (size_t)ni);
+            std::vector<int32_t> ifirst((size_t)ni), icount((size_t)ni), binit(6 * (size_t)ni), bout(6 * (size_t)ni);
+            int largest = 1;
+            for (int i = 0; i < ni; ++i) {
+                const rtb_instance &in = D.instances[i];
+                memcpy(&xf[12 * (size_t)i], in.xform, sizeof(float) * 12);
+                ifirst[(size_t)i] = (int32_t)D.mesh_first[in.mesh];
+                icount[(size_t)i] = (int32_t)(D.mesh_first[in.mesh + 1] - D.mesh_first[in.mesh]);
+                if (icount[(size_t)i] > largest) largest = icount[(size_t)i];
+                for (int k = 0; k < 3; ++k) { binit[6 * (size_t)i + k] = float_to_ordered(FLT_MAX); binit[6 * (size_t)i + 3 + k] = float_to_ordered(-FLT_MAX); }
             }
-            double mag = 0.0;
-            for (int k = 0; k < 3; ++k) { mag = fmax(mag, fabs(lo[k])); mag = fmax(mag, fabs(hi[k])); }
-            const double pad = 1e-5 * mag + 1e-30;
-            F4 l, h;
-            l.x = (float)(lo[0] - pad); l.y = (float)(lo[1] - pad); l.z = (float)(lo[2] - pad); l.w = 0.f;
-            h.x = (float)(hi[0] + pad); h.y = (float)(hi[1] + pad); h.z = (float)(hi[2] + pad); h.w = 0.f;
-            if (!(fabsf(l.x) <= FLT_MAX && fabsf(l.y) <= FLT_MAX && fabsf(l.z) <= FLT_MAX && fabsf(h.x) <= FLT_MAX && fabsf(h.y) <= FLT_MAX && fabsf(h.z) <= FLT_MAX))
-                throw Error(RTB_ERR_INVALID, "instance: world box not finite");
-            blo[(size_t)i] = l; bhi[(size_t)i] = h;
+            InstBoundsK k;
+            k.a.runs = (largest + kInstBoundsRun - 1) / kInstBoundsRun;
+            if ((long long)k.a.runs * ni > 0x7fffffffll) throw Error(RTB_ERR_INVALID, "too many instances x triangles for the bounds pass");
+            float *d_xf = be.template alloc<float>(xf.size());
+            int32_t *d_first = be.template alloc<int32_t>(ni), *d_count = be.template alloc<int32_t>(ni), *d_b = be.template alloc<int32_t>(6 * (size_t)ni);
+            be.upload(d_xf, xf.data(), xf.size()); be.upload(d_first, ifirst.data(), (size_t)ni); be.upload(d_count, icount.data(), (size_t)ni);
+            be.upload(d_b, binit.data(), binit.size());
+            k.a.tris = (const Tri48 *)sc->tris; k.a.xforms = d_xf; k.a.first = d_first; k.a.count = d_count; k.a.bounds = d_b; k.a.num_inst = ni;
+            be.launch(k.a.runs * ni, k);
+            be.download(bout.data(), d_b, bout.size());
+            be.free(d_xf); be.free(d_first); be.free(d_count); be.free(d_b);
+            for (int i = 0; i < ni; ++i) {
+                float lo[3], hi[3];
+                double mag = 0.0;
+                for (int k2 = 0; k2 < 3; ++k2) {
+                    lo[k2] = ordered_to_float(bout[6 * (size_t)i + k2]); hi[k2] = ordered_to_float(bout[6 * (size_t)i + 3 + k2]);
+                    mag = fmax(mag, fmax(fabs((double)lo[k2]), fabs((double)hi[k2])));
+                }
+                const double pad = 1e-5 * mag + 1e-30;
+                F4 l, h;
+                l.x = (float)(lo[0] - pad); l.y = (float)(lo[1] - pad); l.z = (float)(lo[2] - pad); l.w = 0.f;
+                h.x = (float)(hi[0] + pad); h.y = (float)(hi[1] + pad); h.z = (float)(hi[2] + pad); h.w = 0.f;
+                if (!(fabsf(l.x) <= FLT_MAX && fabsf(l.y) <= FLT_MAX && fabsf(l.z) <= FLT_MAX && fabsf(h.x) <= FLT_MAX && fabsf(h.y) <= FLT_MAX && fabsf(h.z) <= FLT_MAX))
+                    throw Error(RTB_ERR_INVALID, "instance: world box not finite");
+                blo[(size_t)i] = l; bhi[(size_t)i] = h;
+            }
         }
         F4 *d_blo = be.template alloc<F4>(ni), *d_bhi = be.template alloc<F4>(ni);
         be.upload(d_blo, blo.data(), (size_t)ni); be.upload(d_bhi, bhi.data(), (size_t)ni);

@@ -30,13 +30,21 @@ def test_shard_samples_partition():
             assert max(counts) - min(counts) <= 1
 
 
-def _worker(rank, world, port, lib_path, out_path):
+def _scene(L, instanced):
+    """the default scene, flat or as two instances (bunny placed by its transform + static shell: two-level BVH)"""
+    if instanced:
+        hs = L.host_scene_instanced(capi.RTB_SCENE_S1, *L.load_mesh())
+        return hs, L.context(0).scene(hs.idesc)
+    hs = L.host_scene(capi.RTB_SCENE_S1, *L.load_mesh())
+    return hs, L.context(0).scene(hs.desc)
+
+
+def _worker(rank, world, port, lib_path, out_path, instanced):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     L = capi.Lib(lib_path)
-    hs = L.host_scene(capi.RTB_SCENE_S1, *L.load_mesh())
-    sc = L.context(0).scene(hs.desc)
+    hs, sc = _scene(L, instanced)
     cam = hs.camera(W / H)
     p = capi.render_params(L, width=W, height=H, spp=SPP, max_bounces=DEPTH)
     accum = torch.zeros(3 * W * H, dtype=torch.float32)
@@ -52,16 +60,15 @@ def _worker(rank, world, port, lib_path, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_two_rank_gloo_render_equals_single_rank(tmp_path, world):
+@pytest.mark.parametrize("world,instanced", [(2, False), (3, False), (2, True)])
+def test_two_rank_gloo_render_equals_single_rank(tmp_path, world, instanced):
     lib_path = build_emu()
     out_path = str(tmp_path / "img.npz")
-    port = 29500 + (os.getpid() % 2000) + world
-    mp.spawn(_worker, args=(world, port, lib_path, out_path), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + world + (10 if instanced else 0)
+    mp.spawn(_worker, args=(world, port, lib_path, out_path, instanced), nprocs=world, join=True)
     got = np.load(out_path)
     L = capi.Lib(lib_path)
-    hs = L.host_scene(capi.RTB_SCENE_S1, *L.load_mesh())
-    sc = L.context(0).scene(hs.desc)
+    hs, sc = _scene(L, instanced)
     ref, st = sc.render(hs.camera(W / H), capi.render_params(L, width=W, height=H, spp=SPP, max_bounces=DEPTH))
     assert got["rays"][0] == st.extend_rays + st.shadow_rays
     assert mean_rel_err(got["img"], ref) <= 1e-5

@@ -13,7 +13,8 @@ sys.path.insert(0, ROOT)
 from rtcuda_b200 import capi  # noqa: E402
 
 W = {"c1": (1, 0, 600, 600, 10, 10), "c2": (1, 0, 1920, 1080, 64, 8), "c2s": (1, 0, 1920, 1080, 4, 8), "c2m": (1, 0, 1920, 1080, 16, 8),
-     "c3s": (3, 12, 3840, 2160, 1, 8), "c4s": (2, 0, 1920, 1080, 4, 16)}
+     "c3s": (3, 12, 3840, 2160, 1, 8), "c4s": (2, 0, 1920, 1080, 4, 16),
+     "c3is": (3, 12, 3840, 2160, 1, 8)}  # c3s given as instances (two-level BVH)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c1")
@@ -24,8 +25,12 @@ a = ap.parse_args()
 kind, grid, w, h, spp, depth = W[a.workload]
 L = capi.Lib()
 ctx = L.context(0)
-hs = L.host_scene(kind, *L.load_mesh(), grid=grid)
-sc = ctx.scene(hs.desc)
+if a.workload == "c3is":
+    hs = L.host_scene_instanced(kind, *L.load_mesh(), grid=grid)
+    sc = ctx.scene(hs.idesc)
+else:
+    hs = L.host_scene(kind, *L.load_mesh(), grid=grid)
+    sc = ctx.scene(hs.desc)
 bs = sc.stats()
 print(f"scene: {bs.num_triangles} tris, {bs.num_nodes} nodes, build {bs.build_ms:.2f} ms, sah {bs.sah_cost:.2f}, "
       f"ploc iters {bs.ploc_iterations}, levels {bs.collapse_levels}")
