@@ -244,6 +244,15 @@ RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 
 }
 
 constexpr int kStackSize = 48;
+// The traversal stack: two dynamically indexed arrays in LOCAL memory.  Its top entries live in L1 (write-back), a
+// push or pop is one STL / LDL pair per node group that leaves siblings behind; the scalar state of the traversal
+// stays in registers because the arrays are outside the Traversal struct.  (rtb_cuda.cu has a variant that keeps the
+// first entries in shared memory, HybridStack: measured, not the default — profiles/README.md.)
+struct LocalStack {
+    uint32_t x[kStackSize], y[kStackSize];
+    RTB_HD void put(int i, uint32_t a, uint32_t b) { x[i] = a; y[i] = b; }
+    RTB_HD void get(int i, uint32_t &a, uint32_t &b) const { a = x[i]; b = y[i]; }
+};
 
 // One ray through the tree, as a resumable state machine so that the
 // persistent kernels can swap finished rays for new ones while the rest of
@@ -291,13 +300,14 @@ struct Traversal {
     // is the plain per-ray composition.
     // (1) pop the nearest pending child, fetch its node, slab-test the 8 child boxes;
     //     (tx, ty) = triangle base | hit triangle bits of that node
-    RTB_HD void node_part(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y, uint32_t &tx, uint32_t &ty) {
+    template <class ST>
+    RTB_HD void node_part(const Bvh8View &B, ST &st, uint32_t &tx, uint32_t &ty) {
         tx = 0; ty = 0;
         if (gy & 0xff000000u) {
             const int bit = bfind(gy);
             gy &= ~(1u << bit);
             const uint32_t base = gx, imask = gy & 0xffu;
-            if (gy & 0xff000000u) { stack_x[sp] = gx; stack_y[sp] = gy; ++sp; }
+            if (gy & 0xff000000u) { st.put(sp, gx, gy); ++sp; }
             const uint32_t slot = ((uint32_t)bit - 24u) ^ r.octinv;
             const uint32_t rel = popc(imask & ~(0xffffffffu << slot));
             const Q4 *np = B.nodes + (size_t)(base + rel) * kNodeWords;
@@ -329,21 +339,23 @@ struct Traversal {
         return false;
     }
     // (3) next pending node group; false when the ray is finished
-    RTB_HD bool advance(const uint32_t *stack_x, const uint32_t *stack_y) {
+    template <class ST>
+    RTB_HD bool advance(const ST &st) {
         if ((gy & 0xff000000u) == 0) {
             if (sp == 0) return false;
-            --sp; gx = stack_x[sp]; gy = stack_y[sp];
+            --sp; st.get(sp, gx, gy);
         }
         return true;
     }
     // ---- INST ----
     // (tx, ty) is a leaf list of the top tree: enter the instance of its highest entry.  The node group still pending
     // and the rest of the list go on the stack first, so they are resumed when the instance has been left.
-    RTB_HD void enter_instance(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y, uint32_t tx, uint32_t &ty, V3 o, V3 d) {
+    template <class ST>
+    RTB_HD void enter_instance(const Bvh8View &B, ST &st, uint32_t tx, uint32_t &ty, V3 o, V3 d) {
         const int bit = bfind(ty);
         ty &= ~(1u << bit);
-        if (gy & 0xff000000u) { stack_x[sp] = gx; stack_y[sp] = gy; ++sp; }
-        if (ty) { stack_x[sp] = tx; stack_y[sp] = ty; ++sp; ty = 0u; }
+        if (gy & 0xff000000u) { st.put(sp, gx, gy); ++sp; }
+        if (ty) { st.put(sp, tx, ty); ++sp; ty = 0u; }
         cur = B.top_inst[tx + (uint32_t)bit];
         sp_enter = sp;
         const F4 *m = B.inst + (size_t)cur * kInstWords;
@@ -353,21 +365,24 @@ struct Traversal {
         gx = (uint32_t)root; gy = 0x80000000u;
     }
     // next pending node group or leaf list; (o, d) = the world ray, set up again when an instance is left
-    RTB_HD bool advance_inst(const uint32_t *stack_x, const uint32_t *stack_y, uint32_t &tx, uint32_t &ty, V3 o, V3 d) {
+    template <class ST>
+    RTB_HD bool advance_inst(const ST &st, uint32_t &tx, uint32_t &ty, V3 o, V3 d) {
         if ((gy & 0xff000000u) == 0) {
             if (cur >= 0 && sp == sp_enter) { cur = -1; r = ray_setup(o, d); }
             if (sp == 0) return false;
             --sp;
-            const uint32_t x = stack_x[sp], y = stack_y[sp];
+            uint32_t x, y;
+            st.get(sp, x, y);
             if (y & 0xff000000u) { gx = x; gy = y; }
             else { tx = x; ty = y; gx = 0u; gy = 0u; }  // the rest of a leaf list of the top tree
         }
         return true;
     }
-    RTB_HD bool step_inst(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y, uint32_t &tx, uint32_t &ty, V3 o, V3 d) {
-        if (ty == 0u) node_part(B, stack_x, stack_y, tx, ty);
+    template <class ST>
+    RTB_HD bool step_inst(const Bvh8View &B, ST &st, uint32_t &tx, uint32_t &ty, V3 o, V3 d) {
+        if (ty == 0u) node_part(B, st, tx, ty);
         if (cur < 0) {
-            if (ty) enter_instance(B, stack_x, stack_y, tx, ty, o, d);
+            if (ty) enter_instance(B, st, tx, ty, o, d);
         } else {
             while (ty) {
                 const int bit = bfind(ty);
@@ -380,12 +395,13 @@ struct Traversal {
                 if (accept(B, idx, t, u, v)) return false;
             }
         }
-        return advance_inst(stack_x, stack_y, tx, ty, o, d);
+        return advance_inst(st, tx, ty, o, d);
     }
     // one node (its 8 child boxes) plus the triangles it exposes; false when the ray is finished
-    RTB_HD bool step(const Bvh8View &B, uint32_t *stack_x, uint32_t *stack_y) {
+    template <class ST>
+    RTB_HD bool step(const Bvh8View &B, ST &st) {
         uint32_t tx, ty;  // triangle group: tri base | hit bits
-        node_part(B, stack_x, stack_y, tx, ty);
+        node_part(B, st, tx, ty);
         while (ty) {
             const int bit = bfind(ty);
             ty &= ~(1u << bit);
@@ -396,7 +412,7 @@ struct Traversal {
             const float t = tri_candidate(tr, r.o, r.d, u, v);
             if (accept(B, idx, t, u, v)) return false;
         }
-        return advance(stack_x, stack_y);
+        return advance(st);
     }
 };
 
@@ -404,9 +420,9 @@ template <bool ANY, bool COUNT>
 RTB_HD bool bvh8_trace(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, HitRec &hit,
                        TraceCounters *cnt) {
     Traversal<ANY, COUNT> T;
-    uint32_t stack_x[kStackSize], stack_y[kStackSize];
+    LocalStack st;
     T.init(o, d, tmax, excluded);
-    while (T.step(B, stack_x, stack_y)) {}
+    while (T.step(B, st)) {}
     hit = T.hit;
     if (COUNT) { cnt->nodes = T.cnt.nodes; cnt->tris = T.cnt.tris; }
     return T.found;
@@ -417,11 +433,11 @@ template <bool ANY, bool COUNT>
 RTB_HD bool bvh8_trace_inst(const Bvh8View &B, V3 o, V3 d, float tmax, int32_t excluded, int32_t excluded_inst, HitRec &hit,
                             int32_t &hit_inst, TraceCounters *cnt) {
     Traversal<ANY, COUNT, true> T;
-    uint32_t stack_x[kStackSize], stack_y[kStackSize];
+    LocalStack st;
     T.init(o, d, tmax, excluded);
     T.excluded_inst = excluded_inst;
     uint32_t tx = 0u, ty = 0u;
-    while (T.step_inst(B, stack_x, stack_y, tx, ty, o, d)) {}
+    while (T.step_inst(B, st, tx, ty, o, d)) {}
     hit = T.hit; hit_inst = T.hit_inst;
     if (COUNT) { cnt->nodes = T.cnt.nodes; cnt->tris = T.cnt.tris; }
     return T.found;

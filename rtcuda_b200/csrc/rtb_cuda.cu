@@ -185,16 +185,37 @@ __device__ __forceinline__ void own_triangles(const Bvh8View &B, Traversal<ANY, 
     }
 }
 
+// Stack variants of the persistent kernel.  Default: LocalStack (rtb_bvh8.h).  HybridStack<N> keeps the first N
+// entries of every thread in shared memory ([N][kBlock] uint2: the bank is the thread, so lanes at different depths
+// never conflict) and the rest in local memory; RTB_SMEM_STACK=N selects it (N = 8) for an A/B.  The shared memory it
+// takes (N x 2 KB per block, four blocks per SM) comes out of the L1 that caches the nodes.
+struct LocalStackK : LocalStack {
+    __device__ explicit LocalStackK(uint2 *) {}
+};
+template <int N>
+struct HybridStack {
+    uint2 *s;
+    uint32_t x[kStackSize - N], y[kStackSize - N];
+    __device__ explicit HybridStack(uint2 *column) : s(column) {}
+    __device__ __forceinline__ void put(int i, uint32_t a, uint32_t b) {
+        if (i < N) s[i * kBlock] = make_uint2(a, b);
+        else { x[i - N] = a; y[i - N] = b; }
+    }
+    __device__ __forceinline__ void get(int i, uint32_t &a, uint32_t &b) const {
+        if (i < N) { const uint2 v = s[i * kBlock]; a = v.x; b = v.y; }
+        else { a = x[i - N]; b = y[i - N]; }
+    }
+};
 // INST: two-level scenes (rtb_bvh8.h, Traversal<.., INST>): stepped schedule only; the world ray a lane needs when it
 // enters or leaves an instance is the one in its shared-memory slot (ws.ro / ws.rd).
-template <bool ANY, bool POOL, bool INST = false>
-__device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveState &W, const SceneView &S, FetchTuning tune) {
+template <bool ANY, bool POOL, bool INST = false, class STACK = LocalStackK>
+__device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveState &W, const SceneView &S, FetchTuning tune, uint2 *ws_stack = nullptr) {
     const int n = ANY ? W.c->n_shadow : W.c->n_extend;
     int32_t *head = ANY ? &W.c->shadow_head : &W.c->extend_head;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanes_below = (1u << lane) - 1u;
     Traversal<ANY, false, INST> T;
-    uint32_t stack_x[kStackSize], stack_y[kStackSize];
+    STACK st(ws_stack);
     bool has = false, exhausted = false, pending = false;
     int qi = 0;
     int chunk_next = 0, chunk_end = 0;  // warp-uniform: the part of the queue this warp has claimed
@@ -279,11 +300,11 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
         const int keep_going = exhausted ? 1 : tune.refill;
         do {
             if constexpr (INST) {
-                if (has && ty == 0u) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+                if (has && ty == 0u) T.node_part(S.bvh, st, tx, ty);
                 if (has && T.cur < 0) {  // (tx, ty) is a leaf list of the top tree: enter its nearest instance
                     if (ty != 0u) {
                         const float4 o = ws.ro[lane], d = ws.rd[lane];
-                        T.enter_instance(S.bvh, stack_x, stack_y, tx, ty, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
+                        T.enter_instance(S.bvh, st, tx, ty, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
                     }
                 } else {
 #pragma unroll 1
@@ -299,20 +320,20 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                 }
                 if (has && ty == 0u) {
                     const float4 o = ws.ro[lane], d = ws.rd[lane];
-                    if (!T.advance_inst(stack_x, stack_y, tx, ty, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z))) { has = false; pending = true; }
+                    if (!T.advance_inst(st, tx, ty, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z))) { has = false; pending = true; }
                 }
             } else if constexpr (POOL) {
                 tx = 0u; ty = 0u;
-                if (has) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+                if (has) T.node_part(S.bvh, st, tx, ty);
                 pooled_triangles<ANY>(ws, S.bvh, T, tx, ty, has, pending, lane, lanes_below);
                 ty = 0u;
-                if (has && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
+                if (has && !T.advance(st)) { has = false; pending = true; }
             } else if (tune.tri_step > 0) {
                 // stepped: at most tri_step triangle tests per lane and step; a lane with more keeps them for
                 // the next steps and sits out the node phase meanwhile (its own order of events is unchanged:
                 // the next node is fetched only once all triangles of the current one are tested), so one
                 // lane's long triangle list no longer idles the rest of the warp
-                if (has && ty == 0u) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+                if (has && ty == 0u) T.node_part(S.bvh, st, tx, ty);
 #pragma unroll 1
                 for (int k = 0; k < tune.tri_step && ty != 0u; ++k) {
                     const int bit = 31 - __clz(ty);
@@ -323,13 +344,13 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                     const float t = tri_candidate(tr, T.r.o, T.r.d, u, v);
                     if (T.accept(S.bvh, idx, t, u, v)) { has = false; pending = true; ty = 0u; }
                 }
-                if (has && ty == 0u && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
+                if (has && ty == 0u && !T.advance(st)) { has = false; pending = true; }
             } else {
                 tx = 0u; ty = 0u;
-                if (has) T.node_part(S.bvh, stack_x, stack_y, tx, ty);
+                if (has) T.node_part(S.bvh, st, tx, ty);
                 own_triangles<ANY>(S.bvh, T, tx, ty, has, pending);
                 ty = 0u;
-                if (has && !T.advance(stack_x, stack_y)) { has = false; pending = true; }
+                if (has && !T.advance(st)) { has = false; pending = true; }
             }
             act = __ballot_sync(0xffffffffu, has);
         } while (__popc(act) >= keep_going);
@@ -350,8 +371,19 @@ __global__ void __launch_bounds__(kBlock, 4) k_trace(WaveState W, SceneView S, F
     if (WHICH == 3) __syncwarp();
     if (WHICH & 2) persistent_trace<true, POOL, INST>(ws, W, S, tune);
 }
+constexpr int kSmemStack = 8;
+__global__ void __launch_bounds__(kBlock, 4) k_trace_smem_stack(WaveState W, SceneView S, FetchTuning tune) {  // k_trace<3, false> with HybridStack
+    __shared__ WarpScratch scratch[kBlock / 32];
+    __shared__ uint2 sstack[kSmemStack][kBlock];
+    WarpScratch &ws = scratch[threadIdx.x >> 5];
+    persistent_trace<false, false, false, HybridStack<kSmemStack>>(ws, W, S, tune, &sstack[0][threadIdx.x]);
+    __syncwarp();
+    persistent_trace<true, false, false, HybridStack<kSmemStack>>(ws, W, S, tune, &sstack[0][threadIdx.x]);
+}
+static int g_smem_stack = 0;  // RTB_SMEM_STACK (A/B)
 template <int WHICH>
 static void launch_trace_kernel(int grid, cudaStream_t st, bool pooled, const WaveState &W, const SceneView &S, const FetchTuning &tune) {
+    if (WHICH == 3 && g_smem_stack && !S.bvh.inst && !pooled) { k_trace_smem_stack<<<grid, kBlock, 0, st>>>(W, S, tune); return; }
     if (S.bvh.inst) {  // two-level scene: stepped schedule
         FetchTuning t = tune;
         if (t.tri_step < 1) t.tri_step = 2;
@@ -426,6 +458,7 @@ struct CudaBackend {
         if (const char *e = getenv("RTB_TRI_STEP")) tune_.tri_step = atoi(e);
         if (const char *e = getenv("RTB_POOLED")) pooled_ = atoi(e);
         if (const char *e = getenv("RTB_FUSED")) fused_ = atoi(e);
+        if (const char *e = getenv("RTB_SMEM_STACK")) g_smem_stack = atoi(e);
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
         int per_sm = 0;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<3, true>, kBlock, 0));
