@@ -306,17 +306,19 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                         const float4 o = ws.ro[lane], d = ws.rd[lane];
                         T.enter_instance(S.bvh, st, tx, ty, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z));
                     }
-                } else {
-#pragma unroll 1
-                    for (int k = 0; k < tune.tri_step && ty != 0u; ++k) {
-                        const int bit = 31 - __clz(ty);
-                        ty &= ~(1u << bit);
-                        const int idx = (int)(tx + (uint32_t)bit);
-                        const Tri48 tr = load_tri(S.bvh.tris, idx);
-                        float u, v;
-                        const float t = tri_candidate(tr, T.r.o, T.r.d, u, v);
-                        if (T.accept(S.bvh, idx, t, u, v)) { has = false; pending = true; ty = 0u; }
-                    }
+                } else if (ty != 0u) {  // two triangles of the list together, as in the flat kernel below
+                    const int bit1 = 31 - __clz(ty);
+                    ty &= ~(1u << bit1);
+                    const bool two = ty != 0u;
+                    const int bit2 = two ? 31 - __clz(ty) : bit1;
+                    ty &= ~(1u << bit2);
+                    const int idx1 = (int)(tx + (uint32_t)bit1), idx2 = (int)(tx + (uint32_t)bit2);
+                    const Tri48 tr1 = load_tri(S.bvh.tris, idx1), tr2 = load_tri(S.bvh.tris, idx2);
+                    float u1, v1, u2, v2;
+                    const float t1 = tri_candidate(tr1, T.r.o, T.r.d, u1, v1);
+                    const float t2 = tri_candidate(tr2, T.r.o, T.r.d, u2, v2);
+                    if (T.accept(S.bvh, idx1, t1, u1, v1)) { has = false; pending = true; ty = 0u; }
+                    else if (two && T.accept(S.bvh, idx2, t2, u2, v2)) { has = false; pending = true; ty = 0u; }
                 }
                 if (has && ty == 0u) {
                     const float4 o = ws.ro[lane], d = ws.rd[lane];
@@ -334,6 +336,25 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                 // the next node is fetched only once all triangles of the current one are tested), so one
                 // lane's long triangle list no longer idles the rest of the warp
                 if (has && ty == 0u) T.node_part(S.bvh, st, tx, ty);
+                // tri_step 2 (default): both triangles are fetched and tested together — the loads of the second overlap the
+                // arithmetic of the first (C3 105.0 -> 100.0 ms, C2 / C4 unchanged: profiles/README.md, session 64) — and the
+                // accept rule then runs on them in list order, so the ray's own order of events is what it was
+                if (tune.tri_step == 2) {
+                  if (ty != 0u) {
+                    const int bit1 = 31 - __clz(ty);
+                    ty &= ~(1u << bit1);
+                    const bool two = ty != 0u;
+                    const int bit2 = two ? 31 - __clz(ty) : bit1;
+                    ty &= ~(1u << bit2);
+                    const int idx1 = (int)(tx + (uint32_t)bit1), idx2 = (int)(tx + (uint32_t)bit2);
+                    const Tri48 tr1 = load_tri(S.bvh.tris, idx1), tr2 = load_tri(S.bvh.tris, idx2);
+                    float u1, v1, u2, v2;
+                    const float t1 = tri_candidate(tr1, T.r.o, T.r.d, u1, v1);
+                    const float t2 = tri_candidate(tr2, T.r.o, T.r.d, u2, v2);
+                    if (T.accept(S.bvh, idx1, t1, u1, v1)) { has = false; pending = true; ty = 0u; }
+                    else if (two && T.accept(S.bvh, idx2, t2, u2, v2)) { has = false; pending = true; ty = 0u; }
+                  }
+                } else {
 #pragma unroll 1
                 for (int k = 0; k < tune.tri_step && ty != 0u; ++k) {
                     const int bit = 31 - __clz(ty);
@@ -343,6 +364,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                     float u, v;
                     const float t = tri_candidate(tr, T.r.o, T.r.d, u, v);
                     if (T.accept(S.bvh, idx, t, u, v)) { has = false; pending = true; ty = 0u; }
+                }
                 }
                 if (has && ty == 0u && !T.advance(st)) { has = false; pending = true; }
             } else {
@@ -384,10 +406,8 @@ static int g_smem_stack = 0;  // RTB_SMEM_STACK (A/B)
 template <int WHICH>
 static void launch_trace_kernel(int grid, cudaStream_t st, bool pooled, const WaveState &W, const SceneView &S, const FetchTuning &tune) {
     if (WHICH == 3 && g_smem_stack && !S.bvh.inst && !pooled) { k_trace_smem_stack<<<grid, kBlock, 0, st>>>(W, S, tune); return; }
-    if (S.bvh.inst) {  // two-level scene: stepped schedule
-        FetchTuning t = tune;
-        if (t.tri_step < 1) t.tri_step = 2;
-        k_trace<WHICH, false, true><<<grid, kBlock, 0, st>>>(W, S, t);
+    if (S.bvh.inst) {  // two-level scene: stepped schedule, two triangles per step
+        k_trace<WHICH, false, true><<<grid, kBlock, 0, st>>>(W, S, tune);
     } else if (pooled) k_trace<WHICH, true><<<grid, kBlock, 0, st>>>(W, S, tune);
     else k_trace<WHICH, false><<<grid, kBlock, 0, st>>>(W, S, tune);
 }
