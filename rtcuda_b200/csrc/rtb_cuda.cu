@@ -24,6 +24,7 @@
 
 #include <cstdlib>
 
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 
@@ -423,6 +424,41 @@ __global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S
     if (i < W.c->n_shadow) shadow_body<COUNT>(W, S, i);
 }
 
+// All remaining PLOC rounds in ONE launch once the clusters fit a thread block: cluster list, nearest neighbours and
+// merge results live in shared memory, the same round bodies (rtb_build.h) run between block barriers, the
+// order-preserving compaction is a block scan.  out[0] = rounds run, out[1] = root node, out[2 + r] = nodes made by round r.
+constexpr int kPlocTail = 1024;
+__global__ void __launch_bounds__(kPlocTail) k_ploc_tail(PlocArgs a, int n_leaves, int32_t *out) {
+    __shared__ int32_t cin[kPlocTail], cout[kPlocTail], nn[kPlocTail];
+    typedef cub::BlockScan<int, kPlocTail> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    const int t = threadIdx.x;
+    int n = a.ncl;
+    if (t < n) cin[t] = a.cin[t];
+    __syncthreads();
+    PlocArgs b = a;
+    b.cin = cin; b.cout = cout; b.nn = nn;
+    int rounds = 0;
+    while (n > 1) {
+        b.ncl = n;
+        ploc_nn_body(b, t);
+        __syncthreads();
+        ploc_merge_body(b, n_leaves, t);  // (new nodes go to global memory: visible to the block after the barrier)
+        __syncthreads();
+        const int v = t < n ? cout[t] : -1;
+        const int flag = v >= 0 ? 1 : 0;
+        int pos, total;
+        Scan(scan_tmp).ExclusiveSum(flag, pos, total);
+        __syncthreads();
+        if (flag) cin[pos] = v;
+        if (t == 0) out[2 + rounds] = n - total;
+        n = total;
+        ++rounds;
+        __syncthreads();
+    }
+    if (t == 0) { out[0] = rounds; out[1] = cin[0]; }
+}
+
 struct NonNegative {
     __host__ __device__ bool operator()(const int32_t &v) const { return v >= 0; }
 };
@@ -443,6 +479,7 @@ struct CudaBackend {
     int pooled_ = 0;  // RTB_POOLED: pooled triangle tests (1), each ray's lane on its own (0, default), by scene size (-1)
     int fused_ = 1;   // RTB_FUSED: extend + shadow rays of one iteration in one launch
     int pool_ = 1 << 25;    // default path pool, RTB_POOL overrides (tuning)
+    int ploc_tail_off_ = 0; // RTB_PLOC_TAIL=0: every PLOC round its own launches (A/B)
 
     explicit CudaBackend(int device) {
         int count = 0;
@@ -479,6 +516,7 @@ struct CudaBackend {
         if (const char *e = getenv("RTB_POOLED")) pooled_ = atoi(e);
         if (const char *e = getenv("RTB_FUSED")) fused_ = atoi(e);
         if (const char *e = getenv("RTB_SMEM_STACK")) g_smem_stack = atoi(e);
+        if (const char *e = getenv("RTB_PLOC_TAIL")) ploc_tail_off_ = atoi(e) == 0;
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
         int per_sm = 0;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<3, true>, kBlock, 0));
@@ -615,6 +653,18 @@ struct CudaBackend {
         if (dv.Current() != vals) copy(vals, dv.Current(), n);
         sync();
         free(k2); free(v2);
+    }
+    bool ploc_tail(const PlocArgs &a, int n_leaves, std::vector<int> &round_counts, int32_t &root) {
+        if (a.ncl > kPlocTail || ploc_tail_off_) return false;
+        int32_t *d_out = alloc<int32_t>(2 + kPlocTail);
+        k_ploc_tail<<<1, kPlocTail, 0, stream_>>>(a, n_leaves, d_out);
+        RTB_CUDA_CHECK(cudaGetLastError());
+        std::vector<int32_t> h(2 + kPlocTail);
+        download(h.data(), d_out, h.size());
+        free(d_out);
+        round_counts.assign(h.begin() + 2, h.begin() + 2 + h[0]);
+        root = h[1];
+        return true;
     }
     int compact_nonneg(const int32_t *in, int32_t *out, int n) {
         if (!d_count_) d_count_ = alloc<int32_t>(1);

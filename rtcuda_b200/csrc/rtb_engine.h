@@ -287,8 +287,16 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     int ncl = n, iters = 0;
     std::vector<int> round_first, round_count;  // binary nodes created by each PLOC round: ids are handed out in merge order
     int next_id = n;
+    int32_t root_b2 = -1;
     while (ncl > 1) {
         PlocArgs a; a.nodes = b2; a.count = count; a.cin = ca; a.cout = cb; a.nn = nn; a.node_counter = ctr; a.ncl = ncl; a.radius = radius;
+        // the last rounds handle a few hundred clusters each and are pure launch + host-sync latency (S1: 36 of 46
+        // rounds): once the clusters fit one thread block, one launch runs all the remaining rounds in shared memory
+        std::vector<int> tail_counts;
+        if (be.ploc_tail(a, n, tail_counts, root_b2)) {
+            for (int c : tail_counts) { round_first.push_back(next_id); round_count.push_back(c); next_id += c; ++iters; }
+            break;
+        }
         PlocNnK k1; k1.a = a; be.launch(ncl, k1);
         PlocMergeK k2; k2.a = a; k2.n_leaves = n; be.launch(ncl, k2);
         const int before = ncl;
@@ -297,8 +305,7 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
         next_id += before - ncl;
         ++iters;
     }
-    int32_t root_b2 = 0;
-    be.download(&root_b2, ca, 1);
+    if (root_b2 < 0) be.download(&root_b2, ca, 1);
     out.ploc_iterations = iters;
     be.free(prim_lo); be.free(prim_hi); be.free(keys); be.free(sorted); be.free(cb); be.free(nn); be.free(ca);
     // 4. collapse plan: bottom-up over the binary tree, one launch per PLOC round (a round's nodes only have older children)

@@ -81,6 +81,7 @@ struct HostBackend {
         memcpy(keys, k.data(), sizeof(uint64_t) * n);
         memcpy(vals, v.data(), sizeof(int32_t) * n);
     }
+    bool ploc_tail(const PlocArgs &, int, std::vector<int> &, int32_t &) { return false; }  // (a launch-latency measure of the CUDA backend)
     int compact_nonneg(const int32_t *in, int32_t *out, int n) {
         int m = 0;
         for (int i = 0; i < n; ++i) if (in[i] >= 0) out[m++] = in[i];
