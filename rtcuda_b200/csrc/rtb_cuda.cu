@@ -41,6 +41,13 @@
 namespace rtb {
 
 constexpr int kBlock = 256;
+// threads per block of the persistent trace kernels (warps are independent there: the block size only sets the
+// granularity at which a finished kernel hands its SM slots to the other wavefront's launches)
+#ifndef RTB_TRACE_BLOCK
+#define RTB_TRACE_BLOCK 256
+#endif
+constexpr int kTraceBlock = RTB_TRACE_BLOCK;
+constexpr int kTraceBlocksPerSm = 1024 / kTraceBlock;  // 32 warps per SM at 64 registers
 
 template <class F>
 __global__ void __launch_bounds__(kBlock) k_for(int n, F f) {
@@ -199,11 +206,11 @@ struct HybridStack {
     uint32_t x[kStackSize - N], y[kStackSize - N];
     __device__ explicit HybridStack(uint2 *column) : s(column) {}
     __device__ __forceinline__ void put(int i, uint32_t a, uint32_t b) {
-        if (i < N) s[i * kBlock] = make_uint2(a, b);
+        if (i < N) s[i * kTraceBlock] = make_uint2(a, b);
         else { x[i - N] = a; y[i - N] = b; }
     }
     __device__ __forceinline__ void get(int i, uint32_t &a, uint32_t &b) const {
-        if (i < N) { const uint2 v = s[i * kBlock]; a = v.x; b = v.y; }
+        if (i < N) { const uint2 v = s[i * kTraceBlock]; a = v.x; b = v.y; }
         else { a = x[i - N]; b = y[i - N]; }
     }
 };
@@ -387,17 +394,17 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
 // 108.9 ms); pooled per warp in shared memory (POOL, RTB_POOLED=1: C3 113.5 ms, C2 47.9 ms).
 // Tried and dropped: prefetching the next node into L2 during the triangle tests (C3 116 -> 140 ms, C2 40 -> 49 ms).
 template <int WHICH, bool POOL, bool INST = false>
-__global__ void __launch_bounds__(kBlock, 4) k_trace(WaveState W, SceneView S, FetchTuning tune) {
-    __shared__ WarpScratch scratch[kBlock / 32];
+__global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSm) k_trace(WaveState W, SceneView S, FetchTuning tune) {
+    __shared__ WarpScratch scratch[kTraceBlock / 32];
     WarpScratch &ws = scratch[threadIdx.x >> 5];
     if (WHICH & 1) persistent_trace<false, POOL, INST>(ws, W, S, tune);
     if (WHICH == 3) __syncwarp();
     if (WHICH & 2) persistent_trace<true, POOL, INST>(ws, W, S, tune);
 }
 constexpr int kSmemStack = 8;
-__global__ void __launch_bounds__(kBlock, 4) k_trace_smem_stack(WaveState W, SceneView S, FetchTuning tune) {  // k_trace<3, false> with HybridStack
-    __shared__ WarpScratch scratch[kBlock / 32];
-    __shared__ uint2 sstack[kSmemStack][kBlock];
+__global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSm) k_trace_smem_stack(WaveState W, SceneView S, FetchTuning tune) {  // k_trace<3, false> with HybridStack
+    __shared__ WarpScratch scratch[kTraceBlock / 32];
+    __shared__ uint2 sstack[kSmemStack][kTraceBlock];
     WarpScratch &ws = scratch[threadIdx.x >> 5];
     persistent_trace<false, false, false, HybridStack<kSmemStack>>(ws, W, S, tune, &sstack[0][threadIdx.x]);
     __syncwarp();
@@ -406,11 +413,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_trace_smem_stack(WaveState W, Sce
 static int g_smem_stack = 0;  // RTB_SMEM_STACK (A/B)
 template <int WHICH>
 static void launch_trace_kernel(int grid, cudaStream_t st, bool pooled, const WaveState &W, const SceneView &S, const FetchTuning &tune) {
-    if (WHICH == 3 && g_smem_stack && !S.bvh.inst && !pooled) { k_trace_smem_stack<<<grid, kBlock, 0, st>>>(W, S, tune); return; }
+    if (WHICH == 3 && g_smem_stack && !S.bvh.inst && !pooled) { k_trace_smem_stack<<<grid, kTraceBlock, 0, st>>>(W, S, tune); return; }
     if (S.bvh.inst) {  // two-level scene: stepped schedule, two triangles per step
-        k_trace<WHICH, false, true><<<grid, kBlock, 0, st>>>(W, S, tune);
-    } else if (pooled) k_trace<WHICH, true><<<grid, kBlock, 0, st>>>(W, S, tune);
-    else k_trace<WHICH, false><<<grid, kBlock, 0, st>>>(W, S, tune);
+        k_trace<WHICH, false, true><<<grid, kTraceBlock, 0, st>>>(W, S, tune);
+    } else if (pooled) k_trace<WHICH, true><<<grid, kTraceBlock, 0, st>>>(W, S, tune);
+    else k_trace<WHICH, false><<<grid, kTraceBlock, 0, st>>>(W, S, tune);
 }
 // one thread per queue entry (A/B against the persistent kernels; COUNT = work counters)
 template <bool COUNT>
@@ -519,7 +526,7 @@ struct CudaBackend {
         if (const char *e = getenv("RTB_PLOC_TAIL")) ploc_tail_off_ = atoi(e) == 0;
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
         int per_sm = 0;
-        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<3, true>, kBlock, 0));
+        RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<3, true>, kTraceBlock, 0));
         blocks_trace_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate, kBlock, 0));
         blocks_generate_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
