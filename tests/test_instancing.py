@@ -40,11 +40,12 @@ def field(L, ctx, bunny):
 
 
 def assert_hits_close(h, ref, tie_fraction=TIE_FRACTION):
-    """same triangle -> t within T_TOL, u / v close; a different triangle (or hit against miss) only on near-ties: a
-    ray within rounding of an edge may take the neighbour, or slip through the crack between two triangles — the
-    reference's triangle test (triangle.cuh:39-58) is not watertight, in either space"""
+    """same triangle -> t within T_TOL, u / v close.  A different triangle at the SAME distance is a tie (a ray through
+    the shared edge of two triangles: pixel-centre rays of the symmetric camera do that on the wall diagonals; which
+    one wins depends on the order of the tests, i.e. on the tree).  Anything else may only happen within rounding of
+    an edge: there a ray takes the neighbour, or slips through the crack between two triangles — the reference's
+    triangle test (triangle.cuh:39-58) is not watertight, in either space."""
     differ = h["prim"] != ref["prim"]
-    assert differ.mean() <= tie_fraction, f"{differ.sum()} of {len(h)} hit ids differ"
     same = ~differ & (ref["prim"] >= 0)
     dt = np.abs(h["t"][same].astype(np.float64) - ref["t"][same])
     assert (dt <= T_TOL * np.maximum(ref["t"][same], 1.0)).all(), dt.max()
@@ -52,13 +53,16 @@ def assert_hits_close(h, ref, tie_fraction=TIE_FRACTION):
     # 12 x 12 field is 5e-4 across, less when seen at a grazing angle)
     duv = np.maximum(np.abs(h["u"][same] - ref["u"][same]), np.abs(h["v"][same] - ref["v"][same]))
     assert np.quantile(duv, 0.99) <= 1e-3 and duv.max() <= 5e-2
-    # where the triangle differs, the one the flattened scene reports was missed by a hair: its hit lies on an edge
-    # (or the other way round)
+    both = (h["prim"] >= 0) & (ref["prim"] >= 0)
+    tie = differ & both & (np.abs(h["t"].astype(np.float64) - ref["t"]) <= T_TOL * np.maximum(ref["t"], 1.0))
+    assert tie.mean() <= 1e-3, f"{tie.sum()} ties of {len(h)}"
+    hard = differ & ~tie
+    assert hard.mean() <= tie_fraction, f"{hard.sum()} of {len(h)} hits differ"
+
     def edge(x):
         e = np.minimum(np.minimum(x["u"], x["v"]), 1 - x["u"] - x["v"])
         return np.where(x["prim"] >= 0, e, 1.0)
-    near_tie = np.abs(h["t"][differ].astype(np.float64) - ref["t"][differ]) <= T_TOL * np.maximum(ref["t"][differ], 1.0)
-    assert ((edge(ref[differ]) <= 1e-3) | (edge(h[differ]) <= 1e-3) | near_tie).all()
+    assert ((edge(ref[hard]) <= 1e-3) | (edge(h[hard]) <= 1e-3)).all()
 
 
 def test_flattening_reproduces_the_flat_generator(emu, bunny):
@@ -128,7 +132,8 @@ def test_feature_buffers_match_the_flattened_scene(field):
     al, no, de, pr = si.render_aovs(cam, 96, 96)
     al2, no2, de2, pr2 = sf.render_aovs(cam, 96, 96)
     same = pr == pr2
-    assert same.mean() >= 1 - 1e-3
+    tie = ~same & (pr >= 0) & (pr2 >= 0) & (np.abs(de - de2) <= T_TOL * np.maximum(de2, 1.0))  # the wall diagonals
+    assert (same | tie).mean() >= 1 - 1e-3 and tie.mean() <= 1e-2
     assert np.abs(al - al2)[same].max() == 0
     assert np.abs(no - no2)[same].max() <= 1e-4
     assert np.abs(de - de2)[same].max() <= T_TOL * max(1.0, float(de2.max()))
