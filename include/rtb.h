@@ -214,7 +214,7 @@ typedef struct rtb_render_stats {
     float ms_shade;        /* summed duration of shade + generate + control (part of ms_other) */
     int32_t fused_trace;   /* 1: extend and shadow rays ran in ONE launch per iteration; then ms_extend
                               is the duration of that launch and ms_shadow is 0 */
-    int32_t pipelines;     /* independent wavefronts run on concurrent streams (1 or 2); the per-stage
+    int32_t pipelines;     /* independent wavefronts run on concurrent streams (1..4); the per-stage
                               times above are only measured with 1 (RTB_RENDER_SINGLE_PIPELINE) */
     int32_t _pad;
 } rtb_render_stats;

@@ -41,10 +41,14 @@
 namespace rtb {
 
 constexpr int kBlock = 256;
-// threads per block of the persistent trace kernels (warps are independent there: the block size only sets the
-// granularity at which a finished kernel hands its SM slots to the other wavefront's launches)
+// Threads per block of the persistent trace kernels (warps are independent there).  At 64 registers 32 warps fill the
+// register file of an SM: a trace kernel launched at full occupancy leaves no room for any block of the OTHER
+// wavefront, whose kernels then only start in its tail.  With two wavefronts each trace kernel therefore takes HALF
+// the SM (4 blocks of 128 threads, trace_grid()), so that the two wavefronts really run side by side — one's
+// issue-bound traversal next to the other's DRAM-bound shading (128-thread shade blocks fit the registers left):
+// C2 37.4 -> 35.4 ms, C4 37.6 -> 29.2 ms, C1 3.34 -> 2.97 ms (profiles/README.md, sessions 74-76).
 #ifndef RTB_TRACE_BLOCK
-#define RTB_TRACE_BLOCK 256
+#define RTB_TRACE_BLOCK 128
 #endif
 constexpr int kTraceBlock = RTB_TRACE_BLOCK;
 constexpr int kTraceBlocksPerSm = 1024 / kTraceBlock;  // 32 warps per SM at 64 registers
@@ -73,14 +77,18 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 // the same SM at the same time.  C2, two wavefronts: 38.62 -> 38.10 ms; alone (one wavefront) shade itself is slower
 // (9.1 -> 10.2 ms) and the trace kernel after it faster (30.2 -> 29.3 ms).
 // The specular kernels need 64 registers: three blocks each.
-constexpr int shade_blocks_per_sm(int type) { return (type == RTB_MIRROR || type == RTB_GLASS) ? 3 : 2; }
+#ifndef RTB_SHADE_BLOCK
+#define RTB_SHADE_BLOCK 128
+#endif
+constexpr int kShadeBlock = RTB_SHADE_BLOCK;  // small blocks: they fit the registers a half-occupancy trace kernel leaves free
+constexpr int shade_blocks_per_sm(int type) { return ((type == RTB_MIRROR || type == RTB_GLASS) ? 3 : 2) * (256 / kShadeBlock); }
 template <int TYPE, bool EXT = false>
-__global__ void __launch_bounds__(kBlock, shade_blocks_per_sm(TYPE)) k_shade(WaveState W, SceneView S, RenderConsts rc, bool shadows) {
-    __shared__ float4 stage[2][3][kBlock];
+__global__ void __launch_bounds__(kShadeBlock, shade_blocks_per_sm(TYPE)) k_shade(WaveState W, SceneView S, RenderConsts rc, bool shadows) {
+    __shared__ float4 stage[2][3][kShadeBlock];
     const int n = W.c->n_mat[TYPE];
-    const int stride = gridDim.x * kBlock, t = threadIdx.x;
+    const int stride = gridDim.x * kShadeBlock, t = threadIdx.x;
     ShadeTally tally; tally.extend = 0u; tally.shadow = 0u;
-    int i = blockIdx.x * kBlock + t;
+    int i = blockIdx.x * kShadeBlock + t;
     if (i < n) {
         const size_t q = (size_t)TYPE * W.pool + (size_t)i;
         cp_async16(&stage[0][0][t], W.ma + q); cp_async16(&stage[0][1][t], W.mb + q); cp_async16(&stage[0][2][t], W.mc + q);
@@ -476,8 +484,9 @@ struct CudaBackend {
     cudaStream_t stream_ = nullptr;  // the stream launches go to: streams_[0] unless use_stream(k) says otherwise
     cudaStream_t streams_[kMaxPipelines] = {nullptr, nullptr};
     cudaEvent_t sync_ev_ = nullptr;
-    int pipelines_ = 2;  // RTB_PIPELINES: concurrent wavefronts per render (1 or 2)
+    int pipelines_ = 0;  // RTB_PIPELINES: concurrent wavefronts per render (1..4); 0 = by scene size, see pipelines()
     int blocks_trace_ = 0, blocks_generate_ = 0;
+    int trace_blocks_per_sm_ = 1, trace_cap_ = 0, active_pipelines_ = 1;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
     int32_t *d_count_ = nullptr;
@@ -527,7 +536,9 @@ struct CudaBackend {
         if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
         int per_sm = 0;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<3, true>, kTraceBlock, 0));
-        blocks_trace_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
+        trace_blocks_per_sm_ = per_sm > 0 ? per_sm : 1;
+        if (const char *e = getenv("RTB_TRACE_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= trace_blocks_per_sm_) trace_cap_ = v; }  // (A/B)
+        blocks_trace_ = num_sms_ * trace_blocks_per_sm_;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate, kBlock, 0));
         blocks_generate_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
     }
@@ -582,21 +593,31 @@ struct CudaBackend {
     void shade(const ShadeK &k) {
         const int grid = num_sms_ * shade_blocks_per_sm(k.type);  // one resident wave: the kernels are grid-stride loops
         if ((k.rc.flags & (RTB_RENDER_TRUE_MIS | RTB_RENDER_RR_TERMINATE)) || k.S.bvh.inst) {  // beyond-the-reference estimator, instanced scenes
-            if (k.type == 0) k_shade<0, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else if (k.type == 1) k_shade<1, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else if (k.type == 2) k_shade<2, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else k_shade<3, true><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            if (k.type == 0) k_shade<0, true><<<grid, kShadeBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 1) k_shade<1, true><<<grid, kShadeBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 2) k_shade<2, true><<<grid, kShadeBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else k_shade<3, true><<<grid, kShadeBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         } else {
-            if (k.type == 0) k_shade<0><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else if (k.type == 1) k_shade<1><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else if (k.type == 2) k_shade<2><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
-            else k_shade<3><<<grid, kBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            if (k.type == 0) k_shade<0><<<grid, kShadeBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 1) k_shade<1><<<grid, kShadeBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else if (k.type == 2) k_shade<2><<<grid, kShadeBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
+            else k_shade<3><<<grid, kShadeBlock, 0, stream_>>>(k.W, k.S, k.rc, k.shadows);
         }
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void control(const WaveState &W, bool shadows) {
         k_control<<<1, 1, 0, stream_>>>(W, shadows);
         RTB_CUDA_CHECK(cudaGetLastError());
+    }
+    // Grid of a persistent trace launch.  Two wavefronts: half the resident blocks each (see kTraceBlock) — unless the
+    // scene is far beyond L2: there the kernel waits on DRAM latency, wants every warp it can get, and the half-size
+    // launches were measured 1 % slower (C3 99.4 -> 100.3 ms).
+    void begin_render(int pipelines) { active_pipelines_ = pipelines; }
+    int trace_grid(const SceneView &S) const {
+        int per = trace_blocks_per_sm_;
+        if (trace_cap_ > 0) per = trace_cap_;
+        else if (active_pipelines_ > 1 && !big_scene(S)) per = per / active_pipelines_ > 0 ? per / active_pipelines_ : 1;
+        return num_sms_ * per;
     }
     // mode 0: persistent, 1: one thread per ray, 2: one thread per ray + work counters
     bool big_scene(const SceneView &S) const {  // nodes + triangles beyond what stays resident in the 126 MB L2
@@ -607,25 +628,27 @@ struct CudaBackend {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
         else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else launch_trace_kernel<1>(blocks_trace_, stream_, use_pooled(S), W, S, tune_);
+        else launch_trace_kernel<1>(trace_grid(S), stream_, use_pooled(S), W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shadow(const WaveState &W, const SceneView &S, int mode) {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
         else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else launch_trace_kernel<2>(blocks_trace_, stream_, use_pooled(S), W, S, tune_);
+        else launch_trace_kernel<2>(trace_grid(S), stream_, use_pooled(S), W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     // both ray types in one launch; false = not available in this mode
     bool trace_fused(const WaveState &W, const SceneView &S, int mode) {
         if (mode != 0 || !fused_) return false;
-        launch_trace_kernel<3>(blocks_trace_, stream_, use_pooled(S), W, S, tune_);
+        launch_trace_kernel<3>(trace_grid(S), stream_, use_pooled(S), W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
         return true;
     }
     // ---- concurrent wavefronts (rtb_engine.h, render_accumulate) ----
-    int pipelines() const { return pipelines_; }
+    // Four wavefronts, each trace kernel a quarter of the SM, while nodes + triangles stay in L2 (C4 29.0 -> 27.5 ms,
+    // C2 35.2 -> 34.9 ms against two); two full-size ones on a scene far beyond it (C3 98.7 ms against 101.6 with four).
+    int pipelines(const SceneView &S) const { return pipelines_ > 0 ? pipelines_ : (big_scene(S) ? 2 : 4); }
     void use_stream(int k) { stream_ = streams_[k]; }
     void fork(int k) {  // stream k continues after what is queued on the main stream
         RTB_CUDA_CHECK(cudaEventRecord(sync_ev_, streams_[0]));

@@ -149,7 +149,7 @@ struct AovK {
 };
 
 // ---- scene ----
-constexpr int kMaxPipelines = 2;
+constexpr int kMaxPipelines = 4;
 template <class BE>
 struct SceneT {
     BE *be = nullptr;
@@ -788,7 +788,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
     long long pool_all = p.pool_size > 0 ? p.pool_size : be.default_pool();
     if ((unsigned long long)pool_all > total) pool_all = (long long)total;
-    int np = be.pipelines();
+    int np = be.pipelines(sc.view());
     if (np > kMaxPipelines) np = kMaxPipelines;
     if (np < 1 || mode != 0 || (p.flags & RTB_RENDER_SINGLE_PIPELINE) || pool_all < (1 << 16)) np = 1;
     const int pool = (int)(((pool_all + np - 1) / np + 31) & ~31ll);
@@ -798,6 +798,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     WaveState W[kMaxPipelines];
     RenderConsts rc[kMaxPipelines];
     be.use_stream(0);  // (an error thrown out of an earlier call may have left another stream selected)
+    be.begin_render(np);
     auto t0 = be.now();
     for (int k = 0; k < np; ++k) {
         if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(2 * kNumMaterialTypes * (size_t)pool);

@@ -64,7 +64,8 @@ struct HostBackend {
     }
     bool trace_fused(const WaveState &, const SceneView &, int) { return false; }
     int32_t done_word_ = 0;
-    int pipelines() const { return 1; }
+    int pipelines(const SceneView &) const { return 1; }
+    void begin_render(int) {}
     void use_stream(int) {}
     void fork(int) {}
     void join(int) {}

@@ -266,7 +266,7 @@ def test_persistent_kernel_matches_one_thread_per_ray(gpu, bunny):
     b, sb = sc.render(cam, capi.render_params(gpu, flags=capi.RTB_RENDER_NONPERSISTENT, **kw))
     c, sc_ = sc.render(cam, capi.render_params(gpu, flags=capi.RTB_RENDER_SINGLE_PIPELINE, **kw))
     assert sa.extend_rays == sb.extend_rays == sc_.extend_rays and sa.shadow_rays == sb.shadow_rays == sc_.shadow_rays
-    assert sa.fused_trace == 1 and sa.pipelines == 2
+    assert sa.fused_trace == 1 and sa.pipelines >= 2
     assert mean_rel_err(a, b) <= 1e-6 and mean_rel_err(c, b) <= 1e-6  # (only the order of the accumulation atomics differs)
 
 
