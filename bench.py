@@ -371,7 +371,7 @@ def main():
         # ---- roofline of the dominant kernel, measured live ----
         # k_trace<3>: the extend AND shadow rays of one iteration in one persistent launch (stats.fused_trace);
         # its duration is ms_extend (CUDA events on the render stream inside rtb_render_accumulate).
-        # The timed steps run two concurrent wavefronts (streams), whose kernels overlap; the per-kernel durations
+        # The timed steps run four (or two) concurrent wavefronts (streams), whose kernels overlap; the per-kernel durations
         # come from extra steps with RTB_RENDER_SINGLE_PIPELINE (one stream, the kernel timed alone).
         ps = capi.render_params(L, width=W, height=H, spp=spp, max_bounces=depth, first_sample=rank * spp,
                                 total_spp=total_spp, pool_size=args.pool, flags=args.flags | capi.RTB_RENDER_SINGLE_PIPELINE)

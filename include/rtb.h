@@ -188,7 +188,7 @@ enum {
     RTB_RENDER_NO_SHADOW = 2,    /* skip next-event estimation (debug) */
     RTB_RENDER_NONPERSISTENT = 4, /* one-thread-per-ray traversal launch (A/B for the persistent kernel) */
     RTB_RENDER_COUNT_WORK = 8,    /* counting kernel variants: fill the *_nodes / *_tris statistics (slower) */
-    RTB_RENDER_SINGLE_PIPELINE = 16, /* one wavefront on one stream (per-stage timing; default is two concurrent ones) */
+    RTB_RENDER_SINGLE_PIPELINE = 16, /* one wavefront on one stream (per-stage timing; default is four concurrent ones, two on scenes beyond L2) */
     /* ---- beyond the reference: OFF by default, parity mode is untouched ---- */
     RTB_RENDER_TRUE_MIS = 32,     /* power_heuristic(float, float) for the light sample, and the path ray itself is the
                                      BSDF sample of the MIS pair: emitters met after a bounce add beta * L * w (the

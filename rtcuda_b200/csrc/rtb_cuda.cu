@@ -43,10 +43,11 @@ namespace rtb {
 constexpr int kBlock = 256;
 // Threads per block of the persistent trace kernels (warps are independent there).  At 64 registers 32 warps fill the
 // register file of an SM: a trace kernel launched at full occupancy leaves no room for any block of the OTHER
-// wavefront, whose kernels then only start in its tail.  With two wavefronts each trace kernel therefore takes HALF
-// the SM (4 blocks of 128 threads, trace_grid()), so that the two wavefronts really run side by side — one's
-// issue-bound traversal next to the other's DRAM-bound shading (128-thread shade blocks fit the registers left):
-// C2 37.4 -> 35.4 ms, C4 37.6 -> 29.2 ms, C1 3.34 -> 2.97 ms (profiles/README.md, sessions 74-76).
+// wavefront, whose kernels then only start in its tail.  With W wavefronts each trace launch therefore takes 1 / W of
+// the SM (8 / W blocks of 128 threads, trace_grid()), so that the wavefronts really run side by side — one's
+// issue-bound traversal next to another's DRAM-bound shading (128-thread shade blocks fit the registers left):
+// two wavefronts C2 37.4 -> 35.4 ms, C4 37.6 -> 29.2 ms, C1 3.34 -> 2.97 ms; four 34.9 / 27.5 / 2.92 ms
+// (profiles/README.md, sessions 74-77).
 #ifndef RTB_TRACE_BLOCK
 #define RTB_TRACE_BLOCK 128
 #endif
@@ -72,11 +73,8 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
-// Two blocks per SM (up to 128 registers: no spills), not the three that fit at 80 registers: shade is bound by DRAM and
-// latency, and what it leaves free lets a block of the OTHER wavefront's trace kernel (64 registers, issue bound) run on
-// the same SM at the same time.  C2, two wavefronts: 38.62 -> 38.10 ms; alone (one wavefront) shade itself is slower
-// (9.1 -> 10.2 ms) and the trace kernel after it faster (30.2 -> 29.3 ms).
-// The specular kernels need 64 registers: three blocks each.
+// Up to 128 registers (no spills; the matte / glossy kernels take 94, 80 would spill): shade is bound by DRAM and
+// latency, not by its occupancy.  The specular kernels need 64 registers and get half as many more blocks.
 #ifndef RTB_SHADE_BLOCK
 #define RTB_SHADE_BLOCK 128
 #endif
