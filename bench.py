@@ -460,6 +460,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline and not instanced:  # (the oracle would need the 10 M flattened triangles)
             cb = cpu_baseline_port(capi, L, hs, cam, capi.render_params(L, width=W, height=H, spp=spp, max_bounces=depth))
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:  # the same port on ONE host thread as well (smaller sample)
+                c1 = cpu_baseline_port(capi, L, hs, cam, capi.render_params(L, width=W, height=H, spp=spp, max_bounces=depth), budget_s=4.0, threads=1)
+                line["cpu_baseline"]["one_thread"] = {"value": c1["value"], "unit": c1["unit"], "cores": 1, "sample": c1["sample"]}
+            except Exception as e:  # (a reported extra, never a reason to lose the line)
+                line["cpu_baseline"]["one_thread"] = {"error": str(e)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
