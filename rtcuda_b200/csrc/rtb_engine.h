@@ -567,11 +567,13 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
         if (d.materials[i].type < 0 || d.materials[i].type >= kNumMaterialTypes) throw Error(RTB_ERR_INVALID, "unknown material type");
     std::vector<int> uses((size_t)nm, 0), ident((size_t)nm, 1);
     std::vector<long long> flat_first((size_t)ni + 1, 0);
+    std::vector<double> inverse(12 * (size_t)ni);  // world -> object, checked before any device work
     for (int i = 0; i < ni; ++i) {
         const rtb_instance &in = D.instances[i];
         if (in.mesh < 0 || in.mesh >= nm) throw Error(RTB_ERR_INVALID, "instance: mesh out of range");
         if (in.material < -1 || in.material >= d.num_materials) throw Error(RTB_ERR_INVALID, "instance: material out of range");
         for (int k = 0; k < 12; ++k) if (!std::isfinite(in.xform[k])) throw Error(RTB_ERR_INVALID, "instance: transform not finite");
+        if (!invert3x4(in.xform, &inverse[12 * (size_t)i])) throw Error(RTB_ERR_INVALID, "instance: transform not invertible");
         uses[(size_t)in.mesh]++;
         if (!is_identity3x4(in.xform)) ident[(size_t)in.mesh] = 0;
         flat_first[(size_t)i + 1] = flat_first[(size_t)i] + (D.mesh_first[in.mesh + 1] - D.mesh_first[in.mesh]);
@@ -721,8 +723,7 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
         std::vector<F4> rec((size_t)ni * kInstWords);
         for (int i = 0; i < ni; ++i) {
             const rtb_instance &in = D.instances[i];
-            double inv[12];
-            if (!invert3x4(in.xform, inv)) throw Error(RTB_ERR_INVALID, "instance: transform not invertible");
+            const double *inv = &inverse[12 * (size_t)i];
             F4 *r = rec.data() + (size_t)i * kInstWords;
             for (int k = 0; k < 3; ++k) {
                 r[k].x = (float)inv[4 * k]; r[k].y = (float)inv[4 * k + 1]; r[k].z = (float)inv[4 * k + 2]; r[k].w = (float)inv[4 * k + 3];
