@@ -421,6 +421,21 @@ def main():
                       "note": "ncu lts__t_bytes per ray x rays per launch / launch duration; peak = tools/l2_bandwidth.cu on this pool's B200 (profiles/l2_bandwidth.json)"}
         except Exception:
             pass
+        # SURVEY 8d floor model: one root-to-leaf descent of a BVH8 with <= 4 triangles per leaf, 80 B nodes, 48 B
+        # triangles, 48 B of ray I/O: ceil(log8(n / 4)) * 80 + 4 * 48 + 48 bytes per ray, all of it from HBM
+        floor = None
+        try:
+            import math
+            n_flat = int(bst.num_flat_triangles) or int(bst.num_triangles)
+            floor_bytes = math.ceil(math.log(max(n_flat / 4.0, 8.0), 8)) * 80 + 4 * 48 + 48
+            rays_per_s = (ext_rays + shd_rays) / (tr_ms * 1e-3) if tr_ms > 0 else 0.0
+            floor_rate = peak * 1e9 / floor_bytes
+            floor = {"bytes_per_ray": floor_bytes, "rays_per_s_at_peak": floor_rate, "kernel_rays_per_s": rays_per_s,
+                     "frac": rays_per_s / floor_rate,
+                     "note": "rays per second of the trace kernel while it runs (single-pipeline steps) against the HBM peak divided by the "
+                             "floor-model bytes per ray; above 1 when the scene is served by L1 / L2 and a ray needs fewer bytes than the model"}
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_trace<3> (extend + shadow rays, one persistent launch per iteration)" if fused else "k_trace<1> + k_trace<2>",
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -430,7 +445,7 @@ def main():
                     "avg_launch_ms": avg_launch_ms, "launches": int(tr_launches), "timed_with": "single pipeline (kernel alone on one stream), %d steps" % len(s0),
                     "single_pipeline_ms_per_step": tot_ms / len(s0),
                     "kernel_share_of_step": tr_ms / tot_ms if tot_ms else None,
-                    "shade_share_of_step": sh_ms / tot_ms if tot_ms else None, "l2": l2,
+                    "shade_share_of_step": sh_ms / tot_ms if tot_ms else None, "l2": l2, "floor_model": floor,
                     "note": "scene (%.1f MB nodes+triangles) %s; node/triangle counts from the counting kernel variant"
                             % ((bst.node_bytes + bst.triangle_bytes) / 1e6,
                                "is L2-resident: the kernel is bound by instruction issue, not by HBM (see profiles/)" if bst.node_bytes + bst.triangle_bytes < 100e6
