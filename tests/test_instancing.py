@@ -291,3 +291,59 @@ def test_full_size_field_as_instances(gpu, bunny):
     b, sb = sf.render(cam, p)
     assert sa.paths == sb.paths
     assert mean_rel_err(a, b) <= IMAGE_TOL
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_affine_placements_match_the_flattened_scene(emu, seed):
+    """two soups, nine instances with RANDOM invertible matrices (rotation, non-uniform scale, shear, some mirrored),
+    random material overrides: hits and a small render equal those of the flattened scene (host build of the kernels)"""
+    rng = np.random.default_rng(100 + seed)
+    n1, n2 = 60, 90
+
+    def soup(n):
+        c = (rng.random((n, 1, 3)).astype(np.float32) - np.float32(0.5))
+        return (c + (rng.random((n, 3, 3)).astype(np.float32) - np.float32(0.5)) * np.float32(0.6)).astype(np.float32)
+    static = np.array([[[0, 0, 0], [1, 0, 0], [1, 0, -1]], [[0, 0, 0], [0, 0, -1], [1, 0, -1]],
+                       [[0.3, 0.99, -0.3], [0.7, 0.99, -0.3], [0.7, 0.99, -0.7]]], np.float32)
+    verts = np.concatenate([soup(n1), soup(n2), static]).reshape(-1, 9)
+    nt = len(verts)
+    mat = (np.arange(nt) % 4).astype(np.int32)
+    mat[-3:] = 0
+    lid = np.full(nt, -1, np.int32)
+    lid[-1] = 0
+    desc, keep = make_desc(verts, mat, lid, std_materials() + [glossy()], [area_light(nt - 1)])
+    mesh_first = np.array([0, n1, n1 + n2, nt], np.int64)
+    placements = []
+    for k in range(9):
+        M = rng.normal(size=(3, 3)) * 0.15 + np.diag(rng.choice([-1.0, 1.0], 3) * (0.12 + 0.15 * rng.random(3)))
+        if abs(np.linalg.det(M)) < 1e-4:
+            M += np.eye(3) * 0.2
+        t = np.array([0.15 + 0.7 * rng.random(), 0.15 + 0.6 * rng.random(), -0.15 - 0.7 * rng.random()])
+        placements.append((int(rng.integers(0, 2)), int(rng.integers(-1, 4)), np.concatenate([M, t[:, None]], axis=1).astype(np.float32).reshape(-1)))
+    placements.append((2, -1, np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)))
+    inst = (capi.Instance * len(placements))()
+    for k, (m, ma, x) in enumerate(placements):
+        inst[k].mesh = m; inst[k].material = ma
+        for j in range(12):
+            inst[k].xform[j] = float(x[j])
+    idesc = capi.InstancedSceneDesc()
+    idesc.geometry = desc
+    idesc.num_meshes = 3
+    idesc.mesh_first = mesh_first.ctypes.data_as(C.c_void_p).value
+    idesc.num_instances = len(placements)
+    idesc.instances = C.cast(inst, C.c_void_p).value
+    ctx = emu.context(0)
+    si = ctx.scene(idesc)
+    flat = emu.flatten(idesc)
+    sf = ctx.scene(flat.desc)
+    assert si.stats().num_flat_triangles == flat.desc.num_triangles
+    cam = emu.camera_look_at((0.5, 0.5, 1.4), (0.5, 0.45, -0.5), (0, 1, 0), 40.0, 1.0)
+    rays = np.concatenate([emu.primary_rays(cam, 96, 96), random_rays(20000, seed=seed)])
+    assert_hits_close(si.trace_closest(rays), sf.trace_closest(rays), tie_fraction=1e-3)
+    occ_i, occ_f = si.trace_any(rays), sf.trace_any(rays)
+    assert (occ_i == occ_f).mean() >= 1 - 1e-3
+    p = capi.render_params(emu, width=40, height=40, spp=4, max_bounces=8, rr_start=2)
+    a, sa = si.render(cam, p)
+    b, sb = sf.render(cam, p)
+    assert sa.paths == sb.paths
+    assert mean_rel_err(a, b) <= IMAGE_TOL
