@@ -176,7 +176,8 @@ typedef struct rtb_render_params {
     int32_t total_spp;      /* divisor used by the tonemap; 0 means spp */
     int32_t pool_size;      /* path slots (NUM_WORKING_PATHS, constant.hpp:8); 0 = auto */
     int32_t flags;          /* RTB_RENDER_* */
-    int32_t _reserved;
+    uint32_t device_mask;   /* rtb_multi_render: bit i set = use GPU i of the rtb_multi; 0 = all of them.  rtb_render /
+                               rtb_render_accumulate run on the one GPU of the scene's context and reject a mask without it */
     float env_L[3];         /* radiance of a constant environment seen by rays that leave the scene (the reference's
                                TODO at render.cuh:105,243,325); (0,0,0) = none, as in the reference */
     int32_t _reserved2;
@@ -194,7 +195,12 @@ enum {
                                      BSDF sample of the MIS pair: emitters met after a bounce add beta * L * w (the
                                      reference truncates the BSDF pdf to int and aims its MIS ray at the wrong triangle,
                                      utility.cuh:53, render.cuh:236; specular paths then never see a light) */
-    RTB_RENDER_RR_TERMINATE = 64  /* a Russian-roulette kill ends the path (the reference only pauses it, render.cuh:112-126) */
+    RTB_RENDER_RR_TERMINATE = 64, /* a Russian-roulette kill ends the path (the reference only pauses it, render.cuh:112-126) */
+    RTB_RENDER_DETERMINISTIC = 128 /* radiance sums in 64-bit fixed point (2^-28) instead of float atomics (vec3.cuh:149-153, whose
+                                     result depends on the order of the splats): the image is bit-identical from run to run and for
+                                     ANY split of the samples over wavefronts, calls and GPUs (rtb_multi_render reduces the integer
+                                     sums).  Splats are clamped to +-2^24.  Slower splats (three 64-bit atomics instead of one
+                                     128-bit vector reduction); off by default */
 };
 
 typedef struct rtb_render_stats {
@@ -228,6 +234,14 @@ RTB_API const char *rtb_version(void);
 RTB_API int rtb_context_create(int device_ordinal, rtb_context **out);
 RTB_API int rtb_context_destroy(rtb_context *ctx);
 RTB_API int rtb_context_device(const rtb_context *ctx);
+/* Schedule of the traversal / wavefront kernels (replaces compile-time choices such as BLOCK_SIZE, render.cuh:413, and
+ * NUM_WORKING_PATHS, constant.hpp:8).  Every schedule gives bit-identical hits; the defaults are the measured best
+ * (DESIGN.md 4).  Names: "refill" (1..32), "chunk" (>= 32), "prefetch" (0/1), "tri_step" (0..4), "pooled" (-1/0/1),
+ * "fused" (0/1), "smem_stack" (0/1), "pipelines" (0 = by scene size, 1..4), "pool" (path slots, >= 1024),
+ * "ploc_tail" (0/1), "trace_blocks" (0 = auto, 1..8 resident blocks per SM).  Unknown names / values out of range:
+ * RTB_ERR_INVALID.  Takes effect for scenes built and renders started afterwards. */
+RTB_API int rtb_context_set_option(rtb_context *ctx, const char *name, int64_t value);
+RTB_API int rtb_context_get_option(const rtb_context *ctx, const char *name, int64_t *value);
 
 /* ---- scene + BVH build (replaces Bvh::Bvh, bvh.cuh:30-219, and the Scene
  *      aggregate scene.cuh:4-8; uploads that main.cu:46-138 does by hand) ---- */
@@ -266,6 +280,17 @@ RTB_API int rtb_trace_closest_device(rtb_scene *scene, const rtb_ray *d_rays, in
 RTB_API int rtb_trace_any_device(rtb_scene *scene, const rtb_ray *d_rays,
                                  const int32_t *d_excluded, int64_t n, uint8_t *d_occluded,
                                  float *ms);
+/* The same two queries through the RENDER path's own traversal kernel (the persistent k_trace launch that
+ * rtb_render runs once per wavefront iteration, in place of kernels ch / ah, render.cuh:278-328): the rays are
+ * loaded into the extend / shadow queues, one iteration's trace launch(es) run with the context's schedule
+ * (rtb_context_set_option), and the results are read back from the hit queues / the accumulation buffer.  The
+ * parity tests compare THIS entry with the reference's Bvh::traverse (bvh.cuh:251-357), so the kernel that is pinned
+ * is the kernel that renders.  Either ray set may be empty (n = 0, null pointers).  Closest-hit rays are unbounded
+ * like the render's path rays (Ray::tmax = FLT_MAX, ray.cuh:10): their tmax field is ignored.  h_excluded as in
+ * rtb_trace_any (not supported on instanced scenes).  *launches (may be NULL) = trace launches made. */
+RTB_API int rtb_trace_wavefront(rtb_scene *scene, const rtb_ray *h_rays, int64_t n, rtb_hit *h_hits,
+                                const rtb_ray *h_shadow_rays, const int32_t *h_excluded, int64_t n_shadow,
+                                uint8_t *h_occluded, int32_t *launches);
 /* traversal work counters for the roofline model: mean 80-byte nodes fetched
  * and triangles tested per ray (closest-hit), from a counting kernel variant */
 RTB_API int rtb_trace_closest_counts(rtb_scene *scene, const rtb_ray *h_rays, int64_t n,
@@ -290,6 +315,13 @@ RTB_API int rtb_render(rtb_scene *scene, const rtb_camera *cam, const rtb_render
 RTB_API int rtb_render_accumulate(rtb_scene *scene, const rtb_camera *cam,
                                   const rtb_render_params *p, float *d_accum,
                                   rtb_render_stats *stats);
+/* the same into a buffer of 64-bit fixed-point sums (int64_t[3*W*H], units of 2^-28, device memory, not cleared):
+ * integer sums of sample-pass shards are exact, so the reduced image does not depend on the sharding
+ * (implies RTB_RENDER_DETERMINISTIC) */
+RTB_API int rtb_render_accumulate_fixed(rtb_scene *scene, const rtb_camera *cam, const rtb_render_params *p,
+                                        int64_t *d_accum_fixed, rtb_render_stats *stats);
+RTB_API int rtb_tonemap_fixed_device(rtb_context *ctx, const int64_t *d_accum_fixed, int64_t num_values,
+                                     int32_t total_spp, float *d_out);
 /* d_out[i] = sqrt(d_accum[i] / total_spp)  (post_process_framebuffer, render.cuh:330-338);
  * d_out may alias d_accum */
 RTB_API int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t num_floats,
@@ -301,6 +333,20 @@ RTB_API int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t n
  * the caller's list (int32[W*H], -1 for a miss).  Any pointer may be NULL.  Row 0 = top, like rtb_render. */
 RTB_API int rtb_render_aovs(rtb_scene *scene, const rtb_camera *cam, int32_t width, int32_t height,
                             float *h_albedo, float *h_normal, float *h_depth, int32_t *h_prim);
+
+/* Known-answer hooks: evaluate ONE device function of the render path per record, on the GPU, so that unit tests
+ * can compare it with the oracle ("unit KATs for ray/triangle, ray/box, offset_ray_origin, BSDF/light
+ * sampling").  h_in / h_out hold n records of floats (integers travel as their bits):
+ *   RTB_KAT_TRI_INTERSECT  in[16] p0 p1 p2 | ray origin, dir, tmax   out[4] hit (0/1), t, u, v      triangle.cuh:4-58
+ *   RTB_KAT_OFFSET_ORIGIN  in[6]  p, n                               out[3] offset origin           utility.cuh:31-47
+ *   RTB_KAT_RAND4          in[4]  seed, pixel, sample, block (u32)   out[4] four uniforms in (0,1]  replaces curand_uniform
+ *   RTB_KAT_SAMPLE_F       in[16] albedo, ior, type (i32), wo, n, u1, u2, 3 pad   out[12] f, n, wi, pdf, 2 pad   material.cuh:60-109
+ *   RTB_KAT_SLAB           in[20] parent box lo hi | child box lo hi | ray origin, dir, tmax, 1 pad   out[1] 1 if the quantised
+ *                          child box passes the slab test of the 8-wide node (must hold whenever the exact box meets [0, tmax]:
+ *                          aabb_intersector.cuh:14-36 restated conservatively)
+ *   RTB_KAT_SAMPLE_LI      in[16] light triangle p0 p1 p2 | shading point, u1, u2, 2 pad   out[8] wi, t, pdf, 3 pad   light.cuh:38-46 */
+enum { RTB_KAT_TRI_INTERSECT = 1, RTB_KAT_OFFSET_ORIGIN = 2, RTB_KAT_RAND4 = 3, RTB_KAT_SAMPLE_F = 4, RTB_KAT_SLAB = 5, RTB_KAT_SAMPLE_LI = 6 };
+RTB_API int rtb_kat_eval(rtb_context *ctx, int32_t which, const float *h_in, int64_t n, float *h_out);
 
 /* ---- host-side scene I/O and procedural scenes (host C++, no GPU work) ---- */
 typedef struct rtb_host_scene rtb_host_scene; /* owns the arrays a rtb_scene_desc points to */

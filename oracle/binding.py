@@ -51,6 +51,11 @@ class Oracle:
                               f, no, wi, C.byref(pdf))
         return np.array(list(f)), np.array(list(no)), np.array(list(wi)), pdf.value
 
+    def sample_li_area(self, verts9, p, u1, u2):
+        wi = (C.c_float * 3)(); t = C.c_float(); pdf = C.c_float()
+        self.lib.orc_sample_li_area((C.c_float * 9)(*verts9), (C.c_float * 3)(*p), C.c_float(u1), C.c_float(u2), wi, C.byref(t), C.byref(pdf))
+        return np.array(list(wi), np.float32), t.value, pdf.value
+
     def camera_look_at(self, cam_struct_type, lookfrom, lookat, up, vfov, aspect):
         cam = cam_struct_type()
         self.lib.orc_camera_look_at((C.c_float * 3)(*lookfrom), (C.c_float * 3)(*lookat), (C.c_float * 3)(*up),

@@ -650,6 +650,20 @@ ORC_API void orc_sample_f(const rtb_material *m, const float wo[3], const float 
     Vec3 r = sample_f(*m, V(wo[0], wo[1], wo[2]), u1, u2, n, w, *pdf);
     f[0] = r.x; f[1] = r.y; f[2] = r.z; n_out[0] = n.x; n_out[1] = n.y; n_out[2] = n.z; wi[0] = w.x; wi[1] = w.y; wi[2] = w.z;
 }
+// Light::sample_Li for an area light (light.cuh:38-46 with Triangle::sample_p / area, triangle.cuh:78-86): the same
+// statements as in trace_path above, on a triangle given by its vertices
+ORC_API void orc_sample_li_area(const float v[9], const float p[3], float u1, float u2, float wi[3], float *t, float *pdf) {
+    Triangle lt(V(v[0], v[1], v[2]), V(v[3], v[4], v[5]), V(v[6], v[7], v[8]));
+    const Vec3 P = V(p[0], p[1], p[2]);
+    float area = 0.5f * length_dev(lt.n);
+    float a = sqrtf(u1);
+    Vec3 q = lt.p(1.f - a, u2 * a);
+    Vec3 w = q - P;
+    *t = length_dev(w);
+    Vec3 wiL = w * (1.f / *t);
+    *pdf = (1.f / area) * (dot_dev(w, w) / fabsf(dot_dev(unit_dev(lt.n), wiL)));
+    wi[0] = wiL.x; wi[1] = wiL.y; wi[2] = wiL.z;
+}
 ORC_API void orc_rand4(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t block, float out[4]) {
     R4 r = rand4(seed, pixel, sample, block);
     out[0] = r.a; out[1] = r.b; out[2] = r.c; out[3] = r.d;

@@ -18,7 +18,7 @@ RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2, RTB_SCENE_S1_GLOSSY = 1, 2, 3, 4
 RTB_MATTE, RTB_MIRROR, RTB_GLASS, RTB_GLOSSY = 0, 1, 2, 3
 RTB_RENDER_PIXEL_CENTRE, RTB_RENDER_NO_SHADOW, RTB_RENDER_NONPERSISTENT, RTB_RENDER_COUNT_WORK = 1, 2, 4, 8
 RTB_RENDER_SINGLE_PIPELINE = 16
-RTB_RENDER_TRUE_MIS, RTB_RENDER_RR_TERMINATE = 32, 64
+RTB_RENDER_TRUE_MIS, RTB_RENDER_RR_TERMINATE, RTB_RENDER_DETERMINISTIC = 32, 64, 128
 
 
 class Material(C.Structure):
@@ -67,7 +67,7 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_bounces", C.c_int32),
                 ("rr_start", C.c_int32), ("rr_threshold", C.c_float), ("seed", C.c_uint32),
                 ("first_sample", C.c_int32), ("total_spp", C.c_int32), ("pool_size", C.c_int32),
-                ("flags", C.c_int32), ("_reserved", C.c_int32), ("env_L", C.c_float * 3), ("_reserved2", C.c_int32)]
+                ("flags", C.c_int32), ("device_mask", C.c_uint32), ("env_L", C.c_float * 3), ("_reserved2", C.c_int32)]
 
 
 class RenderStats(C.Structure):
@@ -92,7 +92,11 @@ SYMBOLS = [
     "rtb_mesh_save_bin", "rtb_free", "rtb_host_scene_build", "rtb_host_scene_desc", "rtb_host_scene_camera",
     "rtb_host_scene_destroy", "rtb_scene_desc_save", "rtb_host_scene_load", "rtb_write_ppm",
     "rtb_scene_create_instanced", "rtb_host_scene_build_instanced", "rtb_host_scene_instanced_desc", "rtb_instanced_flatten",
+    "rtb_trace_wavefront", "rtb_kat_eval", "rtb_context_set_option", "rtb_context_get_option",
+    "rtb_render_accumulate_fixed", "rtb_tonemap_fixed_device",
 ]
+RTB_KAT_TRI_INTERSECT, RTB_KAT_OFFSET_ORIGIN, RTB_KAT_RAND4, RTB_KAT_SAMPLE_F, RTB_KAT_SLAB, RTB_KAT_SAMPLE_LI = 1, 2, 3, 4, 5, 6
+KAT_FLOATS = {1: (16, 4), 2: (6, 3), 3: (4, 4), 4: (16, 12), 5: (20, 1), 6: (16, 8)}  # floats per record: (in, out)
 
 
 class RtbError(RuntimeError):
@@ -221,9 +225,29 @@ class Context:
         """desc: SceneDesc (flat) or InstancedSceneDesc (two-level BVH)"""
         return Scene(self, desc, build_params)
 
+    def set_option(self, name, value):
+        self.L.check(self.L.lib.rtb_context_set_option(self.h, name.encode(), C.c_int64(value)))
+
+    def get_option(self, name):
+        v = C.c_int64()
+        self.L.check(self.L.lib.rtb_context_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def kat(self, which, records):
+        """evaluate one device function per record (rtb_kat_eval); records: float32 [n, KAT_FLOATS[which][0]]"""
+        ni, no = KAT_FLOATS[which]
+        a = np.ascontiguousarray(records, dtype=np.float32).reshape(-1, ni)
+        out = np.zeros((len(a), no), np.float32)
+        self.L.check(self.L.lib.rtb_kat_eval(self.h, which, a.ctypes.data_as(C.c_void_p), C.c_int64(len(a)), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def tonemap_device(self, d_accum_ptr, num_floats, total_spp, d_out_ptr):
         self.L.check(self.L.lib.rtb_tonemap_device(self.h, C.c_void_p(d_accum_ptr), C.c_int64(num_floats),
                                                    total_spp, C.c_void_p(d_out_ptr)))
+
+    def tonemap_fixed_device(self, d_accum_fixed_ptr, num_values, total_spp, d_out_ptr):
+        self.L.check(self.L.lib.rtb_tonemap_fixed_device(self.h, C.c_void_p(d_accum_fixed_ptr), C.c_int64(num_values),
+                                                         total_spp, C.c_void_p(d_out_ptr)))
 
     def __del__(self):
         try:
@@ -275,6 +299,27 @@ class Scene:
                                               occ.ctypes.data_as(C.c_void_p)))
         return occ
 
+    def trace_wavefront(self, rays=None, shadow_rays=None, excluded=None):
+        """closest hits / occlusion through the render path's persistent kernel (rtb_trace_wavefront);
+        returns (hits or None, occluded or None, trace launches)"""
+        n = ns = 0
+        pr = ph = ps = pe = po = None
+        hits = occ = None
+        if rays is not None and len(rays):
+            rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE); n = len(rays)
+            hits = np.zeros(n, dtype=HIT_DTYPE)
+            pr, ph = rays.ctypes.data_as(C.c_void_p), hits.ctypes.data_as(C.c_void_p)
+        if shadow_rays is not None and len(shadow_rays):
+            shadow_rays = np.ascontiguousarray(shadow_rays, dtype=RAY_DTYPE); ns = len(shadow_rays)
+            occ = np.zeros(ns, dtype=np.uint8)
+            ps, po = shadow_rays.ctypes.data_as(C.c_void_p), occ.ctypes.data_as(C.c_void_p)
+            if excluded is not None:
+                excluded = np.ascontiguousarray(excluded, dtype=np.int32)
+                pe = excluded.ctypes.data_as(C.c_void_p)
+        launches = C.c_int32()
+        self.L.check(self.L.lib.rtb_trace_wavefront(self.h, pr, C.c_int64(n), ph, ps, pe, C.c_int64(ns), po, C.byref(launches)))
+        return hits, occ, launches.value
+
     def trace_counts(self, rays):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         a, b = C.c_double(), C.c_double()
@@ -301,6 +346,13 @@ class Scene:
         st = RenderStats()
         self.L.check(self.L.lib.rtb_render_accumulate(self.h, C.byref(cam), C.byref(params),
                                                       C.c_void_p(d_accum_ptr), C.byref(st)))
+        return st
+
+    def render_accumulate_fixed(self, cam, params, d_accum_fixed_ptr):
+        """adds this call's fixed-point radiance sums into the int64[3*W*H] device buffer at d_accum_fixed_ptr"""
+        st = RenderStats()
+        self.L.check(self.L.lib.rtb_render_accumulate_fixed(self.h, C.byref(cam), C.byref(params),
+                                                            C.c_void_p(d_accum_fixed_ptr), C.byref(st)))
         return st
 
     def close(self):

@@ -171,6 +171,58 @@ int rtb_trace_any(rtb_scene *s, const rtb_ray *h_rays, const int32_t *h_excluded
         if (rc != RTB_OK) throw rtb::Error(rc, rtb_last_error());
     });
 }
+int rtb_trace_wavefront(rtb_scene *s, const rtb_ray *h_rays, int64_t n, rtb_hit *h_hits, const rtb_ray *h_srays,
+                        const int32_t *h_excluded, int64_t ns, uint8_t *h_occ, int32_t *launches) {
+    if (!s || n < 0 || ns < 0 || (n && (!h_rays || !h_hits)) || (ns && (!h_srays || !h_occ)) || n > 0x7fffff00 || ns > 0x7fffff00)
+        return rtb::set_error(RTB_ERR_INVALID, "rtb_trace_wavefront: bad arguments");
+    if (launches) *launches = 0;
+    if (n == 0 && ns == 0) return RTB_OK;
+    if (h_excluded)
+        for (int64_t i = 0; i < ns; ++i)
+            if (h_excluded[i] >= s->impl->n_flat) return rtb::set_error(RTB_ERR_INVALID, "excluded triangle out of range");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = s->ctx->be;
+        be.make_current();
+        rtb::DeviceBuf<RTB_BACKEND, rtb_ray> dr(be, (size_t)n), ds(be, (size_t)ns);
+        rtb::DeviceBuf<RTB_BACKEND, rtb_hit> dh(be, (size_t)n);
+        rtb::DeviceBuf<RTB_BACKEND, uint8_t> docc(be, (size_t)ns);
+        rtb::DeviceBuf<RTB_BACKEND, int32_t> dex(be, h_excluded ? (size_t)ns : 0);
+        if (n) be.upload(dr.p, h_rays, (size_t)n);
+        if (ns) be.upload(ds.p, h_srays, (size_t)ns);
+        if (h_excluded && ns) be.upload(dex.p, h_excluded, (size_t)ns);
+        rtb::trace_wavefront(be, *s->impl, dr.p, n, dh.p, ds.p, h_excluded ? dex.p : nullptr, ns, docc.p, launches);
+        if (n) be.download(h_hits, dh.p, (size_t)n);
+        if (ns) be.download(h_occ, docc.p, (size_t)ns);
+    });
+}
+int rtb_kat_eval(rtb_context *ctx, int32_t which, const float *h_in, int64_t n, float *h_out) {
+    if (!ctx || which < 1 || which > 6 || n < 0 || n > (1 << 26) || (n && (!h_in || !h_out))) return rtb::set_error(RTB_ERR_INVALID, "rtb_kat_eval: bad arguments");
+    if (n == 0) return RTB_OK;
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = ctx->be;
+        be.make_current();
+        const size_t ni = (size_t)n * rtb::kat_in_floats(which), no = (size_t)n * rtb::kat_out_floats(which);
+        rtb::DeviceBuf<RTB_BACKEND, float> din(be, ni), dout(be, no);
+        be.upload(din.p, h_in, ni);
+        rtb::KatK k; k.which = which; k.in = din.p; k.out = dout.p; k.n = n;
+        be.launch((int)n, k);
+        be.download(h_out, dout.p, no);
+    });
+}
+int rtb_context_set_option(rtb_context *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return rtb::set_error(RTB_ERR_INVALID, "rtb_context_set_option: null argument");
+    return rtb::guarded([&] {
+        if (!ctx->be.set_option(name, (long long)value))
+            throw rtb::Error(RTB_ERR_INVALID, std::string("rtb_context_set_option: unknown option or value out of range: ") + name);
+    });
+}
+int rtb_context_get_option(const rtb_context *ctx, const char *name, int64_t *value) {
+    if (!ctx || !name || !value) return rtb::set_error(RTB_ERR_INVALID, "rtb_context_get_option: null argument");
+    long long v = 0;
+    if (!ctx->be.get_option(name, v)) return rtb::set_error(RTB_ERR_INVALID, "rtb_context_get_option: unknown option");
+    *value = v;
+    return RTB_OK;
+}
 int rtb_trace_closest_counts(rtb_scene *s, const rtb_ray *h_rays, int64_t n, double *nodes_per_ray, double *tris_per_ray) {
     if (!s || n <= 0 || !h_rays || n > 0x7fffffff) return rtb::set_error(RTB_ERR_INVALID, "rtb_trace_closest_counts: bad arguments");
     return rtb::guarded([&] {
@@ -229,10 +281,19 @@ int rtb_render_aovs(rtb_scene *s, const rtb_camera *cam, int32_t w, int32_t h, f
 }
 
 int rtb_render_accumulate(rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, float *d_accum, rtb_render_stats *stats) {
-    if (!s || !cam || !p) return rtb::set_error(RTB_ERR_INVALID, "rtb_render_accumulate: null argument");
+    if (!s || !cam || !p || !d_accum) return rtb::set_error(RTB_ERR_INVALID, "rtb_render_accumulate: null argument");
     return rtb::guarded([&] {
         s->ctx->be.make_current();
-        rtb::render_accumulate(s->ctx->be, *s->impl, *cam, *p, d_accum, stats);
+        rtb::RenderTarget t; t.add_f32 = d_accum;
+        rtb::render_accumulate(s->ctx->be, *s->impl, *cam, *p, t, stats);
+    });
+}
+int rtb_render_accumulate_fixed(rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, int64_t *d_accum, rtb_render_stats *stats) {
+    if (!s || !cam || !p || !d_accum) return rtb::set_error(RTB_ERR_INVALID, "rtb_render_accumulate_fixed: null argument");
+    return rtb::guarded([&] {
+        s->ctx->be.make_current();
+        rtb::RenderTarget t; t.add_fixed = (long long *)d_accum;
+        rtb::render_accumulate(s->ctx->be, *s->impl, *cam, *p, t, stats);
     });
 }
 int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t n, int32_t total_spp, float *d_out) {
@@ -243,6 +304,14 @@ int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t n, int32_
         ctx->be.sync();
     });
 }
+int rtb_tonemap_fixed_device(rtb_context *ctx, const int64_t *d_accum, int64_t n, int32_t total_spp, float *d_out) {
+    if (!ctx || !d_accum || !d_out) return rtb::set_error(RTB_ERR_INVALID, "rtb_tonemap_fixed_device: null argument");
+    return rtb::guarded([&] {
+        ctx->be.make_current();
+        rtb::tonemap_fixed(ctx->be, (const long long *)d_accum, n, total_spp, d_out);
+        ctx->be.sync();
+    });
+}
 int rtb_render(rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, float *h_rgb, rtb_render_stats *stats) {
     if (!s || !cam || !p || !h_rgb) return rtb::set_error(RTB_ERR_INVALID, "rtb_render: null argument");
     return rtb::guarded([&] {
@@ -250,16 +319,16 @@ int rtb_render(rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, 
         be.make_current();
         auto &sc = *s->impl;
         const int64_t nf = 3 * (int64_t)p->width * (int64_t)p->height;
-        if (nf <= 0) throw rtb::Error(RTB_ERR_INVALID, "rtb_render: bad image size");
-        if (sc.own_accum_floats != nf) {
-            be.free(sc.own_accum);
-            sc.own_accum = be.template alloc<float>((size_t)nf);
-            sc.own_accum_floats = nf;
+        if (p->width <= 0 || p->height <= 0 || nf > 0x7fffff00ll) throw rtb::Error(RTB_ERR_INVALID, "rtb_render: bad image size");
+        if (sc.own_out_floats != nf) {
+            be.free(sc.own_out);
+            sc.own_out = nullptr; sc.own_out_floats = 0;
+            sc.own_out = be.template alloc<float>((size_t)nf);
+            sc.own_out_floats = nf;
         }
-        be.zero(sc.own_accum, (size_t)nf);  // init_framebuffer, render.cuh:61-66
-        rtb::render_accumulate(be, sc, *cam, *p, sc.own_accum, stats);
-        rtb::tonemap(be, sc.own_accum, nf, p->total_spp > 0 ? p->total_spp : p->spp, sc.own_accum);
-        be.download(h_rgb, sc.own_accum, (size_t)nf);  // render.cuh:455-456
+        rtb::RenderTarget t; t.tonemap_to = sc.own_out; t.tonemap_spp = p->total_spp > 0 ? p->total_spp : p->spp;
+        rtb::render_accumulate(be, sc, *cam, *p, t, stats);
+        be.download(h_rgb, sc.own_out, (size_t)nf);  // render.cuh:455-456
     });
 }
 

@@ -22,6 +22,7 @@
 //   k_for<Functor>        one thread per element for builder / utility bodies
 #include <cuda_runtime.h>
 
+#include <cctype>
 #include <cstdlib>
 
 #include <cub/block/block_scan.cuh>
@@ -243,7 +244,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
             if (ANY) {
                 if (!T.found) {  // ah, render.cuh:278-294: unoccluded -> splat
                     const V3 L = v3(fw.x, fw.y, fw.z);
-                    if (finite3(L)) accum_add(W.accum, __float_as_uint(fw.w), L);
+                    if (finite3(L)) accum_add(W, __float_as_uint(fw.w), L);
                 }
             } else if (T.hit.tri < 0) {
                 if (W.has_env) extend_miss(W, __float_as_uint(ws.ro[lane].w), v3(fw.x, fw.y, fw.z));
@@ -416,10 +417,9 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSm) k_trace_smem_s
     __syncwarp();
     persistent_trace<true, false, false, HybridStack<kSmemStack>>(ws, W, S, tune, &sstack[0][threadIdx.x]);
 }
-static int g_smem_stack = 0;  // RTB_SMEM_STACK (A/B)
 template <int WHICH>
-static void launch_trace_kernel(int grid, cudaStream_t st, bool pooled, const WaveState &W, const SceneView &S, const FetchTuning &tune) {
-    if (WHICH == 3 && g_smem_stack && !S.bvh.inst && !pooled) { k_trace_smem_stack<<<grid, kTraceBlock, 0, st>>>(W, S, tune); return; }
+static void launch_trace_kernel(int grid, cudaStream_t st, bool pooled, bool smem_stack, const WaveState &W, const SceneView &S, const FetchTuning &tune) {
+    if (WHICH == 3 && smem_stack && !S.bvh.inst && !pooled) { k_trace_smem_stack<<<grid, kTraceBlock, 0, st>>>(W, S, tune); return; }
     if (S.bvh.inst) {  // two-level scene: stepped schedule, two triangles per step
         k_trace<WHICH, false, true><<<grid, kTraceBlock, 0, st>>>(W, S, tune);
     } else if (pooled) k_trace<WHICH, true><<<grid, kTraceBlock, 0, st>>>(W, S, tune);
@@ -491,7 +491,8 @@ struct CudaBackend {
     int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
     FetchTuning tune_{24, 128, 1, 2};  // RTB_REFILL / RTB_CHUNK / RTB_PREFETCH override (tuning runs)
     int pooled_ = 0;  // RTB_POOLED: pooled triangle tests (1), each ray's lane on its own (0, default), by scene size (-1)
-    int fused_ = 1;   // RTB_FUSED: extend + shadow rays of one iteration in one launch
+    int fused_ = 1;   // "fused": extend + shadow rays of one iteration in one launch
+    int smem_stack_ = 0;  // "smem_stack": first stack entries in shared memory (A/B, k_trace_smem_stack)
     int pool_ = 1 << 25;    // default path pool, RTB_POOL overrides (tuning)
     int ploc_tail_off_ = 0; // RTB_PLOC_TAIL=0: every PLOC round its own launches (A/B)
 
@@ -522,20 +523,18 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaHostAlloc((void **)&h_done_, kMaxPipelines * sizeof(int32_t), cudaHostAllocMapped));
         RTB_CUDA_CHECK(cudaHostGetDevicePointer((void **)&d_done_, h_done_, 0));
         for (int k = 0; k < kMaxPipelines; ++k) h_done_[k] = 0;
-        if (const char *e = getenv("RTB_PIPELINES")) { int v = atoi(e); if (v >= 1 && v <= kMaxPipelines) pipelines_ = v; }
-        if (const char *e = getenv("RTB_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tune_.refill = v; }
-        if (const char *e = getenv("RTB_CHUNK")) { int v = atoi(e); if (v >= 32) tune_.chunk = v; }
-        if (const char *e = getenv("RTB_PREFETCH")) tune_.prefetch = atoi(e);
-        if (const char *e = getenv("RTB_TRI_STEP")) tune_.tri_step = atoi(e);
-        if (const char *e = getenv("RTB_POOLED")) pooled_ = atoi(e);
-        if (const char *e = getenv("RTB_FUSED")) fused_ = atoi(e);
-        if (const char *e = getenv("RTB_SMEM_STACK")) g_smem_stack = atoi(e);
-        if (const char *e = getenv("RTB_PLOC_TAIL")) ploc_tail_off_ = atoi(e) == 0;
-        if (const char *e = getenv("RTB_POOL")) { int v = atoi(e); if (v >= 1024) pool_ = v; }
         int per_sm = 0;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<3, true>, kTraceBlock, 0));
         trace_blocks_per_sm_ = per_sm > 0 ? per_sm : 1;
-        if (const char *e = getenv("RTB_TRACE_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= trace_blocks_per_sm_) trace_cap_ = v; }  // (A/B)
+        // tuning runs (tools/sweep.py) may preset the options of rtb_context_set_option through the environment:
+        // RTB_<NAME IN CAPITALS>=value, read once here; the ABI call is the documented way
+        static const char *const names[] = {"refill", "chunk", "prefetch", "tri_step", "pooled", "fused", "smem_stack", "pipelines", "pool",
+                                            "ploc_tail", "trace_blocks"};
+        for (const char *nm : names) {
+            std::string env = "RTB_";
+            for (const char *c = nm; *c; ++c) env += (char)toupper((unsigned char)*c);
+            if (const char *e = getenv(env.c_str())) set_option(nm, atoll(e));
+        }
         blocks_trace_ = num_sms_ * trace_blocks_per_sm_;
         RTB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate, kBlock, 0));
         blocks_generate_ = num_sms_ * (per_sm > 0 ? per_sm : 1);
@@ -554,6 +553,38 @@ struct CudaBackend {
     CudaBackend(const CudaBackend &) = delete;
     CudaBackend &operator=(const CudaBackend &) = delete;
 
+    // rtb_context_set_option / rtb_context_get_option (include/rtb.h lists the names)
+    bool set_option(const std::string &name, long long v) {
+        auto in = [&](long long lo, long long hi) { return v >= lo && v <= hi; };
+        if (name == "refill") { if (!in(1, 32)) return false; tune_.refill = (int)v; }
+        else if (name == "chunk") { if (!in(32, 1 << 20)) return false; tune_.chunk = (int)v; }
+        else if (name == "prefetch") { if (!in(0, 1)) return false; tune_.prefetch = (int)v; }
+        else if (name == "tri_step") { if (!in(0, 4)) return false; tune_.tri_step = (int)v; }
+        else if (name == "pooled") { if (!in(-1, 1)) return false; pooled_ = (int)v; }
+        else if (name == "fused") { if (!in(0, 1)) return false; fused_ = (int)v; }
+        else if (name == "smem_stack") { if (!in(0, 1)) return false; smem_stack_ = (int)v; }
+        else if (name == "pipelines") { if (!in(0, kMaxPipelines)) return false; pipelines_ = (int)v; }
+        else if (name == "pool") { if (!in(1024, 1ll << 30)) return false; pool_ = (int)v; }
+        else if (name == "ploc_tail") { if (!in(0, 1)) return false; ploc_tail_off_ = v == 0; }
+        else if (name == "trace_blocks") { if (!in(0, trace_blocks_per_sm_)) return false; trace_cap_ = (int)v; }
+        else return false;
+        return true;
+    }
+    bool get_option(const std::string &name, long long &v) const {
+        if (name == "refill") v = tune_.refill;
+        else if (name == "chunk") v = tune_.chunk;
+        else if (name == "prefetch") v = tune_.prefetch;
+        else if (name == "tri_step") v = tune_.tri_step;
+        else if (name == "pooled") v = pooled_;
+        else if (name == "fused") v = fused_;
+        else if (name == "smem_stack") v = smem_stack_;
+        else if (name == "pipelines") v = pipelines_;
+        else if (name == "pool") v = pool_;
+        else if (name == "ploc_tail") v = ploc_tail_off_ ? 0 : 1;
+        else if (name == "trace_blocks") v = trace_cap_;
+        else return false;
+        return true;
+    }
     int device() const { return dev_; }
     void make_current() { RTB_CUDA_CHECK(cudaSetDevice(dev_)); }
     void sync() { RTB_CUDA_CHECK(cudaStreamSynchronize(stream_)); }
@@ -626,20 +657,20 @@ struct CudaBackend {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_extend_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
         else if (mode == 1) k_extend_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else launch_trace_kernel<1>(trace_grid(S), stream_, use_pooled(S), W, S, tune_);
+        else launch_trace_kernel<1>(trace_grid(S), stream_, use_pooled(S), smem_stack_ != 0, W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     void shadow(const WaveState &W, const SceneView &S, int mode) {
         const int flat_grid = (W.pool + kBlock - 1) / kBlock;
         if (mode == 2) k_shadow_flat<true><<<flat_grid, kBlock, 0, stream_>>>(W, S);
         else if (mode == 1) k_shadow_flat<false><<<flat_grid, kBlock, 0, stream_>>>(W, S);
-        else launch_trace_kernel<2>(trace_grid(S), stream_, use_pooled(S), W, S, tune_);
+        else launch_trace_kernel<2>(trace_grid(S), stream_, use_pooled(S), smem_stack_ != 0, W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
     }
     // both ray types in one launch; false = not available in this mode
     bool trace_fused(const WaveState &W, const SceneView &S, int mode) {
         if (mode != 0 || !fused_) return false;
-        launch_trace_kernel<3>(trace_grid(S), stream_, use_pooled(S), W, S, tune_);
+        launch_trace_kernel<3>(trace_grid(S), stream_, use_pooled(S), smem_stack_ != 0, W, S, tune_);
         RTB_CUDA_CHECK(cudaGetLastError());
         return true;
     }

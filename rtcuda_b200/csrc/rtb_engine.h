@@ -26,6 +26,17 @@ struct Error : std::runtime_error {
     Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
 };
 
+// device temporary that is freed on every path out of its scope (an exception included)
+template <class BE, class T>
+struct DeviceBuf {
+    BE &be; T *p;
+    DeviceBuf(BE &b, size_t n) : be(b), p(n ? b.template alloc<T>(n) : nullptr) {}
+    ~DeviceBuf() { be.free(p); }
+    DeviceBuf(const DeviceBuf &) = delete;
+    DeviceBuf &operator=(const DeviceBuf &) = delete;
+    T *release() { T *q = p; p = nullptr; return q; }
+};
+
 // ---- kernel functors (named types => readable kernel names in ncu) ----
 struct PrimSetupK { PrimSetupArgs a; RTB_HD void operator()(int i) const { prim_setup_body(a, i); } };
 struct MortonK { MortonArgs a; RTB_HD void operator()(int i) const { morton_body(a, i); } };
@@ -67,6 +78,46 @@ struct ShadeK { WaveState W; SceneView S; RenderConsts rc; int type; bool shadow
 struct TonemapK {  // post_process_framebuffer, render.cuh:330-338
     const float *in; float *out; int64_t n; float inv_spp;
     RTB_HD void operator()(int i) const { if (i < n) out[i] = fsqrt(fmul(in[i], inv_spp)); }
+};
+// what a render leaves behind: SceneT::accum (one F4 per pixel) or, in deterministic mode, SceneT::accum_fx (three
+// fixed-point sums per pixel); these fold it into the caller's buffers / tonemap it
+struct FoldF32K {  // caller's float[3 * pixels] += sums
+    const F4 *in; const unsigned long long *in_fx; float *out; int64_t pixels;
+    RTB_HD void operator()(int i) const {
+        if (i >= pixels) return;
+        float *o = out + 3 * (size_t)i;
+        if (in_fx) {
+            const unsigned long long *f = in_fx + 3 * (size_t)i;
+            o[0] = fadd(o[0], from_fixed((long long)f[0])); o[1] = fadd(o[1], from_fixed((long long)f[1])); o[2] = fadd(o[2], from_fixed((long long)f[2]));
+        } else {
+            const F4 a = in[i];
+            o[0] = fadd(o[0], a.x); o[1] = fadd(o[1], a.y); o[2] = fadd(o[2], a.z);
+        }
+    }
+};
+struct FoldFixedK {  // caller's int64[3 * pixels] += fixed-point sums
+    const unsigned long long *in_fx; long long *out; int64_t n;
+    RTB_HD void operator()(int i) const { if (i < n) out[i] = (long long)((unsigned long long)out[i] + in_fx[i]); }
+};
+struct TonemapAccumK {  // post_process_framebuffer, render.cuh:330-338, straight from the sums
+    const F4 *in; const unsigned long long *in_fx; float *out; int64_t pixels; float inv_spp;
+    RTB_HD void operator()(int i) const {
+        if (i >= pixels) return;
+        float r, g, b;
+        if (in_fx) {
+            const unsigned long long *f = in_fx + 3 * (size_t)i;
+            r = from_fixed((long long)f[0]); g = from_fixed((long long)f[1]); b = from_fixed((long long)f[2]);
+        } else {
+            const F4 a = in[i];
+            r = a.x; g = a.y; b = a.z;
+        }
+        float *o = out + 3 * (size_t)i;
+        o[0] = fsqrt(fmul(r, inv_spp)); o[1] = fsqrt(fmul(g, inv_spp)); o[2] = fsqrt(fmul(b, inv_spp));
+    }
+};
+struct TonemapFixedK {  // the same from a caller's int64[n] buffer of fixed-point sums (after a reduction over GPUs)
+    const long long *in; float *out; int64_t n; float inv_spp;
+    RTB_HD void operator()(int i) const { if (i < n) out[i] = fsqrt(fmul(from_fixed(in[i]), inv_spp)); }
 };
 RTB_HD bool ray_is_finite(const rtb_ray &r) {
     return finite3(v3(r.origin[0], r.origin[1], r.origin[2])) && finite3(v3(r.dir[0], r.dir[1], r.dir[2]));
@@ -123,6 +174,54 @@ struct TraceAnyK {
     }
 };
 
+// known-answer hooks (rtb_kat_eval): the device functions of the render path, one record per thread.  Record
+// layouts (floats; integers travel as their bits) are given in include/rtb.h.
+RTB_HD int kat_in_floats(int which) { return which == 1 ? 16 : which == 2 ? 6 : which == 3 ? 4 : which == 4 ? 16 : which == 5 ? 20 : which == 6 ? 16 : 0; }
+RTB_HD int kat_out_floats(int which) { return which == 1 ? 4 : which == 2 ? 3 : which == 3 ? 4 : which == 4 ? 12 : which == 5 ? 1 : which == 6 ? 8 : 0; }
+struct KatK {
+    int32_t which; const float *in; float *out; int64_t n;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        const float *a = in + (size_t)i * kat_in_floats(which);
+        float *o = out + (size_t)i * kat_out_floats(which);
+        if (which == RTB_KAT_TRI_INTERSECT) {  // Triangle(p0,p1,p2) + Triangle::intersect, triangle.cuh:4-58
+            const Tri48 tr = tri_from_vertices(v3(a[0], a[1], a[2]), v3(a[3], a[4], a[5]), v3(a[6], a[7], a[8]));
+            float t = 0.f, u = 0.f, v = 0.f;
+            const bool hit = tri_intersect(tr, v3(a[9], a[10], a[11]), v3(a[12], a[13], a[14]), a[15], t, u, v);
+            o[0] = hit ? 1.f : 0.f; o[1] = t; o[2] = u; o[3] = v;
+        } else if (which == RTB_KAT_OFFSET_ORIGIN) {  // offset_ray_origin, utility.cuh:31-47
+            const V3 r = offset_ray_origin(v3(a[0], a[1], a[2]), v3(a[3], a[4], a[5]));
+            o[0] = r.x; o[1] = r.y; o[2] = r.z;
+        } else if (which == RTB_KAT_RAND4) {  // the counter-based generator that replaces curand_uniform, render.cuh:68-73
+            const Rand4 r = rand4(f2u(a[0]), f2u(a[1]), f2u(a[2]), f2u(a[3]));
+            o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
+        } else if (which == RTB_KAT_SAMPLE_F) {  // Material::sample_f, material.cuh:60-109
+            rtb_material m;
+            m.albedo[0] = a[0]; m.albedo[1] = a[1]; m.albedo[2] = a[2]; m.ior = a[3]; m.type = f2i(a[4]);
+            const BsdfSample s = sample_f(m, v3(a[5], a[6], a[7]), v3(a[8], a[9], a[10]), a[11], a[12]);
+            o[0] = s.f.x; o[1] = s.f.y; o[2] = s.f.z; o[3] = s.n.x; o[4] = s.n.y; o[5] = s.n.z;
+            o[6] = s.wi.x; o[7] = s.wi.y; o[8] = s.wi.z; o[9] = s.pdf; o[10] = 0.f; o[11] = 0.f;
+        } else if (which == RTB_KAT_SLAB) {  // one child box through the quantiser and the slab test of the 8-wide node
+            const V3 plo = v3(a[0], a[1], a[2]), phi = v3(a[3], a[4], a[5]);
+            const uint32_t ex = quant_exponent(fsub(phi.x, plo.x)), ey = quant_exponent(fsub(phi.y, plo.y)), ez = quant_exponent(fsub(phi.z, plo.z));
+            const uint32_t e255 = 0xffffff00u, e0 = 0u;
+            Q4 n0, n1, n2, n3, n4;
+            n0.x = f2u(plo.x); n0.y = f2u(plo.y); n0.z = f2u(plo.z); n0.w = ex | (ey << 8) | (ez << 16);
+            n1.x = 0u; n1.y = 0u; n1.z = (1u << 5); n1.w = 0u;  // slot 0: a leaf child with one triangle; the rest empty
+            n2.x = quant_lo(a[6], plo.x, ex) | e255; n2.y = 0xffffffffu; n2.z = quant_lo(a[7], plo.y, ey) | e255; n2.w = 0xffffffffu;
+            n3.x = quant_lo(a[8], plo.z, ez) | e255; n3.y = 0xffffffffu; n3.z = quant_hi(a[9], plo.x, ex) | e0; n3.w = 0u;
+            n4.x = quant_hi(a[10], plo.y, ey) | e0; n4.y = 0u; n4.z = quant_hi(a[11], plo.z, ez) | e0; n4.w = 0u;
+            const RaySetup r = ray_setup(v3(a[12], a[13], a[14]), v3(a[15], a[16], a[17]));
+            o[0] = (node_hitmask(n0, n1, n2, n3, n4, r, a[18]) & 0x00ffffffu) ? 1.f : 0.f;
+        } else if (which == RTB_KAT_SAMPLE_LI) {  // Light::sample_Li (area), light.cuh:38-46 with triangle.cuh:78-86
+            const Tri48 tr = tri_from_vertices(v3(a[0], a[1], a[2]), v3(a[3], a[4], a[5]), v3(a[6], a[7], a[8]));
+            LightDev l; l.type = RTB_AREA_LIGHT; l.px = l.py = l.pz = 0.f; l.tri = 0; l.Lx = l.Ly = l.Lz = 1.f;
+            const LightSample s = sample_Li_area(l, tr, v3(a[9], a[10], a[11]), a[12], a[13]);
+            o[0] = s.wi.x; o[1] = s.wi.y; o[2] = s.wi.z; o[3] = s.t; o[4] = s.pdf; o[5] = o[6] = o[7] = 0.f;
+        }
+    }
+};
+
 // primary-hit feature buffers (rtb_render_aovs)
 struct AovK {
     SceneView S; rtb_camera cam; int32_t width, height;
@@ -170,7 +269,13 @@ struct SceneT {
     // render() and never frees it, render.cuh:374-391)
     WaveState W[kMaxPipelines]{};
     int32_t pool = 0, pipes = 0;  // pool = queue entries PER pipeline
-    float *own_accum = nullptr; int64_t own_accum_floats = 0;
+    F4 *accum = nullptr; unsigned long long *accum_fx = nullptr; int64_t accum_pixels = 0;  // radiance sums of the last render
+    float *own_out = nullptr; int64_t own_out_floats = 0;  // rtb_render's tonemapped image before its copy to the host
+    void ensure_accum(int64_t pixels, bool fixed) {
+        if (accum_pixels != pixels) { be->free(accum); be->free(accum_fx); accum = nullptr; accum_fx = nullptr; accum_pixels = pixels; }
+        if (!fixed && !accum) accum = be->template alloc<F4>((size_t)pixels);
+        if (fixed && !accum_fx) accum_fx = be->template alloc<unsigned long long>(3 * (size_t)pixels);
+    }
 
     SceneView view() const {
         SceneView S;
@@ -209,7 +314,7 @@ struct SceneT {
     ~SceneT() {
         if (!be) return;
         free_wave();
-        be->free(own_accum);
+        be->free(accum); be->free(accum_fx); be->free(own_out);
         be->free(nodes8); be->free(tris); be->free(meta); be->free(prim); be->free(leaf_of_prim);
         be->free(materials); be->free(lights); be->free(inst); be->free(top_inst);
     }
@@ -776,11 +881,20 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
 // The CUDA backend launches each wavefront's trace kernel on an np-th of the SM (CudaBackend::trace_grid), so that one
 // wavefront's issue-bound traversal runs beside another's DRAM-bound shading instead of after it: four wavefronts on
 // scenes that fit L2 (C2 37.4 -> 35.0 ms, C4 37.6 -> 28.1 ms), two with full-size launches beyond.
+// where the radiance sums of a render go once the wavefronts have finished (inside the timed region of the call)
+struct RenderTarget {
+    float *add_f32 = nullptr;        // float[3 * W * H] += sums                       (rtb_render_accumulate)
+    long long *add_fixed = nullptr;  // int64[3 * W * H] += fixed-point sums           (rtb_render_accumulate_fixed)
+    float *tonemap_to = nullptr;     // float[3 * W * H] = sqrt(sums / tonemap_spp)    (rtb_render)
+    int32_t tonemap_spp = 0;
+};
 template <class BE>
-void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_render_params &p, float *d_accum,
+void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_render_params &p, const RenderTarget &target,
                        rtb_render_stats *stats) {
-    if (p.width <= 0 || p.height <= 0 || p.spp <= 0 || p.max_bounces < 0 || !d_accum)
+    if (p.width <= 0 || p.height <= 0 || p.spp <= 0 || p.max_bounces < 0 || !(target.add_f32 || target.add_fixed || target.tonemap_to))
         throw Error(RTB_ERR_INVALID, "rtb_render: bad parameters");
+    if (p.device_mask != 0 && be.device() >= 0 && !(p.device_mask >> be.device() & 1))
+        throw Error(RTB_ERR_INVALID, "rtb_render: device_mask excludes the GPU of this scene's context (use rtb_multi_render to span GPUs)");
     if (p.max_bounces > kMaxBounces) throw Error(RTB_ERR_INVALID, "rtb_render: max_bounces > 255");
     if (p.first_sample < 0 || (long long)p.first_sample + p.spp > kMaxSampleIndex) throw Error(RTB_ERR_INVALID, "rtb_render: sample index >= 2^24");
     const unsigned long long total = (unsigned long long)p.width * (unsigned long long)p.height * (unsigned long long)p.spp;
@@ -793,6 +907,10 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     if (np < 1 || mode != 0 || (p.flags & RTB_RENDER_SINGLE_PIPELINE) || pool_all < (1 << 16)) np = 1;
     const int pool = (int)(((pool_all + np - 1) / np + 31) & ~31ll);
     sc.ensure_wave(pool, np);
+    const bool fixed = (p.flags & RTB_RENDER_DETERMINISTIC) != 0 || target.add_fixed != nullptr;
+    const int64_t pixels = (int64_t)p.width * p.height;
+    if (3 * pixels > 0x7fffff00ll) throw Error(RTB_ERR_INVALID, "image too large");
+    sc.ensure_accum(pixels, fixed);
     const SceneView S = sc.view();
     const bool shadows = sc.num_lights > 0 && !(p.flags & RTB_RENDER_NO_SHADOW);
     WaveState W[kMaxPipelines];
@@ -800,13 +918,16 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     be.use_stream(0);  // (an error thrown out of an earlier call may have left another stream selected)
     be.begin_render(np);
     auto t0 = be.now();
+    if (fixed) be.zero(sc.accum_fx, 3 * (size_t)pixels);  // init_framebuffer, render.cuh:61-66
+    else be.zero(sc.accum, (size_t)pixels);
     for (int k = 0; k < np; ++k) {
         if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(2 * kNumMaterialTypes * (size_t)pool);
         W[k] = sc.W[k];
         if (!(p.flags & RTB_RENDER_TRUE_MIS)) W[k].mis = nullptr;
         W[k].env[0] = p.env_L[0]; W[k].env[1] = p.env_L[1]; W[k].env[2] = p.env_L[2];
         W[k].has_env = (p.env_L[0] != 0.f || p.env_L[1] != 0.f || p.env_L[2] != 0.f) ? 1 : 0;
-        W[k].accum = d_accum;
+        W[k].accum = fixed ? nullptr : sc.accum;
+        W[k].accum_fx = fixed ? sc.accum_fx : nullptr;
         W[k].host_done = be.done_flag_device(k);
         RenderConsts &r = rc[k];
         r.cam = cam; r.width = p.width; r.height = p.height; r.spp = p.spp; r.first_sample = p.first_sample;
@@ -867,6 +988,17 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     }
     be.use_stream(0);
     for (int k = 1; k < np; ++k) be.join(k);  // the main stream continues after stream k's work
+    if (target.add_f32) {
+        FoldF32K k; k.in = sc.accum; k.in_fx = fixed ? sc.accum_fx : nullptr; k.out = target.add_f32; k.pixels = pixels;
+        be.launch((int)pixels, k);
+    }
+    if (target.add_fixed) { FoldFixedK k; k.in_fx = sc.accum_fx; k.out = target.add_fixed; k.n = 3 * pixels; be.launch((int)(3 * pixels), k); }
+    if (target.tonemap_to) {  // post_process_framebuffer, render.cuh:330-338
+        if (target.tonemap_spp <= 0) throw Error(RTB_ERR_INVALID, "rtb_render: bad total_spp");
+        TonemapAccumK k; k.in = sc.accum; k.in_fx = fixed ? sc.accum_fx : nullptr; k.out = target.tonemap_to; k.pixels = pixels;
+        k.inv_spp = 1.0f / (float)target.tonemap_spp;
+        be.launch((int)pixels, k);
+    }
     auto t1 = be.now();
     be.wait(t1);
     for (int k = 0; k < np; ++k) for (auto &e : fences[k]) be.release(e);
@@ -902,10 +1034,139 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     }
 }
 
+// ---- the render path's traversal kernels on caller-supplied rays (rtb_trace_wavefront) ----
+// rtb_trace_closest / rtb_trace_any run one thread per ray (Traversal::step).  The render path does not: its rays sit
+// in the extend / shadow queues and are traversed by the persistent kernel (dynamic fetch, refill, stepped or pooled
+// triangle tests, finish words staged by cp.async, hit records appended per material type).  This entry loads the
+// caller's rays into those queues, runs ONE iteration's trace launch(es) exactly as render_accumulate does, and reads
+// the results back from where the render path leaves them: hit records out of the per-type hit queues (the ray index
+// travels in the pixel field, t in the `mis` side array), occlusion out of the accumulation buffer (an unoccluded
+// shadow ray splats radiance (1,0,0) at "pixel" = ray index).  So the kernel compared with the reference's
+// Bvh::traverse (bvh.cuh:251-357) by the parity tests is the one that renders.
+struct RayLoadK {
+    const rtb_ray *rays; WaveState W; int32_t first, n;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        const rtb_ray r = rays[first + i];
+        F4 a, b, c;
+        a.x = r.origin[0]; a.y = r.origin[1]; a.z = r.origin[2]; a.w = u2f((uint32_t)i);
+        b.x = r.dir[0]; b.y = r.dir[1]; b.z = r.dir[2]; b.w = u2f(0u);
+        c.x = c.y = c.z = 1.f; c.w = 0.f;
+        if (!ray_is_finite(r)) a.w = u2f(kHolePixel);  // retired before the queue in the render (shade_item): reported as a miss
+        W.ea[i] = a; W.eb[i] = b; W.ec[i] = c;
+    }
+};
+struct ShadowLoadK {
+    const rtb_ray *rays; const int32_t *excluded; const int32_t *leaf_of_prim; Bvh8View B; WaveState W; int32_t first, n;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        const rtb_ray r = rays[first + i];
+        int ex = excluded ? excluded[first + i] : -1;
+        if (ex >= 0) ex = leaf_of_prim[ex];
+        F4 o, d, l;
+        o.x = r.origin[0]; o.y = r.origin[1]; o.z = r.origin[2]; o.w = r.tmax;
+        d.x = r.dir[0]; d.y = r.dir[1]; d.z = r.dir[2]; d.w = i2f(ex);
+        l.x = 1.f; l.y = 0.f; l.z = 0.f; l.w = u2f((uint32_t)i);
+        // a hole (tmax = 0) leaves the "pixel" at 0 = reads as occluded: a non-finite ray or tmax <= 0 is reported
+        // unoccluded by TraceAnyK, so splat it here
+        if (!ray_is_finite(r) || !(r.tmax > 0.f)) { o.w = 0.f; accum_add(W, (uint32_t)i, v3(1.f, 0.f, 0.f)); }
+        W.sh_o[i] = o; W.sh_d[i] = d; W.sh_L[i] = l;
+    }
+};
+struct HitGatherK {
+    WaveState W; Bvh8View B; rtb_hit *hits; int32_t first, type, n;
+    RTB_HD void operator()(int j) const {
+        if (j >= n) return;
+        const size_t q = (size_t)type * W.pool + (size_t)j;
+        const F4 a = W.ma[q], c = W.mc[q];
+        const int tri = f2i(c.w);
+        rtb_hit h;
+        h.t = W.mis[2 * q + 1]; h.u = c.y; h.v = c.z;
+        h.prim = hit_prim(B, tri, W.hit_inst ? W.hit_inst[q] : -1);
+        hits[first + (int)f2u(a.w)] = h;
+    }
+};
+struct MissFillK {
+    rtb_hit *hits; int64_t n;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        rtb_hit h; h.t = 0.f; h.u = 0.f; h.v = 0.f; h.prim = -1;
+        hits[i] = h;
+    }
+};
+struct OccludedK {
+    const F4 *accum; uint8_t *occ; int32_t first, n;
+    RTB_HD void operator()(int i) const { if (i < n) occ[first + i] = accum[i].x == 0.f ? 1 : 0; }
+};
+template <class BE>
+void trace_wavefront(BE &be, SceneT<BE> &sc, const rtb_ray *d_rays, int64_t n, rtb_hit *d_hits, const rtb_ray *d_srays,
+                     const int32_t *d_excl, int64_t ns, uint8_t *d_occ, int32_t *launches_out) {
+    if (sc.inst && d_excl) throw Error(RTB_ERR_INVALID, "rtb_trace_wavefront: excluded triangles are not supported on instanced scenes");
+    const int64_t most = n > ns ? n : ns;
+    const int32_t cap = (int32_t)(((most < (1 << 22) ? most : (1 << 22)) + 31) & ~31ll);
+    if (cap == 0) return;
+    be.use_stream(0);
+    be.begin_render(1);
+    WaveState W{};
+    const SceneView S = sc.view();
+    int launches = 0;
+    try {
+        W.ea = be.template alloc<F4>(cap); W.eb = be.template alloc<F4>(cap); W.ec = be.template alloc<F4>(cap);
+        W.ma = be.template alloc<F4>(kNumMaterialTypes * (size_t)cap); W.mb = be.template alloc<F4>(kNumMaterialTypes * (size_t)cap);
+        W.mc = be.template alloc<F4>(kNumMaterialTypes * (size_t)cap);
+        W.sh_o = be.template alloc<F4>(cap); W.sh_d = be.template alloc<F4>(cap); W.sh_L = be.template alloc<F4>(cap);
+        W.c = be.template alloc<Counters>(1);
+        W.mis = be.template alloc<float>(2 * kNumMaterialTypes * (size_t)cap);
+        W.hit_inst = sc.inst ? be.template alloc<int32_t>(kNumMaterialTypes * (size_t)cap) : nullptr;
+        W.accum = be.template alloc<F4>((size_t)cap);
+        W.pool = cap;
+        if (n > 0) { MissFillK k; k.hits = d_hits; k.n = n; be.launch((int)n, k); }
+        for (int64_t first = 0; first < most; first += cap) {
+            const int32_t ne = (int32_t)(first < n ? (n - first < cap ? n - first : cap) : 0);
+            const int32_t nsh = (int32_t)(first < ns ? (ns - first < cap ? ns - first : cap) : 0);
+            be.zero(W.accum, (size_t)cap);
+            if (ne) { RayLoadK k; k.rays = d_rays; k.W = W; k.first = (int32_t)first; k.n = ne; be.launch(ne, k); }
+            if (nsh) {
+                ShadowLoadK k; k.rays = d_srays; k.excluded = d_excl; k.leaf_of_prim = sc.leaf_of_prim; k.B = S.bvh; k.W = W;
+                k.first = (int32_t)first; k.n = nsh;
+                be.launch(nsh, k);
+            }
+            Counters c0;
+            memset(&c0, 0, sizeof c0);
+            c0.n_extend = ne; c0.n_shadow = nsh;
+            be.upload(W.c, &c0, 1);
+            if (be.trace_fused(W, S, 0)) launches += 1;
+            else { be.extend(W, S, 0); be.shadow(W, S, 0); launches += 2; }
+            Counters c1;
+            be.download(&c1, W.c, 1);
+            for (int type = 0; type < kNumMaterialTypes; ++type) {
+                if (c1.n_mat[type] <= 0) continue;
+                HitGatherK k; k.W = W; k.B = S.bvh; k.hits = d_hits; k.first = (int32_t)first; k.type = type; k.n = c1.n_mat[type];
+                be.launch(k.n, k);
+            }
+            if (nsh) { OccludedK k; k.accum = W.accum; k.occ = d_occ; k.first = (int32_t)first; k.n = nsh; be.launch(nsh, k); }
+        }
+        be.sync();
+    } catch (...) {
+        be.free(W.ea); be.free(W.eb); be.free(W.ec); be.free(W.ma); be.free(W.mb); be.free(W.mc); be.free(W.sh_o); be.free(W.sh_d);
+        be.free(W.sh_L); be.free(W.c); be.free(W.mis); be.free(W.hit_inst); be.free(W.accum);
+        throw;
+    }
+    be.free(W.ea); be.free(W.eb); be.free(W.ec); be.free(W.ma); be.free(W.mb); be.free(W.mc); be.free(W.sh_o); be.free(W.sh_d);
+    be.free(W.sh_L); be.free(W.c); be.free(W.mis); be.free(W.hit_inst); be.free(W.accum);
+    if (launches_out) *launches_out = launches;
+}
+
 template <class BE>
 void tonemap(BE &be, const float *d_in, int64_t n, int total_spp, float *d_out) {
-    if (n <= 0 || total_spp <= 0) throw Error(RTB_ERR_INVALID, "rtb_tonemap: bad arguments");
+    if (n <= 0 || n > 0x7fffff00ll || total_spp <= 0) throw Error(RTB_ERR_INVALID, "rtb_tonemap: bad arguments");
     TonemapK k; k.in = d_in; k.out = d_out; k.n = n; k.inv_spp = 1.0f / (float)total_spp;
+    be.launch((int)n, k);
+}
+template <class BE>
+void tonemap_fixed(BE &be, const long long *d_in, int64_t n, int total_spp, float *d_out) {
+    if (n <= 0 || n > 0x7fffff00ll || total_spp <= 0) throw Error(RTB_ERR_INVALID, "rtb_tonemap_fixed: bad arguments");
+    TonemapFixedK k; k.in = d_in; k.out = d_out; k.n = n; k.inv_spp = 1.0f / (float)total_spp;
     be.launch((int)n, k);
 }
 

@@ -199,9 +199,11 @@ struct LightSample {
     float t, pdf;
 };
 // Light::sample_Li, light.cuh:29-48 with Triangle::sample_p / area, triangle.cuh:78-86
+// the area-light branch on a triangle record the caller holds (also evaluated on its own by rtb_kat_eval)
+RTB_HD LightSample sample_Li_area(const LightDev &l, const Tri48 &tr, V3 p, float u1, float u2);
 RTB_HD LightSample sample_Li(const LightDev &l, const Bvh8View &bvh, V3 p, float u1, float u2) {
-    LightSample s;
     if (l.type == RTB_POINT_LIGHT) {
+        LightSample s;
         V3 w = vsub(v3(l.px, l.py, l.pz), p);
         s.t = vlen(w);
         s.Li = vscale(v3(l.Lx, l.Ly, l.Lz), frcp(fmul(s.t, s.t)));
@@ -209,7 +211,10 @@ RTB_HD LightSample sample_Li(const LightDev &l, const Bvh8View &bvh, V3 p, float
         s.pdf = 1.f;
         return s;
     }
-    const Tri48 tr = load_tri(bvh.tris, l.tri);
+    return sample_Li_area(l, load_tri(bvh.tris, l.tri), p, u1, u2);
+}
+RTB_HD LightSample sample_Li_area(const LightDev &l, const Tri48 &tr, V3 p, float u1, float u2) {
+    LightSample s;
     V3 n = tri_n(tr);
     float area = fmul(0.5f, vlen(n));
     float pdf = frcp(area);

@@ -55,7 +55,10 @@ struct WaveState {
     F4 *sh_o, *sh_d, *sh_L;
     Counters *c;
     int32_t *host_done;  // mapped pinned host word (or null): lets the host poll without a stream sync
-    float *accum;        // 3 floats per pixel, radiance sums
+    F4 *accum;           // one 16-byte word per pixel: radiance sums in x, y, z — one vector reduction per splat
+    unsigned long long *accum_fx;  // RTB_RENDER_DETERMINISTIC (null otherwise): three 64-bit fixed-point sums per pixel; integer
+                                   // adds commute, so the image no longer depends on the order of the splats or on how the
+                                   // samples were spread over wavefronts and GPUs
     int32_t pool;
     // beyond the reference (off in parity mode): per-hit {pdf of the BSDF sample that produced the ray, hit
     // distance} for RTB_RENDER_TRUE_MIS ([kNumMaterialTypes][pool], null otherwise); constant environment radiance
@@ -65,6 +68,41 @@ struct WaveState {
     // two-level scenes: instance of every hit ([kNumMaterialTypes][pool], null for flat scenes)
     int32_t *hit_inst;
 };
+
+// ------------------------------------------------------------ framebuffer splat
+// atomic_add(Vec3), vec3.cuh:149-153, is three scalar float atomics on a 12-byte pixel.  Here a pixel is one aligned
+// 16-byte word and a splat is ONE vector reduction (red.global.add.v4.f32, sm_90+: no return value, nothing waits).
+// Deterministic mode: 2^-28 fixed point in 64-bit integers; a splat is clamped to +-2^24 so that 2^11 clamped splats fit.
+constexpr float kFixedScale = 268435456.f;              // 2^28
+constexpr double kFixedInvScale = 1.0 / 268435456.0;
+RTB_HD long long to_fixed(float v) {
+    v = fminf(fmaxf(v, -16777216.f), 16777216.f);
+#if defined(__CUDA_ARCH__)
+    return __float2ll_rn(fmul(v, kFixedScale));
+#else
+    return llrintf(fmul(v, kFixedScale));
+#endif
+}
+RTB_HD float from_fixed(long long v) { return (float)((double)v * kFixedInvScale); }
+RTB_HD void accum_add(const WaveState &W, uint32_t pixel, V3 L) {
+#if defined(__CUDA_ARCH__)
+    if (W.accum_fx) {
+        unsigned long long *p = W.accum_fx + 3 * (size_t)pixel;
+        atomicAdd(p, (unsigned long long)to_fixed(L.x)); atomicAdd(p + 1, (unsigned long long)to_fixed(L.y));
+        atomicAdd(p + 2, (unsigned long long)to_fixed(L.z));
+    } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(W.accum + pixel), "f"(L.x), "f"(L.y), "f"(L.z), "f"(0.f) : "memory");
+    }
+#else
+    if (W.accum_fx) {
+        unsigned long long *p = W.accum_fx + 3 * (size_t)pixel;
+        p[0] += (unsigned long long)to_fixed(L.x); p[1] += (unsigned long long)to_fixed(L.y); p[2] += (unsigned long long)to_fixed(L.z);
+    } else {
+        F4 &a = W.accum[pixel];
+        a.x = fadd(a.x, L.x); a.y = fadd(a.y, L.y); a.z = fadd(a.z, L.z);
+    }
+#endif
+}
 
 constexpr int kMaxBounces = 255;       // bounces share a word with the sample index
 constexpr int kMaxSampleIndex = 1 << 24;
@@ -92,19 +130,11 @@ RTB_HD void tally_flush(Counters *c, const ShadeTally &t) {
         if (s) atomicAdd(&c->stat_shadow, (unsigned long long)s);
     }
 }
-RTB_HD void accum_add(float *accum, uint32_t pixel, V3 L) {
-    float *p = accum + 3 * (size_t)pixel;
-    atomicAdd(p, L.x); atomicAdd(p + 1, L.y); atomicAdd(p + 2, L.z);
-}
 RTB_HD void work_add(unsigned long long *p, unsigned v) { atomicAdd(p, (unsigned long long)v); }
 #else
 RTB_HD int queue_push(int32_t *counter) { return (*counter)++; }
 struct ShadeTally { uint32_t extend, shadow; };
 RTB_HD void tally_flush(Counters *c, const ShadeTally &t) { c->stat_extend += t.extend; c->stat_shadow += t.shadow; }
-RTB_HD void accum_add(float *accum, uint32_t pixel, V3 L) {
-    float *p = accum + 3 * (size_t)pixel;
-    p[0] += L.x; p[1] += L.y; p[2] += L.z;
-}
 RTB_HD void work_add(unsigned long long *p, unsigned v) { *p += v; }
 #endif
 
@@ -148,7 +178,7 @@ RTB_HD int hit_queue_push(const WaveState &W, int type) {
 }
 RTB_HD void extend_miss(const WaveState &W, uint32_t pixel, V3 beta) {  // environment light, rtb_render_params.env_L
     const V3 L = vmul(beta, v3(W.env[0], W.env[1], W.env[2]));
-    if (finite3(L)) accum_add(W.accum, pixel, L);
+    if (finite3(L)) accum_add(W, pixel, L);
 }
 RTB_HD void extend_finish(const WaveState &W, const SceneView &S, int qi, const HitRec &h, int hit_inst = -1) {
     if (h.tri < 0) {
@@ -202,7 +232,7 @@ RTB_HD void shade_item(const WaveState &W, const SceneView &S, const RenderConst
     in.inst = (EXT && W.hit_inst) ? W.hit_inst[q] : -1;
     PathStepOut out;
     path_step<TYPE, EXT>(S, rc, in, out);
-    if (out.emit) accum_add(W.accum, in.pixel, out.emission);
+    if (out.emit) accum_add(W, in.pixel, out.emission);
     // A ray with a non-finite component can hit nothing (every comparison of the triangle test fails),
     // but it would pass every slab test and walk the whole tree: retire it here with the result it
     // would have had — a miss ends the path, an unoccluded shadow ray splats.  (MATTE sampling yields
@@ -211,7 +241,7 @@ RTB_HD void shade_item(const WaveState &W, const SceneView &S, const RenderConst
     if (out.extend && !(finite3(out.o) && finite3(out.d))) out.extend = false;
     if (out.shadow && !(finite3(out.so) && finite3(out.sd) && out.stmax > 0.f)) {
         out.shadow = false;
-        if (finite3(out.sL)) accum_add(W.accum, in.pixel, out.sL);
+        if (finite3(out.sL)) accum_add(W, in.pixel, out.sL);
     }
     // slot of this path in the ray queues = its position in the concatenated hit queues
     const Counters &c = *W.c;
@@ -248,7 +278,7 @@ RTB_HD void shadow_finish(const WaveState &W, int si, bool occluded) {
     if (occluded) return;
     const F4 l = ldg(W.sh_L + si);
     const V3 L = xyz(l);
-    if (finite3(L)) accum_add(W.accum, f2u(l.w), L);
+    if (finite3(L)) accum_add(W, f2u(l.w), L);
 }
 template <bool COUNT>
 RTB_HD void shadow_body(const WaveState &W, const SceneView &S, int si) {

@@ -11,6 +11,8 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <numeric>
 #include <vector>
 
@@ -23,7 +25,22 @@ struct HostBackend {
     int device() const { return -1; }
     void make_current() {}
     void sync() {}
-    int default_pool() const { return 1 << 16; }
+    // the schedule options of the CUDA backend are accepted and remembered (they select kernels the emulation does not
+    // have; "pool" is honoured)
+    std::map<std::string, long long> opts_;
+    bool set_option(const std::string &name, long long v) {
+        static const char *const names[] = {"refill", "chunk", "prefetch", "tri_step", "pooled", "fused", "smem_stack", "pipelines", "pool",
+                                            "ploc_tail", "trace_blocks"};
+        for (const char *n : names) if (name == n) { if (name == "pool" && v < 1024) return false; opts_[name] = v; return true; }
+        return false;
+    }
+    bool get_option(const std::string &name, long long &v) const {
+        auto it = opts_.find(name);
+        if (it == opts_.end()) return false;
+        v = it->second;
+        return true;
+    }
+    int default_pool() const { auto it = opts_.find("pool"); return it == opts_.end() ? 1 << 16 : (int)it->second; }
 
     template <class T> T *alloc(size_t n) {
         void *p = nullptr;

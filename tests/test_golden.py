@@ -149,3 +149,22 @@ def test_gpu_image_converges_to_reference_image(gpu, bunny, name, kind, depth):
     assert err[-1] < err[-2] < err[-3]  # at 4096 spp the reference's own 16k-spp noise shows
     assert abs(bias) < 0.01, bias
     assert err[-1] / np.median(ref[np.isfinite(ref)]) < 0.02
+
+
+def test_oracle_equals_reference_on_the_10m_triangle_scene(emu, oracle, bunny):
+    """configs C3 / C5: the oracle's restatement of Bvh::Bvh (bvh.cuh:30-219) builds the reference's own tree on the
+    10,000,956-triangle field (same node count and depth, ref_bvh.json) and its traversal returns the reference's hit
+    records and any-hit bits (s2_hits.npz / s2_any.npz, made on a B200 by tools/make_golden.py).  ~80 s: the
+    single-threaded full-sweep SAH build."""
+    from test_wavefront_trace import ray_checksum, s2_rays, s2_shadow_rays
+    g, a = load("s2_hits.npz"), load("s2_any.npz")
+    hs = emu.host_scene(capi.RTB_SCENE_S2, *bunny, grid=12)
+    rays = s2_rays(emu, hs)
+    srays, excl = s2_shadow_rays(len(a["occluded"]), hs.desc.num_triangles)
+    assert ray_checksum(rays) == int(g["ray_checksum"]) and ray_checksum(srays) == int(a["ray_checksum"])
+    osc = oracle.scene(hs.desc)
+    info = json.load(open(os.path.join(GOLDEN, "ref_bvh.json")))
+    assert osc.bvh_stats() == (info["s2_bvh"]["nodes"], info["s2_bvh"]["max_depth"])
+    check_hits(osc.trace_closest(rays, capi.HIT_DTYPE), g["hits"])
+    assert 0.3 < (g["hits"]["prim"] >= 0).mean() < 0.9
+    assert (osc.trace_any(srays, excl) == a["occluded"]).all()

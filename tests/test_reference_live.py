@@ -55,12 +55,12 @@ def test_primary_hit_ids_match_the_reference(setup, w, h):
     rays.tofile(rf)
     run_harness(sf, "trace", rf, hf)
     ref = np.fromfile(hf, dtype=capi.HIT_DTYPE)
-    hits = sc.trace_closest(rays)
-    ndiff, nties, max_rel, bitexact = compare(hits, ref)
-    print(f"{w}x{h}: {ndiff} id differences ({nties} exact-t ties), max rel t err {max_rel:.2e}, t bit-exact {bitexact}")
-    assert ndiff == nties, "a hit id differs from the reference without being an exact tie in t"
-    assert ndiff <= 1e-5 * len(rays)
-    assert max_rel <= 1e-5
+    for entry, hits in (("per-ray kernel", sc.trace_closest(rays)), ("render path's persistent kernel", sc.trace_wavefront(rays)[0])):
+        ndiff, nties, max_rel, bitexact = compare(hits, ref)
+        print(f"{w}x{h} {entry}: {ndiff} id differences ({nties} exact-t ties), max rel t err {max_rel:.2e}, t bit-exact {bitexact}")
+        assert ndiff == nties, "a hit id differs from the reference without being an exact tie in t"
+        assert ndiff <= 1e-5 * len(rays)
+        assert max_rel <= 1e-5
 
 
 def test_incoherent_rays_match_the_reference(setup):
@@ -70,6 +70,7 @@ def test_incoherent_rays_match_the_reference(setup):
     rays.tofile(rf)
     run_harness(sf, "trace", rf, hf)
     ref = np.fromfile(hf, dtype=capi.HIT_DTYPE)
-    ndiff, nties, max_rel, bitexact = compare(sc.trace_closest(rays), ref)
-    print(f"random: {ndiff} id differences ({nties} ties), max rel t err {max_rel:.2e}, bit-exact {bitexact}")
-    assert ndiff == nties and ndiff <= 1e-5 * len(rays) and max_rel <= 1e-5
+    for entry, hits in (("per-ray kernel", sc.trace_closest(rays)), ("render path's persistent kernel", sc.trace_wavefront(rays)[0])):
+        ndiff, nties, max_rel, bitexact = compare(hits, ref)
+        print(f"random, {entry}: {ndiff} id differences ({nties} ties), max rel t err {max_rel:.2e}, bit-exact {bitexact}")
+        assert ndiff == nties and ndiff <= 1e-5 * len(rays) and max_rel <= 1e-5

@@ -123,3 +123,42 @@ def test_full_scene_4k_sample_passes_add_up(gpu, field_full):
     assert sa.extend_rays + sb.extend_rays == sf.extend_rays and sa.shadow_rays + sb.shadow_rays == sf.shadow_rays
     assert np.isfinite(full).all()
     assert mean_rel_err(a.astype(np.float64) ** 2 + b.astype(np.float64) ** 2, full.astype(np.float64) ** 2) <= 1e-5
+
+
+# ---------------------------------------------------------------- BASELINE.json's image shapes against the oracle
+def test_c2_shape_image_matches_oracle(gpu, oracle, bunny):
+    """config C2's full frame (1920x1080, depth 8, seed 1) at 2 spp: every pixel index, the pixel * spp path numbering
+    and the 16:9 camera at the size the benchmark runs, against the oracle with the same per-pixel RNG streams"""
+    hs = gpu.host_scene(capi.RTB_SCENE_S1, *bunny)
+    sc = gpu.context(0).scene(hs.desc)
+    cam = hs.camera(1920 / 1080)
+    p = capi.render_params(gpu, width=1920, height=1080, spp=2, max_bounces=8)
+    img, st = sc.render(cam, p)
+    rimg, _, ost = oracle.scene(hs.desc).render(cam, p)
+    err = mean_rel_err(img, rimg)
+    print(f"C2 shape 1920x1080x2spp: mean rel err {err:.2e}, paths {st.paths}, rays {st.extend_rays}+{st.shadow_rays} (oracle {ost[1]}+{ost[2]})")
+    assert st.paths == ost[0] == 1920 * 1080 * 2
+    assert abs(int(st.extend_rays) - int(ost[1])) <= 2e-3 * ost[1] and abs(int(st.shadow_rays) - int(ost[2])) <= 2e-3 * ost[2]
+    assert err <= 1e-3
+    # per-pixel, not only in the mean: 99.9 % of the pixels within 1e-3 of the oracle's value (the rest: a path whose
+    # ulp-level shading difference flipped a discrete decision)
+    close = np.abs(img.astype(np.float64) - rimg).max(axis=2) <= 1e-3 * np.maximum(rimg.max(axis=2), 1e-2)
+    assert close.mean() >= 0.999, close.mean()
+    sc.close()
+
+
+def test_c3_shape_image_matches_oracle(gpu, oracle, field_small):
+    """config C3's frame (3840x2160, depth 8) at 1 spp on the 625k-triangle cut of the field (the oracle's host SAH build
+    of all 10 M triangles takes minutes): 8.3 M pixels, pixel indices beyond 2^23"""
+    hs, sc = field_small
+    cam = hs.camera(3840 / 2160)
+    p = capi.render_params(gpu, width=3840, height=2160, spp=1, max_bounces=8)
+    img, st = sc.render(cam, p)
+    rimg, _, ost = oracle.scene(hs.desc).render(cam, p)
+    err = mean_rel_err(img, rimg)
+    print(f"C3 shape 3840x2160x1spp on 625k triangles: mean rel err {err:.2e}, paths {st.paths}")
+    assert st.paths == ost[0] == 3840 * 2160
+    assert abs(int(st.extend_rays) - int(ost[1])) <= 2e-3 * ost[1] and abs(int(st.shadow_rays) - int(ost[2])) <= 2e-3 * ost[2]
+    assert err <= 1e-3
+    close = np.abs(img.astype(np.float64) - rimg).max(axis=2) <= 1e-3 * np.maximum(rimg.max(axis=2), 1e-2)
+    assert close.mean() >= 0.999, close.mean()
