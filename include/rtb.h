@@ -258,6 +258,12 @@ RTB_API int rtb_scene_create_from_primitives(rtb_context *ctx, const void *h_pri
                                              const void *d_materials, int32_t num_materials,
                                              const void *d_lights, int32_t num_lights,
                                              const rtb_build_params *bp, rtb_scene **out);
+/* The reference constructs `Bvh` BEFORE the light array exists and fills `Scene{bvh, num_lights, d_lights}` afterwards
+ * (main.cu:151-156): pass num_lights = -1 above to build the tree at once (stats are then available, as the
+ * reference's Bvh::num_nodes / max_depth are after its constructor, bvh.cuh:23-27,203-204) and hand the lights over
+ * here; may be called again when the light array changes.  A light pointer outside [d_lights, d_lights + num_lights):
+ * RTB_ERR_INVALID. */
+RTB_API int rtb_scene_attach_lights(rtb_scene *scene, const void *d_lights, int32_t num_lights);
 /* two-level BVH over meshes + instances (see rtb_instanced_scene_desc); every query / render entry point below
  * works on the result like on a flat scene */
 RTB_API int rtb_scene_create_instanced(rtb_context *ctx, const rtb_instanced_scene_desc *desc,
@@ -326,6 +332,49 @@ RTB_API int rtb_tonemap_fixed_device(rtb_context *ctx, const int64_t *d_accum_fi
  * d_out may alias d_accum */
 RTB_API int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t num_floats,
                                int32_t total_spp, float *d_out);
+
+/* ---- several GPUs of one box (the reference has no cudaSetDevice, stream or collective anywhere and
+ *      its render() is not re-entrant: globals at render.cuh:25-59) ----
+ * Every (pixel, sample) path is independent under the counter-based RNG, so the GPUs split the SAMPLES of every pixel
+ * (balanced, contiguous shares of p->spp), each accumulates into its own buffer, and one sum-reduction over NVLink
+ * (NCCL ncclReduce: float sums, or the 64-bit fixed-point sums with RTB_RENDER_DETERMINISTIC, which makes the image
+ * bit-identical for any number of GPUs) followed by the tonemap on the first GPU gives the image.  NCCL (libnccl.so.2)
+ * is loaded on first use; a box without it gets RTB_ERR_NO_DEVICE from these entry points only.
+ *
+ * (1) ONE PROCESS, n GPUs — the drop-in for render() on a multi-GPU box: */
+typedef struct rtb_multi rtb_multi;             /* n contexts + their communicator */
+typedef struct rtb_multi_scene rtb_multi_scene; /* the scene, resident on every GPU of the rtb_multi */
+RTB_API int rtb_multi_create(const int32_t *device_ordinals, int32_t n, rtb_multi **out);
+RTB_API int rtb_multi_destroy(rtb_multi *m);
+RTB_API int rtb_multi_size(const rtb_multi *m);
+RTB_API int rtb_multi_context(rtb_multi *m, int32_t i, rtb_context **ctx); /* borrowed: do not destroy */
+/* built concurrently, one host thread per GPU, each from the same host description */
+RTB_API int rtb_multi_scene_create(rtb_multi *m, const rtb_scene_desc *desc, const rtb_build_params *bp, rtb_multi_scene **out);
+RTB_API int rtb_multi_scene_create_instanced(rtb_multi *m, const rtb_instanced_scene_desc *desc, const rtb_build_params *bp,
+                                             rtb_multi_scene **out);
+/* built once: `primary` (a scene of context 0 of `m`, e.g. from rtb_scene_create_from_primitives, whose device
+ * pointers live on that GPU only) is copied device to device to the other GPUs; `primary` stays owned by the caller
+ * and must outlive the result */
+RTB_API int rtb_multi_scene_replicate(rtb_multi *m, rtb_scene *primary, rtb_multi_scene **out);
+RTB_API int rtb_multi_scene_destroy(rtb_multi_scene *ms);
+/* replaces render(), render.cuh:366-367: p->spp samples per pixel in total, split over the GPUs that p->device_mask
+ * selects (0 = all); h_rgb_out as in rtb_render.  stats: rays / paths summed over the GPUs, ms_total = the slowest GPU's
+ * render + reduce + tonemap */
+RTB_API int rtb_multi_render(rtb_multi_scene *ms, const rtb_camera *cam, const rtb_render_params *p, float *h_rgb_out,
+                             rtb_render_stats *stats);
+/* everything in one call (contexts, scene upload + build on every GPU, render, reduce, tonemap, teardown) */
+RTB_API int rtb_render_multi(const int32_t *device_ordinals, int32_t n, const rtb_scene_desc *desc, const rtb_build_params *bp,
+                             const rtb_camera *cam, const rtb_render_params *p, float *h_rgb_out, rtb_render_stats *stats);
+/* (2) ONE PROCESS PER GPU (torchrun, MPI): rank 0 makes an id and hands its RTB_COMM_ID_BYTES bytes to the other ranks
+ * through the launcher's own channel; every rank renders its shard with rtb_render_accumulate[_fixed] (first_sample /
+ * spp / total_spp of its share) and the buffers are summed in place on every rank. */
+#define RTB_COMM_ID_BYTES 128
+typedef struct rtb_comm rtb_comm;
+RTB_API int rtb_comm_unique_id(uint8_t *id_out);
+RTB_API int rtb_comm_create(rtb_context *ctx, const uint8_t *id, int32_t rank, int32_t world, rtb_comm **out);
+RTB_API int rtb_comm_destroy(rtb_comm *c);
+RTB_API int rtb_comm_allreduce_f32(rtb_comm *c, float *d_buf, int64_t n);     /* ncclAllReduce(ncclFloat32, ncclSum), in place */
+RTB_API int rtb_comm_allreduce_i64(rtb_comm *c, int64_t *d_buf, int64_t n);   /* fixed-point sums: exact */
 
 /* Feature buffers of the primary hits, one camera ray through every pixel centre (what a denoiser wants next to the
  * radiance; SURVEY 8f-4 — the reference has nothing of the kind): albedo of the hit material (float[3*W*H]), geometric

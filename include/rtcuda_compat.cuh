@@ -43,6 +43,25 @@ inline void check_rtb(int rc, const char *what) {
         exit(EXIT_FAILURE);
     }
 }
+// RTB_DEVICES="0,1,..." -> device ordinals; the first must be the current device.  Unset or one entry: that device alone.
+inline std::vector<int32_t> devices_from_env(int current) {
+    std::vector<int32_t> d;
+    if (const char *e = getenv("RTB_DEVICES")) {
+        for (const char *p = e; *p;) {
+            char *end = nullptr;
+            long v = strtol(p, &end, 10);
+            if (end == p) break;
+            d.push_back((int32_t)v);
+            p = *end == ',' ? end + 1 : end;
+        }
+    }
+    if (d.empty()) d.push_back(current);
+    if (d[0] != current) {
+        fprintf(stderr, "RTB_DEVICES must start with the current device %d (the caller's device arrays live there)\n", current);
+        exit(EXIT_FAILURE);
+    }
+    return d;
+}
 }  // namespace rtcuda_compat
 
 struct Vec3 {
@@ -108,45 +127,69 @@ struct Primitive {
 static_assert(sizeof(Vec3) == 12 && sizeof(Triangle) == 48 && sizeof(Material) == 20 && sizeof(Light) == 40 && sizeof(Primitive) == 24,
               "layouts must match the reference (SURVEY.md 8a)");
 
-// Bvh keeps the reference's constructor signature.  The device BVH is built on
-// the GPU the first time the scene is rendered (the light array is only known
-// once `Scene` is filled in, scene.cuh:4-8).
+// Bvh keeps the reference's constructor signature and its public fields (bvh.cuh:17-27).  Like the reference's, the
+// constructor BUILDS the tree (on the GPU, through rtb_scene_create_from_primitives with the lights still to come:
+// `Scene` is filled in afterwards, main.cu:151-156), so num_nodes / max_depth are valid when it returns; the light
+// array is attached at the first render().
+//
+// Several GPUs: with the environment variable RTB_DEVICES="0,1,2,3" (first entry = the current device, where the
+// caller's device arrays live) render() splits the samples over those GPUs (rtb_multi_render: scene copied device to
+// device, per-GPU accumulation, one NCCL reduction, tonemap on the first GPU).  Unset: one GPU, as in the reference.
 struct Bvh {
     struct Impl {
-        std::vector<Primitive> primitives;
         rtb_context *ctx = nullptr;
         rtb_scene *scene = nullptr;
-        const void *built_for_lights = nullptr;
+        rtb_multi *multi = nullptr;
+        rtb_multi_scene *replicas = nullptr;
+        const void *lights_attached = nullptr;
+        int num_lights_attached = -1;
     };
     Bvh() {}
     Bvh(const std::vector<Triangle> &triangles, const std::vector<Primitive> &primitives)
         : num_primitives((int)triangles.size()), impl(new Impl()) {
         if (triangles.size() != primitives.size()) { fprintf(stderr, "Bvh: triangles/primitives size mismatch\n"); exit(EXIT_FAILURE); }
-        impl->primitives = primitives;
-    }
-    rtb_scene *device_scene(int num_lights, Light *d_lights) const {
-        if (impl->scene && impl->built_for_lights == d_lights) return impl->scene;
-        if (impl->scene) rtb_scene_destroy(impl->scene);
-        if (!impl->ctx) {
-            int dev = 0;
-            CHECK_CUDA(cudaGetDevice(&dev));
+        int dev = 0;
+        CHECK_CUDA(cudaGetDevice(&dev));
+        std::vector<int32_t> devices = rtcuda_compat::devices_from_env(dev);
+        if (devices.size() > 1) {
+            rtcuda_compat::check_rtb(rtb_multi_create(devices.data(), (int32_t)devices.size(), &impl->multi), "rtb_multi_create");
+            rtcuda_compat::check_rtb(rtb_multi_context(impl->multi, 0, &impl->ctx), "rtb_multi_context");
+        } else {
             rtcuda_compat::check_rtb(rtb_context_create(dev, &impl->ctx), "rtb_context_create");
         }
         const Triangle *tri_base = nullptr;
         const Material *mat_lo = nullptr, *mat_hi = nullptr;
-        for (const Primitive &p : impl->primitives) {
+        for (const Primitive &p : primitives) {
             if (!tri_base || p.d_triangle < tri_base) tri_base = p.d_triangle;
             if (!mat_lo || p.d_mat < mat_lo) mat_lo = p.d_mat;
             if (!mat_hi || p.d_mat > mat_hi) mat_hi = p.d_mat;
         }
         const int num_materials = mat_lo ? (int)(mat_hi - mat_lo) + 1 : 0;
-        rtcuda_compat::check_rtb(rtb_scene_create_from_primitives(impl->ctx, impl->primitives.data(), (int64_t)impl->primitives.size(), tri_base,
-                                                                  mat_lo, num_materials, d_lights, num_lights, nullptr, &impl->scene),
+        rtcuda_compat::check_rtb(rtb_scene_create_from_primitives(impl->ctx, primitives.data(), (int64_t)primitives.size(), tri_base, mat_lo,
+                                                                  num_materials, nullptr, -1, nullptr, &impl->scene),
                                  "rtb_scene_create_from_primitives");
-        impl->built_for_lights = d_lights;
+        rtb_bvh_stats st;
+        rtcuda_compat::check_rtb(rtb_scene_stats(impl->scene, &st), "rtb_scene_stats");
+        num_nodes = (int)st.num_nodes;           // 80-byte 8-wide nodes (the reference counts its 32-byte binary nodes)
+        max_depth = (int)st.collapse_levels;     // levels of the 8-wide tree
+    }
+    // the device scene with Scene::d_lights attached (scene.cuh:4-8)
+    rtb_scene *device_scene(int num_lights, Light *d_lights) const {
+        if (impl->lights_attached != d_lights || impl->num_lights_attached != num_lights) {
+            if (impl->replicas) { rtb_multi_scene_destroy(impl->replicas); impl->replicas = nullptr; }
+            rtcuda_compat::check_rtb(rtb_scene_attach_lights(impl->scene, d_lights, num_lights), "rtb_scene_attach_lights");
+            impl->lights_attached = d_lights; impl->num_lights_attached = num_lights;
+        }
         return impl->scene;
     }
+    rtb_multi_scene *device_replicas(int num_lights, Light *d_lights) const {
+        rtb_scene *s = device_scene(num_lights, d_lights);
+        if (!impl->replicas) rtcuda_compat::check_rtb(rtb_multi_scene_replicate(impl->multi, s, &impl->replicas), "rtb_multi_scene_replicate");
+        return impl->replicas;
+    }
     int num_primitives = 0;
+    int num_nodes = 0;
+    int max_depth = 0;
     Impl *impl = nullptr;
 };
 
@@ -180,6 +223,11 @@ inline void render(int width, int height, int num_samples, int max_bounces, Came
     rtb_render_params_default(&p);
     p.width = width; p.height = height; p.spp = num_samples; p.max_bounces = max_bounces;
     framebuffer.resize((size_t)width * (size_t)height);
+    if (scene.bvh.impl->multi) {
+        rtb_multi_scene *ms = scene.bvh.device_replicas(scene.num_lights, scene.d_lights);
+        rtcuda_compat::check_rtb(rtb_multi_render(ms, reinterpret_cast<const rtb_camera *>(&camera), &p, &framebuffer.data()->x, nullptr), "rtb_multi_render");
+        return;
+    }
     rtcuda_compat::check_rtb(rtb_render(s, reinterpret_cast<const rtb_camera *>(&camera), &p, &framebuffer.data()->x, nullptr), "rtb_render");
 }
 

@@ -12,6 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.environ.get("RTB_LIB") or os.path.join(HERE, "librtb.so")  # RTB_LIB: A/B builds (tuning runs only)
+HOST_LIB = os.path.join(HERE, "librtb_host.so")  # the host-side part alone: scene generators, mesh / scene / PPM I/O (no CUDA)
 BUNNY_BIN = os.path.join(HERE, "data", "bunny.rtbm")
 
 RTB_SCENE_S1, RTB_SCENE_S1_MIXED, RTB_SCENE_S2, RTB_SCENE_S1_GLOSSY = 1, 2, 3, 4
@@ -94,7 +95,11 @@ SYMBOLS = [
     "rtb_scene_create_instanced", "rtb_host_scene_build_instanced", "rtb_host_scene_instanced_desc", "rtb_instanced_flatten",
     "rtb_trace_wavefront", "rtb_kat_eval", "rtb_context_set_option", "rtb_context_get_option",
     "rtb_render_accumulate_fixed", "rtb_tonemap_fixed_device",
+    "rtb_multi_create", "rtb_multi_destroy", "rtb_multi_size", "rtb_multi_context", "rtb_multi_scene_create",
+    "rtb_multi_scene_create_instanced", "rtb_multi_scene_replicate", "rtb_multi_scene_destroy", "rtb_multi_render", "rtb_render_multi",
+    "rtb_scene_attach_lights", "rtb_comm_unique_id", "rtb_comm_create", "rtb_comm_destroy", "rtb_comm_allreduce_f32", "rtb_comm_allreduce_i64",
 ]
+RTB_COMM_ID_BYTES = 128
 RTB_KAT_TRI_INTERSECT, RTB_KAT_OFFSET_ORIGIN, RTB_KAT_RAND4, RTB_KAT_SAMPLE_F, RTB_KAT_SLAB, RTB_KAT_SAMPLE_LI = 1, 2, 3, 4, 5, 6
 KAT_FLOATS = {1: (16, 4), 2: (6, 3), 3: (4, 4), 4: (16, 12), 5: (20, 1), 6: (16, 8)}  # floats per record: (in, out)
 
@@ -358,6 +363,114 @@ class Scene:
     def close(self):
         if self.h:
             self.L.lib.rtb_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Multi:
+    """several GPUs driven from this process (rtb_multi): contexts + their NCCL communicator"""
+
+    def __init__(self, L, devices):
+        self.L = L
+        self.h = C.c_void_p()
+        arr = (C.c_int32 * len(devices))(*devices)
+        L.check(L.lib.rtb_multi_create(arr, len(devices), C.byref(self.h)))
+        self.n = len(devices)
+
+    def context(self, i):
+        """borrowed Context of member i (not destroyed by this wrapper)"""
+        c = Context.__new__(Context)
+        c.L, c.h = self.L, C.c_void_p()
+        self.L.check(self.L.lib.rtb_multi_context(self.h, i, C.byref(c.h)))
+        c.__class__ = BorrowedContext
+        return c
+
+    def scene(self, desc, build_params=None):
+        return MultiScene(self, desc, build_params)
+
+    def replicate(self, primary):
+        return MultiScene(self, None, None, primary=primary)
+
+    def close(self):
+        if self.h:
+            self.L.lib.rtb_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BorrowedContext(Context):
+    def __del__(self):
+        pass
+
+
+class MultiScene:
+    def __init__(self, multi, desc, build_params=None, primary=None):
+        self.multi, self.L = multi, multi.L
+        self.h = C.c_void_p()
+        self.primary = primary  # keep alive: the replica set borrows it
+        bp = C.byref(build_params) if build_params is not None else None
+        if primary is not None:
+            self.L.check(self.L.lib.rtb_multi_scene_replicate(multi.h, primary.h, C.byref(self.h)))
+        elif isinstance(desc, InstancedSceneDesc):
+            self.L.check(self.L.lib.rtb_multi_scene_create_instanced(multi.h, C.byref(desc), bp, C.byref(self.h)))
+        else:
+            self.L.check(self.L.lib.rtb_multi_scene_create(multi.h, C.byref(desc), bp, C.byref(self.h)))
+
+    def render(self, cam, params, out=None):
+        """params.spp samples per pixel in TOTAL, split over the GPUs params.device_mask selects"""
+        if out is None:
+            out = np.zeros((params.height, params.width, 3), dtype=np.float32)
+        st = RenderStats()
+        ptr = out.ctypes.data_as(C.c_void_p) if isinstance(out, np.ndarray) else C.c_void_p(out)
+        self.L.check(self.L.lib.rtb_multi_render(self.h, C.byref(cam), C.byref(params), ptr, C.byref(st)))
+        return out, st
+
+    def close(self):
+        if self.h:
+            self.L.lib.rtb_multi_scene_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    """one process per GPU: NCCL communicator owned by the library (rtb_comm)"""
+
+    def __init__(self, ctx, id_bytes, rank, world):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        buf = (C.c_uint8 * RTB_COMM_ID_BYTES).from_buffer_copy(bytes(id_bytes))
+        self.L.check(self.L.lib.rtb_comm_create(ctx.h, buf, rank, world, C.byref(self.h)))
+
+    @staticmethod
+    def unique_id(L):
+        buf = (C.c_uint8 * RTB_COMM_ID_BYTES)()
+        L.check(L.lib.rtb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def allreduce_f32(self, d_ptr, n):
+        self.L.check(self.L.lib.rtb_comm_allreduce_f32(self.h, C.c_void_p(d_ptr), C.c_int64(n)))
+
+    def allreduce_i64(self, d_ptr, n):
+        self.L.check(self.L.lib.rtb_comm_allreduce_i64(self.h, C.c_void_p(d_ptr), C.c_int64(n)))
+
+    def close(self):
+        if self.h:
+            self.L.lib.rtb_comm_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

@@ -163,6 +163,10 @@ extern "C" {
 int rtb_host_scene_build(int32_t kind, const float *mv, int64_t nv, const int32_t *mf, int64_t nf, int32_t grid,
                          uint32_t seed, rtb_host_scene **out) {
     if (!out || !mv || !mf || nv <= 0 || nf <= 0) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_build: null mesh");
+    *out = nullptr;
+    for (int64_t i = 0; i < 3 * nf; ++i)
+        if (mf[i] < 0 || mf[i] >= nv) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_build: face index out of range");
+    return rtb::host_guarded(RTB_ERR_INVALID, [&]() -> int {
     rtb_host_scene *hs = new rtb_host_scene();
     Builder &b = hs->b;
     // materials, main.cu:42-45
@@ -210,6 +214,7 @@ int rtb_host_scene_build(int32_t kind, const float *mv, int64_t nv, const int32_
     default_camera(hs);
     *out = hs;
     return RTB_OK;
+    });
 }
 
 // Instanced form: the meshes stay in object space, the placements become instance transforms.
@@ -217,6 +222,10 @@ int rtb_host_scene_build_instanced(int32_t kind, const float *mv, int64_t nv, co
                                    uint32_t seed, rtb_host_scene **out) {
     if (!out || !mv || !mf || nv <= 0 || nf <= 0) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_build_instanced: null mesh");
     if (kind != RTB_SCENE_S2 && kind != RTB_SCENE_S1) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_build_instanced: RTB_SCENE_S1 or RTB_SCENE_S2");
+    *out = nullptr;
+    for (int64_t i = 0; i < 3 * nf; ++i)
+        if (mf[i] < 0 || mf[i] >= nv) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_build_instanced: face index out of range");
+    return rtb::host_guarded(RTB_ERR_INVALID, [&]() -> int {
     rtb_host_scene *hs = new rtb_host_scene();
     Builder &b = hs->b;
     const int red = b.add_material(RTB_MATTE, 0.65f, 0.05f, 0.05f, 0.f);
@@ -244,6 +253,7 @@ int rtb_host_scene_build_instanced(int32_t kind, const float *mv, int64_t nv, co
     default_camera(hs);
     *out = hs;
     return RTB_OK;
+    });
 }
 
 int rtb_host_scene_instanced_desc(const rtb_host_scene *hs, rtb_instanced_scene_desc *d) {
@@ -264,6 +274,13 @@ int rtb_instanced_flatten(const rtb_instanced_scene_desc *D, rtb_host_scene **ou
         !D->geometry.material_ids)
         return rtb::set_error(RTB_ERR_INVALID, "rtb_instanced_flatten: incomplete description");
     const rtb_scene_desc &g = D->geometry;
+    *out = nullptr;
+    if (g.num_triangles < 0 || g.num_materials <= 0 || !g.materials || (g.num_lights > 0 && !g.lights) || D->mesh_first[0] != 0 ||
+        D->mesh_first[D->num_meshes] != g.num_triangles)
+        return rtb::set_error(RTB_ERR_INVALID, "rtb_instanced_flatten: inconsistent description");
+    for (int m = 0; m < D->num_meshes; ++m)
+        if (D->mesh_first[m + 1] < D->mesh_first[m]) return rtb::set_error(RTB_ERR_INVALID, "rtb_instanced_flatten: mesh_first must ascend");
+    return rtb::host_guarded(RTB_ERR_INVALID, [&]() -> int {
     rtb_host_scene *hs = new rtb_host_scene();
     Builder &b = hs->b;
     b.materials.assign(g.materials, g.materials + g.num_materials);
@@ -291,6 +308,7 @@ int rtb_instanced_flatten(const rtb_instanced_scene_desc *D, rtb_host_scene **ou
     default_camera(hs);
     *out = hs;
     return RTB_OK;
+    });
 }
 
 int rtb_host_scene_desc(const rtb_host_scene *hs, rtb_scene_desc *d) {
@@ -350,6 +368,8 @@ int rtb_camera_look_at(const float from[3], const float at[3], const float up[3]
 
 // ------------------------------------------------------------------ mesh I/O
 int rtb_mesh_load_ply(const char *path, float **verts_out, int64_t *nv_out, int32_t **faces_out, int64_t *nf_out) {
+    if (!path || !verts_out || !nv_out || !faces_out || !nf_out) return rtb::set_error(RTB_ERR_INVALID, "rtb_mesh_load_ply: null argument");
+    return rtb::host_guarded(RTB_ERR_IO, [&]() -> int {
     std::ifstream in(path);
     if (!in) return rtb::set_error(RTB_ERR_IO, std::string("cannot open ") + path);
     std::string line, tok;
@@ -372,26 +392,33 @@ int rtb_mesh_load_ply(const char *path, float **verts_out, int64_t *nv_out, int3
         else if (tok == "end_header") break;
     }
     if (!ascii || nv < 0 || nf < 0 || vprops < 3) return rtb::set_error(RTB_ERR_IO, "unsupported PLY (need ascii, vertex x y z first, face lists)");
-    float *v = (float *)malloc(sizeof(float) * 3 * (size_t)nv);
+    if (nv > 0x7fffffff || nf > 0x7fffffff) return rtb::set_error(RTB_ERR_IO, "PLY: element count out of range");
+    std::vector<float> verts(3 * (size_t)nv);
     std::vector<int32_t> faces;
-    faces.reserve((size_t)nf * 3);
     for (int64_t i = 0; i < nv; ++i) {
-        std::getline(in, line);
+        if (!std::getline(in, line)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the vertex list");
         std::istringstream ss(line);
-        ss >> v[3 * i] >> v[3 * i + 1] >> v[3 * i + 2];  // x y z are the first three properties
+        if (!(ss >> verts[3 * i] >> verts[3 * i + 1] >> verts[3 * i + 2]))  // x y z are the first three properties
+            return rtb::set_error(RTB_ERR_IO, "PLY: bad vertex line");
     }
     for (int64_t i = 0; i < nf; ++i) {
-        std::getline(in, line);
+        if (!std::getline(in, line)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the face list");
         std::istringstream ss(line);
-        int k; ss >> k;
-        std::vector<int32_t> idx(k);
-        for (int j = 0; j < k; ++j) ss >> idx[j];
+        int k = -1;
+        if (!(ss >> k) || k < 3 || k > 64) return rtb::set_error(RTB_ERR_IO, "PLY: bad face vertex count");
+        int32_t idx[64];
+        for (int j = 0; j < k; ++j)
+            if (!(ss >> idx[j]) || idx[j] < 0 || idx[j] >= nv) return rtb::set_error(RTB_ERR_IO, "PLY: face index out of range");
         for (int j = 1; j + 1 < k; ++j) { faces.push_back(idx[0]); faces.push_back(idx[j]); faces.push_back(idx[j + 1]); }
     }
-    int32_t *f = (int32_t *)malloc(sizeof(int32_t) * faces.size());
+    float *v = (float *)malloc(sizeof(float) * (verts.size() ? verts.size() : 1));
+    int32_t *f = (int32_t *)malloc(sizeof(int32_t) * (faces.size() ? faces.size() : 1));
+    if (!v || !f) { free(v); free(f); return rtb::set_error(RTB_ERR_OOM, "out of host memory"); }
+    memcpy(v, verts.data(), sizeof(float) * verts.size());
     memcpy(f, faces.data(), sizeof(int32_t) * faces.size());
     *verts_out = v; *nv_out = nv; *faces_out = f; *nf_out = (int64_t)faces.size() / 3;
     return RTB_OK;
+    });
 }
 
 int rtb_mesh_save_bin(const char *path, const float *verts, int64_t nv, const int32_t *faces, int64_t nf) {
@@ -406,15 +433,20 @@ int rtb_mesh_save_bin(const char *path, const float *verts, int64_t nv, const in
 }
 
 int rtb_mesh_load_bin(const char *path, float **verts_out, int64_t *nv_out, int32_t **faces_out, int64_t *nf_out) {
+    if (!path || !verts_out || !nv_out || !faces_out || !nf_out) return rtb::set_error(RTB_ERR_INVALID, "rtb_mesh_load_bin: null argument");
     FILE *f = fopen(path, "rb");
     if (!f) return rtb::set_error(RTB_ERR_IO, std::string("cannot open ") + path);
     uint32_t hdr[3];
     if (fread(hdr, 4, 3, f) != 3 || hdr[0] != 0x4d425452u) { fclose(f); return rtb::set_error(RTB_ERR_IO, "bad mesh file"); }
-    float *v = (float *)malloc(12 * (size_t)hdr[1]);
-    int32_t *fc = (int32_t *)malloc(12 * (size_t)hdr[2]);
+    if (hdr[1] > 0x7fffffffu || hdr[2] > 0x7fffffffu) { fclose(f); return rtb::set_error(RTB_ERR_IO, "bad mesh file: counts out of range"); }
+    float *v = (float *)malloc(12 * (size_t)(hdr[1] ? hdr[1] : 1));
+    int32_t *fc = (int32_t *)malloc(12 * (size_t)(hdr[2] ? hdr[2] : 1));
+    if (!v || !fc) { free(v); free(fc); fclose(f); return rtb::set_error(RTB_ERR_OOM, "out of host memory"); }
     bool ok = fread(v, 12, hdr[1], f) == hdr[1] && fread(fc, 12, hdr[2], f) == hdr[2];
     fclose(f);
     if (!ok) { free(v); free(fc); return rtb::set_error(RTB_ERR_IO, "truncated mesh file"); }
+    for (size_t i = 0; i < 3 * (size_t)hdr[2]; ++i)
+        if (fc[i] < 0 || (uint32_t)fc[i] >= hdr[1]) { free(v); free(fc); return rtb::set_error(RTB_ERR_IO, "bad mesh file: face index out of range"); }
     *verts_out = v; *nv_out = hdr[1]; *faces_out = fc; *nf_out = hdr[2];
     return RTB_OK;
 }
@@ -426,6 +458,8 @@ void rtb_free(void *p) { free(p); }
 //   f32 vertices[9n] i32 material_ids[n] i32 light_ids[n]
 //   rtb_material[num_materials] rtb_light[num_lights]
 int rtb_scene_desc_save(const char *path, const rtb_scene_desc *d) {
+    if (!path || !d || d->num_triangles < 0 || (d->num_triangles > 0 && (!d->vertices || !d->material_ids || !d->light_ids)))
+        return rtb::set_error(RTB_ERR_INVALID, "rtb_scene_desc_save: incomplete description (vertices, material_ids and light_ids are all written)");
     FILE *f = fopen(path, "wb");
     if (!f) return rtb::set_error(RTB_ERR_IO, std::string("cannot write ") + path);
     uint32_t magic = 0x53425452u;
@@ -443,29 +477,48 @@ int rtb_scene_desc_save(const char *path, const rtb_scene_desc *d) {
 }
 
 int rtb_host_scene_load(const char *path, rtb_host_scene **out) {
+    if (!path || !out) return rtb::set_error(RTB_ERR_INVALID, "rtb_host_scene_load: null argument");
+    *out = nullptr;
     FILE *f = fopen(path, "rb");
     if (!f) return rtb::set_error(RTB_ERR_IO, std::string("cannot open ") + path);
     uint32_t magic; int64_t n; int32_t nm, nl;
     bool ok = fread(&magic, 4, 1, f) == 1 && magic == 0x53425452u && fread(&n, 8, 1, f) == 1 &&
               fread(&nm, 4, 1, f) == 1 && fread(&nl, 4, 1, f) == 1;
     if (!ok) { fclose(f); return rtb::set_error(RTB_ERR_IO, "bad scene file"); }
-    rtb_host_scene *hs = new rtb_host_scene();
+    // the counts must be plausible for the file that holds them before anything is sized from them
+    long here = ftell(f);
+    fseek(f, 0, SEEK_END);
+    const long long remaining = (long long)ftell(f) - here;
+    fseek(f, here, SEEK_SET);
+    if (n < 0 || nm < 0 || nl < 0 || n > 0x3fffffff || (long long)n * 44 + (long long)nm * 20 + (long long)nl * 40 != remaining) {
+        fclose(f);
+        return rtb::set_error(RTB_ERR_IO, "bad scene file: counts do not match the file size");
+    }
+    return rtb::host_guarded(RTB_ERR_IO, [&]() -> int {
+    rtb_host_scene *hs = nullptr;
+    try { hs = new rtb_host_scene(); } catch (...) { fclose(f); throw; }
     Builder &b = hs->b;
-    b.verts.resize(9 * (size_t)n); b.mat.resize((size_t)n); b.light.resize((size_t)n);
-    b.materials.resize((size_t)nm); b.lights.resize((size_t)nl);
+    try {
+        b.verts.resize(9 * (size_t)n); b.mat.resize((size_t)n); b.light.resize((size_t)n);
+        b.materials.resize((size_t)nm); b.lights.resize((size_t)nl);
+    } catch (...) { fclose(f); delete hs; throw; }
     ok = fread(b.verts.data(), 4, b.verts.size(), f) == b.verts.size() && fread(b.mat.data(), 4, (size_t)n, f) == (size_t)n &&
          fread(b.light.data(), 4, (size_t)n, f) == (size_t)n &&
          fread(b.materials.data(), sizeof(rtb_material), (size_t)nm, f) == (size_t)nm &&
          fread(b.lights.data(), sizeof(rtb_light), (size_t)nl, f) == (size_t)nl;
     fclose(f);
     if (!ok) { delete hs; return rtb::set_error(RTB_ERR_IO, "truncated scene file"); }
+    for (int64_t i = 0; i < n; ++i)
+        if (b.mat[(size_t)i] < 0 || b.mat[(size_t)i] >= nm || b.light[(size_t)i] >= nl) { delete hs; return rtb::set_error(RTB_ERR_IO, "bad scene file: material / light id out of range"); }
     default_camera(hs);
     *out = hs;
     return RTB_OK;
+    });
 }
 
 // main.cu:178-191
 int rtb_write_ppm(const char *path, const float *rgb, int32_t w, int32_t h) {
+    if (!path || !rgb || w <= 0 || h <= 0) return rtb::set_error(RTB_ERR_INVALID, "rtb_write_ppm: bad arguments");
     FILE *f = fopen(path, "w");
     if (!f) return rtb::set_error(RTB_ERR_IO, std::string("cannot write ") + path);
     fprintf(f, "P3\n%d %d\n255\n", w, h);

@@ -63,8 +63,13 @@ struct PrimSetupArgs {
     Tri48 *tri_in;                // [n] caller order
     F4 *prim_lo, *prim_hi;        // [n] bounds (w unused)
     int32_t *scene_bounds;        // 6 ordered ints: min xyz, max xyz
+    int32_t *bad;                 // raised when a vertex is not finite or beyond kMaxCoord
     int32_t n;
 };
+// Coordinates the builder accepts: finite and |x| <= 2^100.  (An infinite vertex gives a cluster whose merged area is
+// never below any other, so PLOC could not pair it; beyond 2^100 box extents and areas overflow.  The reference has no
+// such check: its host SAH sweep just produces a useless tree.)
+constexpr float kMaxCoord = 1.2676506e30f;
 RTB_HD void prim_setup_body(const PrimSetupArgs &a, int i) {
     if (i >= a.n) return;
     Tri48 t;
@@ -79,6 +84,12 @@ RTB_HD void prim_setup_body(const PrimSetupArgs &a, int i) {
     V3 p0 = tri_p0(t), p1 = vsub(p0, tri_e1(t)), p2 = vadd(p0, tri_e2(t));
     V3 lo = v3(fminf(p0.x, fminf(p1.x, p2.x)), fminf(p0.y, fminf(p1.y, p2.y)), fminf(p0.z, fminf(p1.z, p2.z)));
     V3 hi = v3(fmaxf(p0.x, fmaxf(p1.x, p2.x)), fmaxf(p0.y, fmaxf(p1.y, p2.y)), fmaxf(p0.z, fmaxf(p1.z, p2.z)));
+    // (fminf / fmaxf drop a NaN operand, so the vertices are looked at themselves)
+    const float worst = fmaxf(fmaxf(fmaxf(fabsf(p0.x), fabsf(p0.y)), fmaxf(fabsf(p0.z), fabsf(p1.x))),
+                              fmaxf(fmaxf(fabsf(p1.y), fabsf(p1.z)), fmaxf(fabsf(p2.x), fmaxf(fabsf(p2.y), fabsf(p2.z)))));
+    const bool nan = p0.x != p0.x || p0.y != p0.y || p0.z != p0.z || p1.x != p1.x || p1.y != p1.y || p1.z != p1.z || p2.x != p2.x ||
+                     p2.y != p2.y || p2.z != p2.z;
+    if (nan || !(worst <= kMaxCoord)) *a.bad = 1;
     F4 l; l.x = lo.x; l.y = lo.y; l.z = lo.z; l.w = 0.f;
     F4 h; h.x = hi.x; h.y = hi.y; h.z = hi.z; h.w = 0.f;
     a.prim_lo[i] = l; a.prim_hi[i] = h;
@@ -157,7 +168,7 @@ RTB_HD void ploc_nn_body(const PlocArgs &a, int i) {
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
         const float ar = union_half_area(me, a.nodes[a.cin[j]]);
-        if (ar < best) { best = ar; bj = j; }
+        if (bj < 0 || ar < best) { best = ar; bj = j; }  // total: every cluster names a neighbour, whatever its area
     }
     a.nn[i] = bj;
 }

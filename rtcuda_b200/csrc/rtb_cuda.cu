@@ -21,9 +21,12 @@
 //                         render.cuh:433-445)
 //   k_for<Functor>        one thread per element for builder / utility bodies
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is opened with dlopen on first use (no link-time dependency)
 
 #include <cctype>
 #include <cstdlib>
+#include <mutex>
 
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -465,12 +468,53 @@ __global__ void __launch_bounds__(kPlocTail) k_ploc_tail(PlocArgs a, int n_leave
         __syncthreads();
         if (flag) cin[pos] = v;
         if (t == 0) out[2 + rounds] = n - total;
+        const bool stuck = total >= n;  // a round that merged nothing would spin here for ever (cannot happen with finite boxes)
         n = total;
         ++rounds;
         __syncthreads();
+        if (stuck) break;
     }
-    if (t == 0) { out[0] = rounds; out[1] = cin[0]; }
+    if (t == 0) { out[0] = n > 1 ? -1 : rounds; out[1] = cin[0]; }
 }
+
+// NCCL, loaded on first use.  A process that already holds a libnccl.so.2 (torch brings its own) gets that one.
+struct Nccl {
+    void *lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclReduce) Reduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    static Nccl &get() {
+        static Nccl n;
+        static std::once_flag once;
+        std::call_once(once, [] {
+            for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+                n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+                if (n.lib) break;
+            }
+            if (!n.lib) return;
+#define RTB_NCCL_SYM(f) n.f = (decltype(n.f))dlsym(n.lib, "nccl" #f)
+            RTB_NCCL_SYM(GetUniqueId); RTB_NCCL_SYM(CommInitRank); RTB_NCCL_SYM(CommInitAll); RTB_NCCL_SYM(CommDestroy);
+            RTB_NCCL_SYM(AllReduce); RTB_NCCL_SYM(Reduce); RTB_NCCL_SYM(GroupStart); RTB_NCCL_SYM(GroupEnd); RTB_NCCL_SYM(GetErrorString);
+#undef RTB_NCCL_SYM
+        });
+        if (!n.lib || !n.GetUniqueId || !n.CommInitRank || !n.CommInitAll || !n.CommDestroy || !n.AllReduce || !n.Reduce || !n.GroupStart ||
+            !n.GroupEnd || !n.GetErrorString)
+            throw Error(RTB_ERR_NO_DEVICE, "NCCL (libnccl.so.2) could not be loaded: multi-GPU entry points need it");
+        return n;
+    }
+};
+#define RTB_NCCL_CHECK(expr)                                                                                               \
+    do {                                                                                                                   \
+        ncclResult_t r_ = (expr);                                                                                          \
+        if (r_ != ncclSuccess) throw rtb::Error(RTB_ERR_CUDA, std::string(#expr) + ": " + rtb::Nccl::get().GetErrorString(r_)); \
+    } while (0)
+static_assert(sizeof(ncclUniqueId) == RTB_COMM_ID_BYTES, "rtb.h: RTB_COMM_ID_BYTES must be sizeof(ncclUniqueId)");
 
 struct NonNegative {
     __host__ __device__ bool operator()(const int32_t &v) const { return v >= 0; }
@@ -482,6 +526,7 @@ struct CudaBackend {
     cudaStream_t stream_ = nullptr;  // the stream launches go to: streams_[0] unless use_stream(k) says otherwise
     cudaStream_t streams_[kMaxPipelines] = {nullptr, nullptr};
     cudaEvent_t sync_ev_ = nullptr;
+    cudaMemPool_t pool_mem_ = nullptr;
     int pipelines_ = 0;  // RTB_PIPELINES: concurrent wavefronts per render (1..4); 0 = by scene size, see pipelines()
     int blocks_trace_ = 0, blocks_generate_ = 0;
     int trace_blocks_per_sm_ = 1, trace_cap_ = 0, active_pipelines_ = 1;
@@ -514,12 +559,18 @@ struct CudaBackend {
         for (int k = 0; k < kMaxPipelines; ++k) RTB_CUDA_CHECK(cudaStreamCreateWithFlags(&streams_[k], cudaStreamDefault));
         stream_ = streams_[0];
         RTB_CUDA_CHECK(cudaEventCreateWithFlags(&sync_ev_, cudaEventDisableTiming));
-        // stream-ordered allocator that keeps freed blocks: scene builds and renders reuse memory
-        // instead of paying cudaMalloc/cudaFree (each an implicit device synchronisation) every call
-        cudaMemPool_t mp;
-        RTB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&mp, dev_));
+        // stream-ordered allocator that keeps freed blocks: scene builds and renders reuse memory instead of paying
+        // cudaMalloc / cudaFree (each an implicit device synchronisation) every call.  The pool is this context's own
+        // (the device's default pool is process-wide state that a host framework may also use); it is destroyed with
+        // the context, which returns every byte to the driver.
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev_;
+        RTB_CUDA_CHECK(cudaMemPoolCreate(&pool_mem_, &props));
         unsigned long long keep = ~0ull;
-        RTB_CUDA_CHECK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+        RTB_CUDA_CHECK(cudaMemPoolSetAttribute(pool_mem_, cudaMemPoolAttrReleaseThreshold, &keep));
         RTB_CUDA_CHECK(cudaHostAlloc((void **)&h_done_, kMaxPipelines * sizeof(int32_t), cudaHostAllocMapped));
         RTB_CUDA_CHECK(cudaHostGetDevicePointer((void **)&d_done_, h_done_, 0));
         for (int k = 0; k < kMaxPipelines; ++k) h_done_[k] = 0;
@@ -549,6 +600,7 @@ struct CudaBackend {
         if (h_done_) cudaFreeHost(h_done_);
         if (sync_ev_) cudaEventDestroy(sync_ev_);
         for (int k = 0; k < kMaxPipelines; ++k) if (streams_[k]) { cudaStreamSynchronize(streams_[k]); cudaStreamDestroy(streams_[k]); }
+        if (pool_mem_) cudaMemPoolDestroy(pool_mem_);
     }
     CudaBackend(const CudaBackend &) = delete;
     CudaBackend &operator=(const CudaBackend &) = delete;
@@ -592,7 +644,7 @@ struct CudaBackend {
 
     template <class T> T *alloc(size_t n) {
         void *p = nullptr;
-        RTB_CUDA_CHECK(cudaMallocAsync(&p, sizeof(T) * (n ? n : 1), stream_));
+        RTB_CUDA_CHECK(cudaMallocFromPoolAsync(&p, sizeof(T) * (n ? n : 1), pool_mem_, stream_));
         return (T *)p;
     }
     void free(void *p) { if (p) cudaFreeAsync(p, stream_); }
@@ -608,6 +660,67 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(T) * n, cudaMemcpyDeviceToDevice, stream_));
     }
     template <class T> void zero(T *p, size_t n) { RTB_CUDA_CHECK(cudaMemsetAsync(p, 0, sizeof(T) * n, stream_)); }
+    // device memory of another context's GPU -> this one's (NVLink peer copy when the driver can, staged otherwise)
+    template <class T> void copy_from(CudaBackend &src_be, T *dst, const T *src, size_t n) {
+        if (!n) return;
+        if (src_be.dev_ == dev_) { copy(dst, src, n); return; }
+        RTB_CUDA_CHECK(cudaMemcpyPeerAsync(dst, dev_, src, src_be.dev_, sizeof(T) * n, stream_));
+    }
+    // ---- collectives over the GPUs of one process (rtb_multi) and over processes (rtb_comm) ----
+    struct Group { std::vector<ncclComm_t> comms; };
+    static Group *group_create(const std::vector<CudaBackend *> &members) {
+        Nccl &nc = Nccl::get();
+        std::vector<int> devs;
+        for (CudaBackend *b : members) devs.push_back(b->dev_);
+        Group *g = new Group();
+        g->comms.resize(members.size());
+        ncclResult_t r = nc.CommInitAll(g->comms.data(), (int)devs.size(), devs.data());
+        if (r != ncclSuccess) { delete g; throw Error(RTB_ERR_CUDA, std::string("ncclCommInitAll: ") + nc.GetErrorString(r)); }
+        return g;
+    }
+    static void group_destroy(Group *g) {
+        if (!g) return;
+        for (ncclComm_t c : g->comms) if (c) Nccl::get().CommDestroy(c);
+        delete g;
+    }
+    // sum of every member's buffer into the root's, in place; enqueued on each member's stream, one NCCL group
+    template <class T>
+    static void group_reduce(Group *g, const std::vector<CudaBackend *> &members, const std::vector<T *> &bufs, size_t n, int root) {
+        Nccl &nc = Nccl::get();
+        const ncclDataType_t dt = sizeof(T) == 8 ? ncclInt64 : ncclFloat32;
+        RTB_NCCL_CHECK(nc.GroupStart());
+        for (size_t r = 0; r < members.size(); ++r) {
+            ncclResult_t e = nc.Reduce(bufs[r], bufs[r], n, dt, ncclSum, root, g->comms[r], members[r]->streams_[0]);
+            if (e != ncclSuccess) { nc.GroupEnd(); throw Error(RTB_ERR_CUDA, std::string("ncclReduce: ") + nc.GetErrorString(e)); }
+        }
+        RTB_NCCL_CHECK(nc.GroupEnd());
+    }
+    struct Comm { ncclComm_t comm = nullptr; int rank = 0, world = 1; };
+    static void comm_unique_id(uint8_t *out) {
+        ncclUniqueId id;
+        RTB_NCCL_CHECK(Nccl::get().GetUniqueId(&id));
+        memcpy(out, &id, sizeof id);
+    }
+    Comm *comm_create(const uint8_t *id_bytes, int rank, int world) {
+        ncclUniqueId id;
+        memcpy(&id, id_bytes, sizeof id);
+        make_current();
+        Comm *c = new Comm();
+        c->rank = rank; c->world = world;
+        ncclResult_t r = Nccl::get().CommInitRank(&c->comm, world, id, rank);
+        if (r != ncclSuccess) { delete c; throw Error(RTB_ERR_CUDA, std::string("ncclCommInitRank: ") + Nccl::get().GetErrorString(r)); }
+        return c;
+    }
+    static void comm_destroy(Comm *c) {
+        if (!c) return;
+        if (c->comm) Nccl::get().CommDestroy(c->comm);
+        delete c;
+    }
+    template <class T> void comm_allreduce(Comm *c, T *buf, size_t n) {
+        const ncclDataType_t dt = sizeof(T) == 8 ? ncclInt64 : ncclFloat32;
+        RTB_NCCL_CHECK(Nccl::get().AllReduce(buf, buf, n, dt, ncclSum, c->comm, streams_[0]));
+        RTB_CUDA_CHECK(cudaStreamSynchronize(streams_[0]));
+    }
 
     template <class F> void launch(int n, F f) {
         if (n <= 0) return;
@@ -696,7 +809,7 @@ struct CudaBackend {
         if (bytes <= cub_temp_bytes_) return;
         if (cub_temp_) cudaFreeAsync(cub_temp_, stream_);
         cub_temp_ = nullptr; cub_temp_bytes_ = 0;
-        RTB_CUDA_CHECK(cudaMallocAsync(&cub_temp_, bytes, stream_));
+        RTB_CUDA_CHECK(cudaMallocFromPoolAsync(&cub_temp_, bytes, pool_mem_, stream_));
         cub_temp_bytes_ = bytes;
     }
     void sort_pairs(uint64_t *keys, int32_t *vals, int n) {
@@ -721,6 +834,7 @@ struct CudaBackend {
         std::vector<int32_t> h(2 + kPlocTail);
         download(h.data(), d_out, h.size());
         free(d_out);
+        if (h[0] < 0) throw Error(RTB_ERR_INVALID, "internal: a PLOC round merged nothing");
         round_counts.assign(h.begin() + 2, h.begin() + 2 + h[0]);
         root = h[1];
         return true;

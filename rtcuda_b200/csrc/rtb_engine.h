@@ -14,6 +14,7 @@
 #include <cmath>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "rtb_build.h"
@@ -37,6 +38,27 @@ struct DeviceBuf {
     T *release() { T *q = p; p = nullptr; return q; }
 };
 
+// the device temporaries of one build: whatever is still held when the scope ends — normally or by an exception — is freed
+template <class BE>
+struct Temps {
+    BE &be;
+    std::vector<void *> held;
+    explicit Temps(BE &b) : be(b) {}
+    ~Temps() { for (void *p : held) be.free(p); }
+    Temps(const Temps &) = delete;
+    Temps &operator=(const Temps &) = delete;
+    template <class T> T *alloc(size_t n) {
+        held.push_back(nullptr);  // (the slot first: push_back may throw, an allocation must not be lost to it)
+        T *p = be.template alloc<T>(n);
+        held.back() = p;
+        return p;
+    }
+    void free(void *p) {  // early release (peak memory): no longer held
+        for (auto &h : held) if (h == p) { h = nullptr; break; }
+        be.free(p);
+    }
+};
+
 // ---- kernel functors (named types => readable kernel names in ncu) ----
 struct PrimSetupK { PrimSetupArgs a; RTB_HD void operator()(int i) const { prim_setup_body(a, i); } };
 struct MortonK { MortonArgs a; RTB_HD void operator()(int i) const { morton_body(a, i); } };
@@ -56,7 +78,8 @@ struct LightFixK {
 struct RefPrimitive { const void *tri, *mat, *light; };
 struct IngestK {
     const RefPrimitive *prims; const char *tri_base, *mat_base, *light_base;
-    const rtb_material *materials; Tri48 *tri_in; TriMeta *meta_in; int64_t *light_tri; int n;
+    const rtb_material *materials; Tri48 *tri_in; TriMeta *meta_in; int64_t *light_tri; const void **light_ptr; int32_t *bad;
+    int n, num_mats, num_lights;
     RTB_HD void operator()(int i) const {
         if (i >= n) return;
         const RefPrimitive p = prims[i];
@@ -65,12 +88,35 @@ struct IngestK {
         r.p0x = t[0]; r.p0y = t[1]; r.p0z = t[2]; r.e1x = t[3]; r.e1y = t[4]; r.e1z = t[5];
         r.e2x = t[6]; r.e2y = t[7]; r.e2z = t[8]; r.nx = t[9]; r.ny = t[10]; r.nz = t[11];
         tri_in[i] = r;
-        const int m = (int)(((const char *)p.mat - mat_base) / 20);
+        const long long mo = (const char *)p.mat - mat_base;
         TriMeta tm;
+        tm.light = -1;
+        if (mo < 0 || mo % 20 != 0 || mo / 20 >= num_mats) { *bad = 1; tm.material = 0; meta_in[i] = tm; return; }  // a pointer outside d_materials
+        const int m = (int)(mo / 20);
         tm.material = m | (materials[m].type << 24);
-        tm.light = p.light ? (int)(((const char *)p.light - light_base) / 40) : -1;
+        if (light_ptr) {  // lights follow later (attach_lights): remember the pointer
+            light_ptr[i] = p.light;
+        } else if (p.light) {
+            const long long lo = (const char *)p.light - light_base;
+            if (lo < 0 || lo % 40 != 0 || lo / 40 >= num_lights) { *bad = 2; meta_in[i] = tm; return; }
+            tm.light = (int)(lo / 40);
+            light_tri[tm.light] = i;
+        }
         meta_in[i] = tm;
-        if (tm.light >= 0) light_tri[tm.light] = i;
+    }
+};
+// Scene{bvh, num_lights, d_lights} filled in after Bvh::Bvh (scene.cuh:4-8, main.cu:151-156): resolve the primitives'
+// light pointers against the light array now known
+struct AttachLightsK {
+    const void *const *light_ptr; const char *light_base; const int32_t *leaf_of_prim; TriMeta *meta; int32_t *bad; int n, num_lights;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        int idx = -1;
+        if (light_ptr[i]) {
+            const long long lo = (const char *)light_ptr[i] - light_base;
+            if (lo < 0 || lo % 40 != 0 || lo / 40 >= num_lights) *bad = 2; else idx = (int)(lo / 40);
+        }
+        meta[leaf_of_prim[i]].light = idx;
     }
 };
 struct GenerateK { WaveState W; RenderConsts rc; };
@@ -264,6 +310,9 @@ struct SceneT {
     LightDev *lights = nullptr;
     int32_t num_materials = 0, num_lights = 0, num_nodes = 0;
     uint32_t type_mask = 0;  // bit t set iff some material has type t
+    // reference-pointer ingest with the lights still to come (rtb_scene_attach_lights): the primitives' light pointers
+    // in caller order, and the base of the caller's triangle array (area lights name their triangle by pointer)
+    const void **deferred_light_ptr = nullptr; const char *ref_tri_base = nullptr;
     rtb_bvh_stats stats{};
     // render state kept between calls (the reference re-allocates ~293 MB per
     // render() and never frees it, render.cuh:374-391)
@@ -316,7 +365,7 @@ struct SceneT {
         free_wave();
         be->free(accum); be->free(accum_fx); be->free(own_out);
         be->free(nodes8); be->free(tris); be->free(meta); be->free(prim); be->free(leaf_of_prim);
-        be->free(materials); be->free(lights); be->free(inst); be->free(top_inst);
+        be->free(materials); be->free(lights); be->free(inst); be->free(top_inst); be->free((void *)deferred_light_ptr);
     }
 };
 
@@ -350,28 +399,35 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
                      const rtb_build_params &bp, int max_leaf, Tri48 *tris_out, TriMeta *meta_out, int32_t *prim_out,
                      int32_t *leaf_of_prim) {
     BuiltTree out;
+    Temps<BE> tmp(be);
     if (bp.builder != RTB_BUILDER_PLOC) throw Error(RTB_ERR_INVALID, "unknown BVH builder");
     const int radius = bp.ploc_radius > 0 ? bp.ploc_radius : 16;
     // 1. per-triangle records, bounds
-    F4 *prim_lo = be.template alloc<F4>(n), *prim_hi = be.template alloc<F4>(n);
-    int32_t *bounds = be.template alloc<int32_t>(6);
+    F4 *prim_lo = tmp.template alloc<F4>(n), *prim_hi = tmp.template alloc<F4>(n);
+    int32_t *bounds = tmp.template alloc<int32_t>(7);  // [6] = "a vertex is not finite / out of range"
     {
-        int32_t init[6];
+        int32_t init[7];
         for (int k = 0; k < 3; ++k) { init[k] = float_to_ordered(FLT_MAX); init[3 + k] = float_to_ordered(-FLT_MAX); }
-        be.upload(bounds, init, 6);
+        init[6] = 0;
+        be.upload(bounds, init, 7);
         if (box_lo) {
             be.copy(prim_lo, box_lo, (size_t)n); be.copy(prim_hi, box_hi, (size_t)n);
             BoxBoundsK k; k.lo = box_lo; k.hi = box_hi; k.bounds = bounds; k.n = n;
             be.launch(n, k);
         } else {
             PrimSetupK k; k.a.vertices = d_vertices; k.a.tri_in = tri_in; k.a.prim_lo = prim_lo; k.a.prim_hi = prim_hi;
-            k.a.scene_bounds = bounds; k.a.n = n;
+            k.a.scene_bounds = bounds; k.a.bad = bounds + 6; k.a.n = n;
             be.launch(n, k);
+            int32_t bad = 0;
+            be.download(&bad, bounds + 6, 1);
+            if (bad) {
+                throw Error(RTB_ERR_INVALID, "a triangle vertex is not finite or beyond 2^100: the scene cannot be built");
+            }
         }
     }
     // 2. Morton codes + sort
-    uint64_t *keys = be.template alloc<uint64_t>(n);
-    int32_t *sorted = be.template alloc<int32_t>(n);
+    uint64_t *keys = tmp.template alloc<uint64_t>(n);
+    int32_t *sorted = tmp.template alloc<int32_t>(n);
     {
         MortonK k; k.a.prim_lo = prim_lo; k.a.prim_hi = prim_hi; k.a.scene_bounds = bounds; k.a.keys = keys; k.a.vals = sorted; k.a.n = n;
         be.launch(n, k);
@@ -379,10 +435,10 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     }
     // 3. PLOC
     const int n_b2 = 2 * n - 1;
-    B2Node *b2 = be.template alloc<B2Node>(n_b2);
-    int32_t *count = be.template alloc<int32_t>(n_b2);
-    int32_t *ca = be.template alloc<int32_t>(n), *cb = be.template alloc<int32_t>(n), *nn = be.template alloc<int32_t>(n);
-    int32_t *ctr = be.template alloc<int32_t>(4);  // [0] b2 node counter, [1] wide node counter, [2] tri counter, [3] work out
+    B2Node *b2 = tmp.template alloc<B2Node>(n_b2);
+    int32_t *count = tmp.template alloc<int32_t>(n_b2);
+    int32_t *ca = tmp.template alloc<int32_t>(n), *cb = tmp.template alloc<int32_t>(n), *nn = tmp.template alloc<int32_t>(n);
+    int32_t *ctr = tmp.template alloc<int32_t>(4);  // [0] b2 node counter, [1] wide node counter, [2] tri counter, [3] work out
     {
         PlocLeafK k; k.lo = prim_lo; k.hi = prim_hi; k.sorted = sorted; k.nodes = b2; k.count = count; k.clusters = ca; k.n = n;
         be.launch(n, k);
@@ -406,18 +462,19 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
         PlocMergeK k2; k2.a = a; k2.n_leaves = n; be.launch(ncl, k2);
         const int before = ncl;
         ncl = be.compact_nonneg(cb, ca, ncl);
+        if (ncl >= before) throw Error(RTB_ERR_INVALID, "internal: a PLOC round merged nothing");  // (cannot happen with finite boxes: the lowest-area pair is mutual)
         round_first.push_back(next_id); round_count.push_back(before - ncl);
         next_id += before - ncl;
         ++iters;
     }
     if (root_b2 < 0) be.download(&root_b2, ca, 1);
     out.ploc_iterations = iters;
-    be.free(prim_lo); be.free(prim_hi); be.free(keys); be.free(sorted); be.free(cb); be.free(nn); be.free(ca);
+    tmp.free(prim_lo); tmp.free(prim_hi); tmp.free(keys); tmp.free(sorted); tmp.free(cb); tmp.free(nn); tmp.free(ca);
     // 4. collapse plan: bottom-up over the binary tree, one launch per PLOC round (a round's nodes only have older children)
     float *plan_cost = nullptr; uint8_t *plan = nullptr;
     if (bp.collapse == RTB_COLLAPSE_SAH_OPTIMAL && n > max_leaf) {
-        plan_cost = be.template alloc<float>((size_t)n_b2 * 7);
-        plan = be.template alloc<uint8_t>((size_t)n_b2 * 8);
+        plan_cost = tmp.template alloc<float>((size_t)n_b2 * 7);
+        plan = tmp.template alloc<uint8_t>((size_t)n_b2 * 8);
         for (size_t r = 0; r < round_first.size(); ++r) {
             PlanK k; k.a.nodes = b2; k.a.count = count; k.a.cost = plan_cost; k.a.plan = plan;
             k.a.first = round_first[r]; k.a.n = round_count[r]; k.a.max_leaf = max_leaf;
@@ -426,9 +483,9 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     }
     // 5. collapse to the 8-wide compressed tree
     const int max_nodes = n > 1 ? n : 1;
-    Q4 *nodes_tmp = be.template alloc<Q4>((size_t)max_nodes * kNodeWords);
-    WorkItem *wa = be.template alloc<WorkItem>(max_nodes), *wb = be.template alloc<WorkItem>(max_nodes);
-    float *sah = be.template alloc<float>(1);
+    Q4 *nodes_tmp = tmp.template alloc<Q4>((size_t)max_nodes * kNodeWords);
+    WorkItem *wa = tmp.template alloc<WorkItem>(max_nodes), *wb = tmp.template alloc<WorkItem>(max_nodes);
+    float *sah = tmp.template alloc<float>(1);
     {
         float z = 0.f; be.upload(sah, &z, 1);
         WorkItem r; r.b2 = root_b2; r.wide = 0;
@@ -457,7 +514,7 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     if (c4[2] != n) throw Error(RTB_ERR_INVALID, "internal: collapse lost triangles");
     out.nodes8 = be.template alloc<Q4>((size_t)out.num_nodes * kNodeWords);
     be.copy(out.nodes8, nodes_tmp, (size_t)out.num_nodes * kNodeWords);
-    be.free(nodes_tmp); be.free(wa); be.free(wb); be.free(plan_cost); be.free(plan);
+    tmp.free(nodes_tmp); tmp.free(wa); tmp.free(wb); tmp.free(plan_cost); tmp.free(plan);
     float sah_h = 0.f;
     be.download(&sah_h, sah, 1);
     int32_t bnd[6];
@@ -467,7 +524,7 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     const float root_area = half_area(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
     out.sah_cost = root_area > 0.f ? sah_h / root_area : 0.f;
     for (int k = 0; k < 3; ++k) { out.bounds[2 * k] = lo[k]; out.bounds[2 * k + 1] = hi[k]; }
-    be.free(b2); be.free(count); be.free(ctr); be.free(sah); be.free(bounds);
+    tmp.free(b2); tmp.free(count); tmp.free(ctr); tmp.free(sah); tmp.free(bounds);
     return out;
 }
 
@@ -559,14 +616,14 @@ SceneT<BE> *scene_from_desc(BE &be, const rtb_scene_desc &d, const rtb_build_par
         be.upload(sc->materials, d.materials, d.num_materials);
         for (int i = 0; i < d.num_materials; ++i) sc->type_mask |= 1u << d.materials[i].type;
         sc->lights = be.template alloc<LightDev>(d.num_lights > 0 ? d.num_lights : 1);
-        int64_t *d_light_tri = be.template alloc<int64_t>(d.num_lights > 0 ? d.num_lights : 1);
+        Temps<BE> tmp(be);
+        int64_t *d_light_tri = tmp.template alloc<int64_t>(d.num_lights > 0 ? d.num_lights : 1);
         if (d.num_lights) { be.upload(sc->lights, lights.data(), d.num_lights); be.upload(d_light_tri, light_tri.data(), d.num_lights); }
-        float *d_vertices = be.template alloc<float>(n > 0 ? 9 * (size_t)n : 1);
-        Tri48 *tri_in = be.template alloc<Tri48>(n > 0 ? n : 1);
-        TriMeta *meta_in = be.template alloc<TriMeta>(n > 0 ? n : 1);
+        float *d_vertices = tmp.template alloc<float>(n > 0 ? 9 * (size_t)n : 1);
+        Tri48 *tri_in = tmp.template alloc<Tri48>(n > 0 ? n : 1);
+        TriMeta *meta_in = tmp.template alloc<TriMeta>(n > 0 ? n : 1);
         if (n) { be.upload(d_vertices, d.vertices, 9 * (size_t)n); be.upload(meta_in, meta.data(), (size_t)n); }
         build_bvh(be, *sc, d_vertices, tri_in, meta_in, d_light_tri, bp);
-        be.free(d_vertices); be.free(tri_in); be.free(meta_in); be.free(d_light_tri);
     } catch (...) {
         delete sc;
         throw;
@@ -576,10 +633,39 @@ SceneT<BE> *scene_from_desc(BE &be, const rtb_scene_desc &d, const rtb_build_par
 
 // Bvh::Bvh(triangles, primitives) + Scene{bvh,num_lights,d_lights} through the
 // reference's own device arrays (bvh.cuh:30, scene.cuh:4-8, main.cu:141-156)
+// lights in the reference's layout (light.cuh:9-28: type@0 pos@4 d_triangle@16 L@24, 40 bytes) -> LightDev + the index
+// of each area light's triangle in the caller's triangle array
+template <class BE>
+void ingest_ref_lights(BE &be, const void *d_lights, int num_lights, const void *d_tris, int64_t n, std::vector<LightDev> &lights,
+                       std::vector<int64_t> &light_tri) {
+    std::vector<char> hl(40 * (size_t)(num_lights > 0 ? num_lights : 1));
+    if (num_lights) be.download(hl.data(), (const char *)d_lights, 40 * (size_t)num_lights);
+    lights.assign((size_t)(num_lights > 0 ? num_lights : 1), LightDev{});
+    light_tri.assign((size_t)(num_lights > 0 ? num_lights : 1), 0);
+    for (int i = 0; i < num_lights; ++i) {
+        const char *p = hl.data() + 40 * (size_t)i;
+        LightDev &o = lights[(size_t)i];
+        memcpy(&o.type, p, 4); memcpy(&o.px, p + 4, 12); memcpy(&o.Lx, p + 24, 12);
+        o.tri = -1;
+        if (o.type != RTB_POINT_LIGHT && o.type != RTB_AREA_LIGHT) throw Error(RTB_ERR_INVALID, "unknown light type");
+        const void *tp; memcpy(&tp, p + 16, 8);
+        if (o.type == RTB_AREA_LIGHT) {
+            const long long off = (const char *)tp - (const char *)d_tris;
+            if (off < 0 || off % 48 != 0 || off / 48 >= n) throw Error(RTB_ERR_INVALID, "area light: d_triangle does not point into the triangle array");
+            light_tri[(size_t)i] = off / 48;
+        }
+    }
+}
+// Bvh::Bvh(triangles, primitives) + Scene{bvh,num_lights,d_lights} through the
+// reference's own device arrays (bvh.cuh:30, scene.cuh:4-8, main.cu:141-156).
+// num_lights < 0: the light array is not known yet (the reference fills `Scene` after constructing `Bvh`); the tree
+// is built now and attach_lights() resolves the primitives' light pointers later.
 template <class BE>
 SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const void *d_tris, const void *d_mats,
                                   int num_mats, const void *d_lights, int num_lights, const rtb_build_params &bp) {
-    if (n < 0 || (n > 0 && (!h_prims || !d_tris)) || !d_mats || num_mats <= 0 || (num_lights > 0 && !d_lights))
+    const bool deferred = num_lights < 0;
+    if (deferred) num_lights = 0;
+    if (n < 0 || n > 0x3fffffff || (n > 0 && (!h_prims || !d_tris)) || !d_mats || num_mats <= 0 || (num_lights > 0 && !d_lights))
         throw Error(RTB_ERR_INVALID, "rtb_scene_create_from_primitives: bad arguments");
     SceneT<BE> *sc = new SceneT<BE>();
     try {
@@ -587,6 +673,7 @@ SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const 
         sc->n = n;
         sc->num_materials = num_mats;
         sc->num_lights = num_lights;
+        sc->ref_tri_base = (const char *)d_tris;
         sc->materials = be.template alloc<rtb_material>(num_mats);
         be.copy((char *)sc->materials, (const char *)d_mats, 20 * (size_t)num_mats);  // same 20-byte layout
         {
@@ -597,40 +684,111 @@ SceneT<BE> *scene_from_primitives(BE &be, const void *h_prims, int64_t n, const 
                 sc->type_mask |= 1u << hm[(size_t)i].type;
             }
         }
-        // Light (light.cuh:9-28): type@0 pos@4 d_triangle@16 L@24, 40 bytes
-        std::vector<char> hl(40 * (size_t)(num_lights > 0 ? num_lights : 1));
-        if (num_lights) be.download(hl.data(), (const char *)d_lights, 40 * (size_t)num_lights);
-        std::vector<LightDev> lights((size_t)(num_lights > 0 ? num_lights : 1));
-        std::vector<int64_t> light_tri((size_t)(num_lights > 0 ? num_lights : 1), 0);
-        for (int i = 0; i < num_lights; ++i) {
-            const char *p = hl.data() + 40 * (size_t)i;
-            LightDev &o = lights[(size_t)i];
-            memcpy(&o.type, p, 4); memcpy(&o.px, p + 4, 12); memcpy(&o.Lx, p + 24, 12);
-            o.tri = -1;
-            const void *tp; memcpy(&tp, p + 16, 8);
-            if (o.type == RTB_AREA_LIGHT) light_tri[(size_t)i] = ((const char *)tp - (const char *)d_tris) / 48;
-        }
-        sc->lights = be.template alloc<LightDev>(num_lights > 0 ? num_lights : 1);
-        int64_t *d_light_tri = be.template alloc<int64_t>(num_lights > 0 ? num_lights : 1);
+        std::vector<LightDev> lights;
+        std::vector<int64_t> light_tri;
+        ingest_ref_lights(be, d_lights, num_lights, d_tris, n, lights, light_tri);
+        sc->lights = be.template alloc<LightDev>(lights.size());
+        DeviceBuf<BE, int64_t> d_light_tri(be, light_tri.size());
         be.upload(sc->lights, lights.data(), lights.size());
-        be.upload(d_light_tri, light_tri.data(), light_tri.size());
-        RefPrimitive *d_prims = be.template alloc<RefPrimitive>(n > 0 ? n : 1);
-        Tri48 *tri_in = be.template alloc<Tri48>(n > 0 ? n : 1);
-        TriMeta *meta_in = be.template alloc<TriMeta>(n > 0 ? n : 1);
+        be.upload(d_light_tri.p, light_tri.data(), light_tri.size());
+        DeviceBuf<BE, RefPrimitive> d_prims(be, (size_t)(n > 0 ? n : 1));
+        DeviceBuf<BE, Tri48> tri_in(be, (size_t)(n > 0 ? n : 1));
+        DeviceBuf<BE, TriMeta> meta_in(be, (size_t)(n > 0 ? n : 1));
+        DeviceBuf<BE, int32_t> bad(be, 1);
+        be.zero(bad.p, 1);
+        if (deferred) sc->deferred_light_ptr = (const void **)be.template alloc<const void *>((size_t)(n > 0 ? n : 1));
         if (n) {
-            be.upload(d_prims, (const RefPrimitive *)h_prims, (size_t)n);
-            IngestK k; k.prims = d_prims; k.tri_base = (const char *)d_tris; k.mat_base = (const char *)d_mats;
-            k.light_base = (const char *)d_lights; k.materials = sc->materials; k.tri_in = tri_in; k.meta_in = meta_in;
-            k.light_tri = d_light_tri; k.n = (int)n;
+            be.upload(d_prims.p, (const RefPrimitive *)h_prims, (size_t)n);
+            IngestK k; k.prims = d_prims.p; k.tri_base = (const char *)d_tris; k.mat_base = (const char *)d_mats;
+            k.light_base = (const char *)d_lights; k.materials = sc->materials; k.tri_in = tri_in.p; k.meta_in = meta_in.p;
+            k.light_tri = d_light_tri.p; k.light_ptr = sc->deferred_light_ptr; k.bad = bad.p; k.n = (int)n; k.num_mats = num_mats; k.num_lights = num_lights;
             be.launch((int)n, k);
+            int32_t b = 0;
+            be.download(&b, bad.p, 1);
+            if (b == 1) throw Error(RTB_ERR_INVALID, "a Primitive's d_mat does not point into the material array");
+            if (b == 2) throw Error(RTB_ERR_INVALID, "a Primitive's d_area_light does not point into the light array");
         }
-        build_bvh(be, *sc, nullptr, tri_in, meta_in, d_light_tri, bp);
-        be.free(d_prims); be.free(tri_in); be.free(meta_in); be.free(d_light_tri);
+        build_bvh(be, *sc, nullptr, tri_in.p, meta_in.p, d_light_tri.p, bp);
+        be.sync();
     } catch (...) {
         delete sc;
         throw;
     }
     return sc;
+}
+template <class BE>
+void attach_lights(BE &be, SceneT<BE> &sc, const void *d_lights, int num_lights) {
+    if (!sc.deferred_light_ptr) throw Error(RTB_ERR_INVALID, "rtb_scene_attach_lights: the scene was not created with num_lights < 0");
+    if (num_lights < 0 || (num_lights > 0 && !d_lights)) throw Error(RTB_ERR_INVALID, "rtb_scene_attach_lights: bad arguments");
+    std::vector<LightDev> lights;
+    std::vector<int64_t> light_tri;
+    ingest_ref_lights(be, d_lights, num_lights, sc.ref_tri_base, sc.n, lights, light_tri);
+    be.free(sc.lights);
+    sc.lights = nullptr;
+    sc.lights = be.template alloc<LightDev>(lights.size());
+    sc.num_lights = num_lights;
+    DeviceBuf<BE, int64_t> d_light_tri(be, light_tri.size());
+    DeviceBuf<BE, int32_t> bad(be, 1);
+    be.zero(bad.p, 1);
+    be.upload(sc.lights, lights.data(), lights.size());
+    be.upload(d_light_tri.p, light_tri.data(), light_tri.size());
+    if (sc.n) {
+        AttachLightsK k; k.light_ptr = sc.deferred_light_ptr; k.light_base = (const char *)d_lights; k.leaf_of_prim = sc.leaf_of_prim;
+        k.meta = sc.meta; k.bad = bad.p; k.n = (int)sc.n; k.num_lights = num_lights;
+        be.launch((int)sc.n, k);
+        int32_t b = 0;
+        be.download(&b, bad.p, 1);
+        if (b) throw Error(RTB_ERR_INVALID, "a Primitive's d_area_light does not point into the light array");
+    }
+    if (num_lights > 0) {
+        LightFixK k; k.lights = sc.lights; k.light_tri = d_light_tri.p; k.leaf_of_prim = sc.leaf_of_prim; k.n = num_lights;
+        be.launch(num_lights, k);
+    }
+    be.sync();
+}
+
+// ---- a built scene copied to another GPU (rtb_multi_scene_replicate) ----
+// "build once and broadcast, or build concurrently on all GPUs".  The copy moves the finished arrays
+// (8-wide nodes, leaf-order triangles, meta, index maps, materials, lights, instance records) device to device; nothing
+// is rebuilt, so every GPU traverses the very same tree.
+template <class BE>
+SceneT<BE> *clone_scene(BE &dst, BE &src_be, const SceneT<BE> &src) {
+    SceneT<BE> *sc = new SceneT<BE>();
+    try {
+        sc->be = &dst;
+        sc->n = src.n; sc->n_flat = src.n_flat; sc->num_inst = src.num_inst;
+        sc->num_materials = src.num_materials; sc->num_lights = src.num_lights; sc->num_nodes = src.num_nodes;
+        sc->type_mask = src.type_mask; sc->stats = src.stats;
+        const size_t n = (size_t)(src.n > 0 ? src.n : 1);
+        auto dup = [&](auto *&d, const auto *s_, size_t count) {
+            using T = typename std::remove_cv<typename std::remove_pointer<decltype(s_)>::type>::type;
+            d = dst.template alloc<T>(count);
+            dst.copy_from(src_be, d, s_, count);
+        };
+        dup(sc->nodes8, src.nodes8, (size_t)src.num_nodes * kNodeWords);
+        dup(sc->tris, src.tris, 3 * n);
+        dup(sc->meta, src.meta, n);
+        dup(sc->prim, src.prim, n);
+        dup(sc->leaf_of_prim, src.leaf_of_prim, n);
+        dup(sc->materials, src.materials, (size_t)src.num_materials);
+        dup(sc->lights, src.lights, (size_t)(src.num_lights > 0 ? src.num_lights : 1));
+        if (src.inst) {
+            dup(sc->inst, src.inst, (size_t)src.num_inst * kInstWords);
+            dup(sc->top_inst, src.top_inst, (size_t)src.num_inst);
+        }
+        dst.sync();
+    } catch (...) {
+        delete sc;
+        throw;
+    }
+    return sc;
+}
+
+// contiguous, balanced split of `total` samples over `world` shards -> (first, count) of shard `rank`
+inline void shard_samples(int total, int rank, int world, int &first, int &count) {
+    const int base = total / world, rem = total % world;
+    count = base + (rank < rem ? 1 : 0);
+    first = rank * base + (rank < rem ? rank : rem);
 }
 
 // ---- two-level scenes (rtb_scene_create_instanced) ----
@@ -723,16 +881,17 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
         sc->n_flat = flat_first[(size_t)ni];
         sc->num_materials = d.num_materials;
         sc->num_lights = d.num_lights;
+        Temps<BE> tmp(be);
         auto t0 = be.now();
         sc->materials = be.template alloc<rtb_material>(d.num_materials);
         be.upload(sc->materials, d.materials, d.num_materials);
         for (int i = 0; i < d.num_materials; ++i) sc->type_mask |= 1u << d.materials[i].type;
         sc->lights = be.template alloc<LightDev>(d.num_lights > 0 ? d.num_lights : 1);
-        int64_t *d_light_tri = be.template alloc<int64_t>(d.num_lights > 0 ? d.num_lights : 1);
+        int64_t *d_light_tri = tmp.template alloc<int64_t>(d.num_lights > 0 ? d.num_lights : 1);
         if (d.num_lights) { be.upload(sc->lights, lights.data(), d.num_lights); be.upload(d_light_tri, light_tri.data(), d.num_lights); }
-        float *d_vertices = be.template alloc<float>(9 * (size_t)n);
-        Tri48 *tri_in = be.template alloc<Tri48>(n);
-        TriMeta *meta_in = be.template alloc<TriMeta>(n);
+        float *d_vertices = tmp.template alloc<float>(9 * (size_t)n);
+        Tri48 *tri_in = tmp.template alloc<Tri48>(n);
+        TriMeta *meta_in = tmp.template alloc<TriMeta>(n);
         be.upload(d_vertices, d.vertices, 9 * (size_t)n);
         be.upload(meta_in, meta.data(), (size_t)n);
         sc->tris = (F4 *)be.template alloc<Tri48>(n);
@@ -752,7 +911,7 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
             mesh_nodes += trees[(size_t)m].num_nodes;
             if (trees[(size_t)m].levels > mesh_levels) mesh_levels = trees[(size_t)m].levels;
         }
-        be.free(d_vertices); be.free(tri_in); be.free(meta_in);
+        tmp.free(d_vertices); tmp.free(tri_in); tmp.free(meta_in);
         // the instances' world boxes, from the transformed vertices of their meshes, padded by more than the rounding of
         // the ray transform can move a hit point (1e-5 of the coordinates' magnitude)
         std::vector<F4> blo((size_t)ni), bhi((size_t)ni);
@@ -771,14 +930,14 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
             InstBoundsK k;
             k.a.runs = (largest + kInstBoundsRun - 1) / kInstBoundsRun;
             if ((long long)k.a.runs * ni > 0x7fffffffll) throw Error(RTB_ERR_INVALID, "too many instances x triangles for the bounds pass");
-            float *d_xf = be.template alloc<float>(xf.size());
-            int32_t *d_first = be.template alloc<int32_t>(ni), *d_count = be.template alloc<int32_t>(ni), *d_b = be.template alloc<int32_t>(6 * (size_t)ni);
+            float *d_xf = tmp.template alloc<float>(xf.size());
+            int32_t *d_first = tmp.template alloc<int32_t>(ni), *d_count = tmp.template alloc<int32_t>(ni), *d_b = tmp.template alloc<int32_t>(6 * (size_t)ni);
             be.upload(d_xf, xf.data(), xf.size()); be.upload(d_first, ifirst.data(), (size_t)ni); be.upload(d_count, icount.data(), (size_t)ni);
             be.upload(d_b, binit.data(), binit.size());
             k.a.tris = (const Tri48 *)sc->tris; k.a.xforms = d_xf; k.a.first = d_first; k.a.count = d_count; k.a.bounds = d_b; k.a.num_inst = ni;
             be.launch(k.a.runs * ni, k);
             be.download(bout.data(), d_b, bout.size());
-            be.free(d_xf); be.free(d_first); be.free(d_count); be.free(d_b);
+            tmp.free(d_xf); tmp.free(d_first); tmp.free(d_count); tmp.free(d_b);
             for (int i = 0; i < ni; ++i) {
                 float lo[3], hi[3];
                 double mag = 0.0;
@@ -795,17 +954,17 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
                 blo[(size_t)i] = l; bhi[(size_t)i] = h;
             }
         }
-        F4 *d_blo = be.template alloc<F4>(ni), *d_bhi = be.template alloc<F4>(ni);
+        F4 *d_blo = tmp.template alloc<F4>(ni), *d_bhi = tmp.template alloc<F4>(ni);
         be.upload(d_blo, blo.data(), (size_t)ni); be.upload(d_bhi, bhi.data(), (size_t)ni);
         sc->top_inst = be.template alloc<int32_t>(ni);
-        int32_t *top_leaf_of = be.template alloc<int32_t>(ni);
+        int32_t *top_leaf_of = tmp.template alloc<int32_t>(ni);
         // every instance gets a child box of its own in the top tree (leaf lists of one entry)
         // (the SAH-optimal collapse: its tie-breaking caveat concerns triangles, and it halves the top tree — S2: 57 -> 27
         // nodes, 3.55 -> 3.38 nodes per primary ray; leaf lists of 2 or 3 instances were measured worse)
         rtb_build_params tbp = bp;
         tbp.collapse = RTB_COLLAPSE_SAH_OPTIMAL;
         top = build_tree(be, ni, nullptr, nullptr, nullptr, d_blo, d_bhi, tbp, 1, nullptr, nullptr, sc->top_inst, top_leaf_of);
-        be.free(d_blo); be.free(d_bhi); be.free(top_leaf_of);
+        tmp.free(d_blo); tmp.free(d_bhi); tmp.free(top_leaf_of);
         // stack: a node group per level of both trees, plus the rest of a leaf list per level of the top tree
         if (2 * top.levels + mesh_levels >= kStackSize) throw Error(RTB_ERR_INVALID, "BVH too deep for the traversal stack");
         // one node array: the top tree, then the meshes' trees rebased
@@ -846,7 +1005,7 @@ SceneT<BE> *scene_from_instanced(BE &be, const rtb_instanced_scene_desc &D, cons
             be.launch(sc->num_lights, k);
         }
         be.sync();
-        be.free(d_light_tri);
+        tmp.free(d_light_tri);
         sc->stats = rtb_bvh_stats{};
         sc->stats.num_triangles = n;
         sc->stats.num_bvh2_nodes = 2 * (int64_t)n - nm + 2 * (int64_t)ni - 1;

@@ -4,7 +4,8 @@
 // against include/rtcuda_compat.cuh + librtb.so.  It renders a small image of
 // the scene file it is given and writes the raw float framebuffer, so the test
 // can compare it with rtb_render() on the flat description of the same scene.
-//   compat_main <scene.rtbs> <W> <H> <spp> <bounces> <out.f32>
+//   compat_main <scene.rtbs> <W> <H> <spp> <bounces> <out.f32>            main.cu-style program; RTB_DEVICES="0,1,.." spans GPUs
+//   compat_main <scene.rtbs> <W> <H> <spp> <bounces> <out.f32> multi      rtb_render_multi() on every GPU of the box (C ABI, C++ caller)
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -18,6 +19,28 @@ int main(int argc, char **argv) {
     rtb_scene_desc d;
     rtb_host_scene_desc(hs, &d);
     const int W = atoi(argv[2]), H = atoi(argv[3]), spp = atoi(argv[4]), bounces = atoi(argv[5]);
+
+    if (argc >= 8 && std::string(argv[7]) == "multi") {
+        // the one-call C entry on all GPUs of the box: contexts, concurrent scene builds, sample shards, NCCL reduce, tonemap
+        int ndev = 0;
+        CHECK_CUDA(cudaGetDeviceCount(&ndev));
+        std::vector<int32_t> devs;
+        for (int i = 0; i < ndev; ++i) devs.push_back(i);
+        rtb_camera cam;
+        const float from[3] = {0.5f, 0.5f, 1.5f}, at[3] = {0.5f, 0.5f, 0.0f}, up[3] = {0.0f, 1.0f, 0.0f};
+        rtcuda_compat::check_rtb(rtb_camera_look_at(from, at, up, 37.8f, (float)W / (float)H, &cam), "rtb_camera_look_at");
+        rtb_render_params p;
+        rtb_render_params_default(&p);
+        p.width = W; p.height = H; p.spp = spp; p.max_bounces = bounces;
+        std::vector<float> fb(3 * (size_t)W * H);
+        rtb_render_stats st;
+        rtcuda_compat::check_rtb(rtb_render_multi(devs.data(), ndev, &d, nullptr, &cam, &p, fb.data(), &st), "rtb_render_multi");
+        FILE *f = fopen(argv[6], "wb");
+        fwrite(fb.data(), sizeof(float), fb.size(), f);
+        fclose(f);
+        printf("compat_main multi: %d GPU(s), %dx%d, %d spp, %llu paths, %.2f ms\n", ndev, W, H, spp, (unsigned long long)st.paths, st.ms_total);
+        return 0;
+    }
 
     std::vector<Material> materials;
     for (int i = 0; i < d.num_materials; ++i) {
@@ -59,6 +82,8 @@ int main(int argc, char **argv) {
     }
 
     Bvh bvh(triangles, primitives);
+    printf("compat_main: Bvh built: %d primitives, %d nodes, depth %d\n", bvh.num_primitives, bvh.num_nodes, bvh.max_depth);  // bvh.cuh:203-204
+    if (bvh.num_nodes <= 0 || bvh.max_depth <= 0) return 3;
     Scene scene = {bvh, num_lights, d_lights};
     Camera camera(Vec3(0.5f, 0.5f, 1.5f), Vec3(0.5f, 0.5f, 0.0f), Vec3(0.0f, 1.0f, 0.0f), 37.8f, (float)W / (float)H);
     std::vector<Vec3> framebuffer;

@@ -21,8 +21,9 @@
 namespace rtb {
 
 struct HostBackend {
-    explicit HostBackend(int) {}
-    int device() const { return -1; }
+    int ordinal_;
+    explicit HostBackend(int ordinal) : ordinal_(ordinal) {}
+    int device() const { return -1; }  // (no GPU: device masks are not checked against it)
     void make_current() {}
     void sync() {}
     // the schedule options of the CUDA backend are accepted and remembered (they select kernels the emulation does not
@@ -52,6 +53,26 @@ struct HostBackend {
     template <class T> void download(T *dst, const T *src, size_t n) { memcpy(dst, src, sizeof(T) * n); }
     template <class T> void copy(T *dst, const T *src, size_t n) { memcpy(dst, src, sizeof(T) * n); }
     template <class T> void zero(T *p, size_t n) { memset(p, 0, sizeof(T) * n); }
+    template <class T> void copy_from(HostBackend &, T *dst, const T *src, size_t n) { memcpy(dst, src, sizeof(T) * n); }
+    // the "GPUs" of an emulated rtb_multi are HostBackend objects in one address space: a reduction is a loop
+    struct Group { int n; };
+    static Group *group_create(const std::vector<HostBackend *> &members) { return new Group{(int)members.size()}; }
+    static void group_destroy(Group *g) { delete g; }
+    template <class T>
+    static void group_reduce(Group *, const std::vector<HostBackend *> &members, const std::vector<T *> &bufs, size_t n, int root) {
+        for (size_t r = 0; r < members.size(); ++r) {  // rank order: the order NCCL's ring would not promise, but integers do not care
+            if ((int)r == root) continue;
+            for (size_t i = 0; i < n; ++i) bufs[root][i] += bufs[r][i];
+        }
+    }
+    struct Comm { int rank, world; };
+    static void comm_unique_id(uint8_t *out) { memset(out, 0, RTB_COMM_ID_BYTES); }
+    Comm *comm_create(const uint8_t *, int rank, int world) {
+        if (world != 1) throw Error(RTB_ERR_NO_DEVICE, "emu: a communicator over processes needs NCCL and GPUs");
+        return new Comm{rank, world};
+    }
+    static void comm_destroy(Comm *c) { delete c; }
+    template <class T> void comm_allreduce(Comm *, T *, size_t) {}
 
     template <class F> void launch(int n, F f) { for (int i = 0; i < n; ++i) f(i); }
     template <class F> void launch_trace(int n, F f) { launch(n, f); }

@@ -491,3 +491,19 @@ def test_bad_arguments_return_status_codes(L, ctx, s1_dev):
     h = C.c_void_p()
     assert lib.rtb_scene_create(ctx.h, C.byref(desc), None, C.byref(h)) == -1
     assert b"material id" in lib.rtb_last_error()
+
+
+@pytest.mark.parametrize("bad", [np.inf, -np.inf, np.nan, 3e38, -2e30])
+def test_non_finite_or_huge_vertices_are_rejected_not_hung(L, ctx, bad):
+    """one infinite vertex used to leave PLOC without a mutual pair for ever (the build never returned).
+    The builder now checks every vertex on the device and returns RTB_ERR_INVALID; 1e25 still builds."""
+    verts, mat, lid = small_scene_arrays(n=50)
+    v = verts.copy(); v[17, 4] = bad
+    desc, keep = make_desc(v, mat, np.full(len(mat), -1, np.int32), std_materials(), [])
+    h = C.c_void_p()
+    assert L.lib.rtb_scene_create(ctx.h, C.byref(desc), None, C.byref(h)) == -1
+    assert b"not finite" in L.lib.rtb_last_error()
+    v[17, 4] = 1e25
+    desc, keep = make_desc(v, mat, np.full(len(mat), -1, np.int32), std_materials(), [])
+    assert L.lib.rtb_scene_create(ctx.h, C.byref(desc), None, C.byref(h)) == 0
+    L.lib.rtb_scene_destroy(h)
