@@ -333,6 +333,26 @@ RTB_API int rtb_tonemap_fixed_device(rtb_context *ctx, const int64_t *d_accum_fi
 RTB_API int rtb_tonemap_device(rtb_context *ctx, const float *d_accum, int64_t num_floats,
                                int32_t total_spp, float *d_out);
 
+/* ---- progressive rendering and checkpoints (SURVEY 5 "checkpoint / resume", 8f-4; the reference writes its image
+ *      once at exit, main.cu:173-192, and its int sample counter caps one call at 258 spp in 4K, render.cuh:371) ----
+ * An rtb_accum is the accumulation buffer of one image (device memory) plus the index of the next sample: sample
+ * passes are added to it call by call (each pass renders samples [next, next + spp) of every pixel, so the passes of
+ * one image never repeat a random stream), the image so far can be resolved after any pass, and the state can be
+ * written to a file and picked up again — by another process or another day — exactly where it stopped. */
+typedef struct rtb_accum rtb_accum;
+/* deterministic != 0: 64-bit fixed-point sums (see RTB_RENDER_DETERMINISTIC): a resumed render is then bit-identical to
+ * an uninterrupted one */
+RTB_API int rtb_accum_create(rtb_context *ctx, int32_t width, int32_t height, int32_t deterministic, rtb_accum **out);
+RTB_API int rtb_accum_destroy(rtb_accum *a);
+/* adds p->spp samples; p->width / height must match, p->first_sample and p->total_spp are ignored (the buffer knows) */
+RTB_API int rtb_accum_add_samples(rtb_accum *a, rtb_scene *scene, const rtb_camera *cam, const rtb_render_params *p,
+                                  rtb_render_stats *stats);
+RTB_API int rtb_accum_samples(const rtb_accum *a);  /* samples per pixel accumulated so far */
+/* the image so far: sqrt(sum / samples), float[3*W*H], row 0 = top (as rtb_render) */
+RTB_API int rtb_accum_resolve(rtb_accum *a, float *h_rgb_out);
+RTB_API int rtb_accum_save(rtb_accum *a, const char *path);
+RTB_API int rtb_accum_load(rtb_context *ctx, const char *path, rtb_accum **out);
+
 /* ---- several GPUs of one box (the reference has no cudaSetDevice, stream or collective anywhere and
  *      its render() is not re-entrant: globals at render.cuh:25-59) ----
  * Every (pixel, sample) path is independent under the counter-based RNG, so the GPUs split the SAMPLES of every pixel

@@ -97,7 +97,8 @@ SYMBOLS = [
     "rtb_render_accumulate_fixed", "rtb_tonemap_fixed_device",
     "rtb_multi_create", "rtb_multi_destroy", "rtb_multi_size", "rtb_multi_context", "rtb_multi_scene_create",
     "rtb_multi_scene_create_instanced", "rtb_multi_scene_replicate", "rtb_multi_scene_destroy", "rtb_multi_render", "rtb_render_multi",
-    "rtb_scene_attach_lights", "rtb_comm_unique_id", "rtb_comm_create", "rtb_comm_destroy", "rtb_comm_allreduce_f32", "rtb_comm_allreduce_i64",
+    "rtb_scene_attach_lights", "rtb_accum_create", "rtb_accum_destroy", "rtb_accum_add_samples", "rtb_accum_samples",
+    "rtb_accum_resolve", "rtb_accum_save", "rtb_accum_load", "rtb_comm_unique_id", "rtb_comm_create", "rtb_comm_destroy", "rtb_comm_allreduce_f32", "rtb_comm_allreduce_i64",
 ]
 RTB_COMM_ID_BYTES = 128
 RTB_KAT_TRI_INTERSECT, RTB_KAT_OFFSET_ORIGIN, RTB_KAT_RAND4, RTB_KAT_SAMPLE_F, RTB_KAT_SLAB, RTB_KAT_SAMPLE_LI = 1, 2, 3, 4, 5, 6
@@ -471,6 +472,47 @@ class Comm:
     def close(self):
         if self.h:
             self.L.lib.rtb_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Accum:
+    """progressive accumulation buffer + sample counter (rtb_accum): add passes, resolve, save / load"""
+
+    def __init__(self, ctx, width=0, height=0, deterministic=False, path=None):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        if path is not None:
+            self.L.check(self.L.lib.rtb_accum_load(ctx.h, path.encode(), C.byref(self.h)))
+        else:
+            self.L.check(self.L.lib.rtb_accum_create(ctx.h, width, height, 1 if deterministic else 0, C.byref(self.h)))
+        self.width, self.height = width, height
+
+    @property
+    def samples(self):
+        return self.L.lib.rtb_accum_samples(self.h)
+
+    def add(self, scene, cam, params):
+        st = RenderStats()
+        self.L.check(self.L.lib.rtb_accum_add_samples(self.h, scene.h, C.byref(cam), C.byref(params), C.byref(st)))
+        return st
+
+    def resolve(self, width, height):
+        out = np.zeros((height, width, 3), np.float32)
+        self.L.check(self.L.lib.rtb_accum_resolve(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def save(self, path):
+        self.L.check(self.L.lib.rtb_accum_save(self.h, path.encode()))
+
+    def close(self):
+        if self.h:
+            self.L.lib.rtb_accum_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

@@ -347,6 +347,124 @@ int rtb_render(rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, 
 
 }  // extern "C"
 
+// ---------------------------------------------------------------- progressive rendering / checkpoints (rtb_accum)
+struct rtb_accum {
+    rtb_context *ctx = nullptr;
+    int32_t width = 0, height = 0, samples = 0;
+    bool fixed = false;
+    float *sum_f32 = nullptr;      // float[3 * W * H]
+    long long *sum_fixed = nullptr;  // int64[3 * W * H], units of 2^-28
+    int64_t values() const { return 3 * (int64_t)width * height; }
+};
+namespace rtb {
+struct AccumFileHeader {  // "RTBA", version 1
+    uint32_t magic, version;
+    int32_t width, height, samples, fixed;
+};
+inline rtb_accum *accum_new(rtb_context *ctx, int32_t w, int32_t h, bool fixed) {
+    if (!ctx || w <= 0 || h <= 0 || 3 * (int64_t)w * h > 0x7fffff00ll) throw Error(RTB_ERR_INVALID, "rtb_accum: bad image size");
+    std::unique_ptr<rtb_accum> a(new rtb_accum());
+    a->ctx = ctx; a->width = w; a->height = h; a->fixed = fixed;
+    RTB_BACKEND &be = ctx->be;
+    be.make_current();
+    be.use_stream(0);
+    if (fixed) { a->sum_fixed = be.template alloc<long long>((size_t)a->values()); be.zero(a->sum_fixed, (size_t)a->values()); }
+    else { a->sum_f32 = be.template alloc<float>((size_t)a->values()); be.zero(a->sum_f32, (size_t)a->values()); }
+    be.sync();
+    return a.release();
+}
+}  // namespace rtb
+
+extern "C" {
+int rtb_accum_create(rtb_context *ctx, int32_t w, int32_t h, int32_t deterministic, rtb_accum **out) {
+    if (!out) return rtb::set_error(RTB_ERR_INVALID, "rtb_accum_create: null out");
+    *out = nullptr;
+    return rtb::guarded([&] { *out = rtb::accum_new(ctx, w, h, deterministic != 0); });
+}
+int rtb_accum_destroy(rtb_accum *a) {
+    return rtb::guarded([&] {
+        if (!a) return;
+        a->ctx->be.make_current();
+        a->ctx->be.free(a->sum_f32); a->ctx->be.free(a->sum_fixed);
+        delete a;
+    });
+}
+int rtb_accum_samples(const rtb_accum *a) { return a ? a->samples : 0; }
+int rtb_accum_add_samples(rtb_accum *a, rtb_scene *s, const rtb_camera *cam, const rtb_render_params *p, rtb_render_stats *stats) {
+    if (!a || !s || !cam || !p) return rtb::set_error(RTB_ERR_INVALID, "rtb_accum_add_samples: null argument");
+    if (s->ctx != a->ctx) return rtb::set_error(RTB_ERR_INVALID, "rtb_accum_add_samples: scene and buffer belong to different contexts");
+    if (p->width != a->width || p->height != a->height) return rtb::set_error(RTB_ERR_INVALID, "rtb_accum_add_samples: image size differs from the buffer's");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = a->ctx->be;
+        be.make_current();
+        rtb_render_params q = *p;
+        q.first_sample = a->samples;
+        q.total_spp = 0;
+        if (a->fixed) q.flags |= RTB_RENDER_DETERMINISTIC;
+        rtb::RenderTarget t;
+        if (a->fixed) t.add_fixed = a->sum_fixed; else t.add_f32 = a->sum_f32;
+        rtb::render_accumulate(be, *s->impl, *cam, q, t, stats);
+        a->samples += p->spp;
+    });
+}
+int rtb_accum_resolve(rtb_accum *a, float *h_rgb) {
+    if (!a || !h_rgb) return rtb::set_error(RTB_ERR_INVALID, "rtb_accum_resolve: null argument");
+    if (a->samples <= 0) return rtb::set_error(RTB_ERR_INVALID, "rtb_accum_resolve: no samples yet");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = a->ctx->be;
+        be.make_current();
+        be.use_stream(0);
+        rtb::DeviceBuf<RTB_BACKEND, float> out(be, (size_t)a->values());
+        if (a->fixed) rtb::tonemap_fixed(be, a->sum_fixed, a->values(), a->samples, out.p);
+        else rtb::tonemap(be, a->sum_f32, a->values(), a->samples, out.p);
+        be.download(h_rgb, out.p, (size_t)a->values());
+    });
+}
+int rtb_accum_save(rtb_accum *a, const char *path) {
+    if (!a || !path) return rtb::set_error(RTB_ERR_INVALID, "rtb_accum_save: null argument");
+    return rtb::guarded([&] {
+        RTB_BACKEND &be = a->ctx->be;
+        be.make_current();
+        be.use_stream(0);
+        const size_t bytes = (size_t)a->values() * (a->fixed ? 8 : 4);
+        std::vector<char> host(bytes);
+        be.download(host.data(), a->fixed ? (const char *)a->sum_fixed : (const char *)a->sum_f32, bytes);
+        rtb::AccumFileHeader h{0x41425452u, 1u, a->width, a->height, a->samples, a->fixed ? 1 : 0};
+        FILE *f = fopen(path, "wb");
+        if (!f) throw rtb::Error(RTB_ERR_IO, std::string("cannot write ") + path);
+        const bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(host.data(), 1, bytes, f) == bytes;
+        if (fclose(f) != 0 || !ok) throw rtb::Error(RTB_ERR_IO, std::string("short write to ") + path);
+    });
+}
+int rtb_accum_load(rtb_context *ctx, const char *path, rtb_accum **out) {
+    if (!ctx || !path || !out) return rtb::set_error(RTB_ERR_INVALID, "rtb_accum_load: null argument");
+    *out = nullptr;
+    return rtb::guarded([&] {
+        FILE *f = fopen(path, "rb");
+        if (!f) throw rtb::Error(RTB_ERR_IO, std::string("cannot open ") + path);
+        rtb::AccumFileHeader h;
+        bool ok = fread(&h, sizeof h, 1, f) == 1 && h.magic == 0x41425452u && h.version == 1u && h.width > 0 && h.height > 0 && h.samples >= 0 &&
+                  (h.fixed == 0 || h.fixed == 1) && 3 * (int64_t)h.width * h.height <= 0x7fffff00ll;
+        std::vector<char> host;
+        if (ok) {
+            const size_t bytes = (size_t)(3 * (int64_t)h.width * h.height) * (h.fixed ? 8 : 4);
+            long here = ftell(f);
+            fseek(f, 0, SEEK_END);
+            ok = (size_t)(ftell(f) - here) == bytes;  // the header must match the file before anything is sized from it
+            fseek(f, here, SEEK_SET);
+            if (ok) { host.resize(bytes); ok = fread(host.data(), 1, bytes, f) == bytes; }
+        }
+        fclose(f);
+        if (!ok) throw rtb::Error(RTB_ERR_IO, std::string("not an accumulation checkpoint (or truncated): ") + path);
+        std::unique_ptr<rtb_accum> a(rtb::accum_new(ctx, h.width, h.height, h.fixed != 0));
+        a->samples = h.samples;
+        RTB_BACKEND &be = ctx->be;
+        be.upload(a->fixed ? (char *)a->sum_fixed : (char *)a->sum_f32, (const char *)host.data(), host.size());
+        *out = a.release();
+    });
+}
+}  // extern "C"
+
 // ---------------------------------------------------------------- several GPUs, one process (rtb_multi)
 struct rtb_multi {
     std::vector<rtb_context *> ctx;
