@@ -174,6 +174,16 @@ RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 // there) must not loosen the test on the other two.  (Round 1 first used one
 // pad 2^-21 max|c| for all three axes: such rays then passed every slab test
 // and walked whole slices of a 10 M-triangle scene; see profiles/README.md.)
+//
+// Byte -> float.  I2F.U8 runs on the quarter-rate XU pipe: 48 of them per node made XU the busiest pipe of k_trace
+// (ncu r1: XU 52 %, FMA 21 %).  RTB_NODE_CVT_HALF (device builds): two bytes at a time are placed under the exponent
+// byte 0x64 of a half2 (one PRMT on the ALU pipe: 0x6400 | q = 1024 + q exactly) and widened with HADD2.F32 on the FMA
+// pipe; the 1024 is taken out of the constant, t = (1024 + q) a + (c - 1024 a).  The computed a cancels exactly between
+// the two terms, so the only new error is the rounding of (c - 1024 a), at most 2^-24 (|c| + 1024 |a|): the pads below
+// grow by 2^-13 |a| — a ten-thousandth of one quantisation step.
+#if defined(__CUDA_ARCH__) && !defined(RTB_NODE_CVT_I2F)
+#define RTB_NODE_CVT_HALF 1
+#endif
 struct NodeFrame {
     float ax, ay, az;     // 2^e / d
     float nx, ny, nz;     // c lowered: for the entry planes
@@ -188,16 +198,56 @@ RTB_HD NodeFrame node_frame(const Q4 &n0, const RaySetup &r) {
     const float cy = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
     const float cz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
     const float k = 4.76837158203125e-07f;  // 2^-21
+#if defined(RTB_NODE_CVT_HALF)
+    // pad = 2^-21 (|c| + 256 |a|) = 2^-21 |c| + 2^-13 |a|;  base = c - 1024 a
+    const float px = fmul(ffma(fabsf(f.ax), 256.f, fabsf(cx)), k), bx = ffma(-1024.f, f.ax, cx);
+    const float py = fmul(ffma(fabsf(f.ay), 256.f, fabsf(cy)), k), by = ffma(-1024.f, f.ay, cy);
+    const float pz = fmul(ffma(fabsf(f.az), 256.f, fabsf(cz)), k), bz = ffma(-1024.f, f.az, cz);
+    f.nx = fsub(bx, px); f.fx = fadd(bx, px);
+    f.ny = fsub(by, py); f.fy = fadd(by, py);
+    f.nz = fsub(bz, pz); f.fz = fadd(bz, pz);
+#else
     f.nx = ffma(-fabsf(cx), k, cx); f.fx = ffma(fabsf(cx), k, cx);
     f.ny = ffma(-fabsf(cy), k, cy); f.fy = ffma(fabsf(cy), k, cy);
     f.nz = ffma(-fabsf(cz), k, cz); f.fz = ffma(fabsf(cz), k, cz);
+#endif
     return f;
 }
+#if defined(RTB_NODE_CVT_HALF)
+// bytes 2h and 2h+1 of w as the half2 {1024 + b(2h), 1024 + b(2h+1)}
+template <int H>
+__device__ __forceinline__ uint32_t byte_pair_half2(uint32_t w) { return __byte_perm(w, 0x64646464u, H ? 0x4342 : 0x4140); }
+// 1024 + byte J of the quadruple whose two pairs are (lo, hi), as a float
+template <int J>
+__device__ __forceinline__ float biased_byte(uint32_t lo, uint32_t hi) {
+    const uint32_t p = (J & 2) ? hi : lo;
+    float r;
+    if (J & 1) asm("{.reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, h;}" : "=f"(r) : "r"(p));
+    else asm("{.reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, l;}" : "=f"(r) : "r"(p));
+    return r;
+}
+#endif
 // The per-child meta decode is done four children at a time in packed bytes
 // (bits4 = unary triangle count or 1 for an inner child, pos4 = bit position
 // in the hit mask with the octant permutation already applied to inner
 // children), after Ylitie et al. 2017, so a hit child costs two byte
 // extracts, a shift and an OR.
+#if defined(RTB_NODE_CVT_HALF)
+struct PlanePairs { uint32_t nxl, nxh, nyl, nyh, nzl, nzh, fxl, fxh, fyl, fyh, fzl, fzh; };
+template <int J>
+__device__ __forceinline__ uint32_t child_hit_bits(const NodeFrame &f, uint32_t bits4, uint32_t pos4, const PlanePairs &q, float tmax) {
+    const float tnx = ffma(biased_byte<J>(q.nxl, q.nxh), f.ax, f.nx);
+    const float tny = ffma(biased_byte<J>(q.nyl, q.nyh), f.ay, f.ny);
+    const float tnz = ffma(biased_byte<J>(q.nzl, q.nzh), f.az, f.nz);
+    const float tfx = ffma(biased_byte<J>(q.fxl, q.fxh), f.ax, f.fx);
+    const float tfy = ffma(biased_byte<J>(q.fyl, q.fyh), f.ay, f.fy);
+    const float tfz = ffma(biased_byte<J>(q.fzl, q.fzh), f.az, f.fz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    if (tn <= fmul(tf, 1.0000019f)) return byte_of(bits4, J) << byte_of(pos4, J);
+    return 0u;
+}
+#endif
 template <int J>
 RTB_HD uint32_t child_hit_bits(const NodeFrame &f, uint32_t bits4, uint32_t pos4, uint32_t nx4, uint32_t ny4, uint32_t nz4,
                                uint32_t fx4, uint32_t fy4, uint32_t fz4, float tmax) {
@@ -235,10 +285,21 @@ RTB_HD uint32_t node_hitmask(const Q4 &n0, const Q4 &n1, const Q4 &n2, const Q4 
         const uint32_t nz4 = pz ? loz : hiz, fz4 = pz ? hiz : loz;
         uint32_t bits4, pos4;
         meta_decode4(meta4, r.octinv * 0x01010101u, bits4, pos4);
+#if defined(RTB_NODE_CVT_HALF)
+        PlanePairs q;
+        q.nxl = byte_pair_half2<0>(nx4); q.nxh = byte_pair_half2<1>(nx4); q.nyl = byte_pair_half2<0>(ny4); q.nyh = byte_pair_half2<1>(ny4);
+        q.nzl = byte_pair_half2<0>(nz4); q.nzh = byte_pair_half2<1>(nz4); q.fxl = byte_pair_half2<0>(fx4); q.fxh = byte_pair_half2<1>(fx4);
+        q.fyl = byte_pair_half2<0>(fy4); q.fyh = byte_pair_half2<1>(fy4); q.fzl = byte_pair_half2<0>(fz4); q.fzh = byte_pair_half2<1>(fz4);
+        mask |= child_hit_bits<0>(f, bits4, pos4, q, tmax);
+        mask |= child_hit_bits<1>(f, bits4, pos4, q, tmax);
+        mask |= child_hit_bits<2>(f, bits4, pos4, q, tmax);
+        mask |= child_hit_bits<3>(f, bits4, pos4, q, tmax);
+#else
         mask |= child_hit_bits<0>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
         mask |= child_hit_bits<1>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
         mask |= child_hit_bits<2>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
         mask |= child_hit_bits<3>(f, bits4, pos4, nx4, ny4, nz4, fx4, fy4, fz4, tmax);
+#endif
     }
     return mask;
 }

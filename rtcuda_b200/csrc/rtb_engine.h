@@ -105,6 +105,19 @@ struct IngestK {
         meta_in[i] = tm;
     }
 };
+// per-triangle material / light ids of a flat description -> TriMeta (material index | type << 24, light index)
+struct MetaK {
+    const int32_t *mat, *light; const rtb_material *materials; TriMeta *out; int32_t *bad; int n, num_mats, num_lights;
+    RTB_HD void operator()(int i) const {
+        if (i >= n) return;
+        const int m = mat[i], l = light ? light[i] : -1;
+        TriMeta t; t.material = 0; t.light = -1;
+        if (m < 0 || m >= num_mats) atomic_max_i(bad, 2);  // (the material error outranks the light error when a description has both)
+        else if (l >= num_lights) atomic_max_i(bad, 1);
+        else { t.material = m | (materials[m].type << 24); t.light = l < 0 ? -1 : l; }
+        out[i] = t;
+    }
+};
 // Scene{bvh, num_lights, d_lights} filled in after Bvh::Bvh (scene.cuh:4-8, main.cu:151-156): resolve the primitives'
 // light pointers against the light array now known
 struct AttachLightsK {
@@ -587,15 +600,7 @@ SceneT<BE> *scene_from_desc(BE &be, const rtb_scene_desc &d, const rtb_build_par
     const int64_t n = d.num_triangles;
     for (int i = 0; i < d.num_materials; ++i)
         if (d.materials[i].type < 0 || d.materials[i].type >= kNumMaterialTypes) throw Error(RTB_ERR_INVALID, "unknown material type");
-    std::vector<TriMeta> meta((size_t)n);
-    for (int64_t i = 0; i < n; ++i) {
-        const int m = d.material_ids[i];
-        if (m < 0 || m >= d.num_materials) throw Error(RTB_ERR_INVALID, "material id out of range");
-        const int l = d.light_ids ? d.light_ids[i] : -1;
-        if (l >= d.num_lights) throw Error(RTB_ERR_INVALID, "light id out of range");
-        meta[(size_t)i].material = m | (d.materials[m].type << 24);
-        meta[(size_t)i].light = l;
-    }
+    if (n > 0x3fffffff) throw Error(RTB_ERR_INVALID, "too many triangles (max 2^30-1)");
     std::vector<LightDev> lights((size_t)d.num_lights);
     std::vector<int64_t> light_tri((size_t)d.num_lights);
     for (int i = 0; i < d.num_lights; ++i) {
@@ -622,7 +627,24 @@ SceneT<BE> *scene_from_desc(BE &be, const rtb_scene_desc &d, const rtb_build_par
         float *d_vertices = tmp.template alloc<float>(n > 0 ? 9 * (size_t)n : 1);
         Tri48 *tri_in = tmp.template alloc<Tri48>(n > 0 ? n : 1);
         TriMeta *meta_in = tmp.template alloc<TriMeta>(n > 0 ? n : 1);
-        if (n) { be.upload(d_vertices, d.vertices, 9 * (size_t)n); be.upload(meta_in, meta.data(), (size_t)n); }
+        if (n) {
+            // the per-triangle ids go up as they are and become TriMeta records on the device, where they are also range
+            // checked (a 10 M-triangle description used to spend 30 ms of host time in that loop)
+            int32_t *d_mat = tmp.template alloc<int32_t>((size_t)n), *d_light = d.light_ids ? tmp.template alloc<int32_t>((size_t)n) : nullptr;
+            int32_t *bad = tmp.template alloc<int32_t>(1);
+            be.zero(bad, 1);
+            be.upload(d_vertices, d.vertices, 9 * (size_t)n);
+            be.upload(d_mat, d.material_ids, (size_t)n);
+            if (d_light) be.upload(d_light, d.light_ids, (size_t)n);
+            MetaK k; k.mat = d_mat; k.light = d_light; k.materials = sc->materials; k.out = meta_in; k.bad = bad;
+            k.n = (int)n; k.num_mats = d.num_materials; k.num_lights = d.num_lights;
+            be.launch((int)n, k);
+            int32_t b = 0;
+            be.download(&b, bad, 1);
+            if (b == 2) throw Error(RTB_ERR_INVALID, "material id out of range");
+            if (b == 1) throw Error(RTB_ERR_INVALID, "light id out of range");
+            tmp.free(d_mat); tmp.free(d_light); tmp.free(bad);
+        }
         build_bvh(be, *sc, d_vertices, tri_in, meta_in, d_light_tri, bp);
     } catch (...) {
         delete sc;
