@@ -56,7 +56,10 @@ constexpr int kBlock = 256;
 #define RTB_TRACE_BLOCK 128
 #endif
 constexpr int kTraceBlock = RTB_TRACE_BLOCK;
-constexpr int kTraceBlocksPerSm = 1024 / kTraceBlock;  // 32 warps per SM at 64 registers
+#ifndef RTB_TRACE_MIN_BLOCKS
+#define RTB_TRACE_MIN_BLOCKS (1024 / RTB_TRACE_BLOCK)  // 32 warps per SM at 64 registers (40 warps at 51 registers: A/B in profiles/r2)
+#endif
+constexpr int kTraceBlocksPerSm = RTB_TRACE_MIN_BLOCKS;
 
 template <class F>
 __global__ void __launch_bounds__(kBlock) k_for(int n, F f) {
@@ -92,13 +95,13 @@ __global__ void __launch_bounds__(kShadeBlock, shade_blocks_per_sm(TYPE)) k_shad
     ShadeTally tally; tally.extend = 0u; tally.shadow = 0u;
     int i = blockIdx.x * kShadeBlock + t;
     if (i < n) {
-        const size_t q = (size_t)TYPE * W.pool + (size_t)i;
+        const size_t q = (size_t)W.qbase[TYPE] + (size_t)i;
         cp_async16(&stage[0][0][t], W.ma + q); cp_async16(&stage[0][1][t], W.mb + q); cp_async16(&stage[0][2][t], W.mc + q);
     }
     asm volatile("cp.async.commit_group;");
     for (int buf = 0; i < n; i += stride, buf ^= 1) {
         if (i + stride < n) {
-            const size_t q = (size_t)TYPE * W.pool + (size_t)(i + stride);
+            const size_t q = (size_t)W.qbase[TYPE] + (size_t)(i + stride);
             cp_async16(&stage[buf ^ 1][0][t], W.ma + q); cp_async16(&stage[buf ^ 1][1][t], W.mb + q); cp_async16(&stage[buf ^ 1][2][t], W.mc + q);
         }
         asm volatile("cp.async.commit_group;");

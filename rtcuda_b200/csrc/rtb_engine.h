@@ -357,19 +357,30 @@ struct SceneT {
         }
         pool = 0; pipes = 0;
     }
+    // hit queues exist for the material types the scene HAS (an all-matte scene used to carry three unused queues,
+    // 4.8 GB at the default pool); type t's block starts at entry qbase[t] of ma / mb / mc / mis / hit_inst
+    int num_present() const { int c = 0; for (int t = 0; t < kNumMaterialTypes; ++t) c += (type_mask >> t) & 1u; return c > 0 ? c : 1; }
+    void fill_qbase(WaveState &w, int32_t p) const {
+        int slot = 0;
+        for (int t = 0; t < kNumMaterialTypes; ++t) {
+            w.qbase[t] = ((type_mask >> t) & 1u) ? slot * p : 0;  // (a type that is absent is never pushed)
+            slot += (type_mask >> t) & 1u;
+        }
+    }
     void ensure_wave(int32_t p, int np) {
         if (pool == p && pipes == np) return;
         free_wave();
+        const size_t nq = (size_t)num_present() * (size_t)p;
         for (int k = 0; k < np; ++k) {
             WaveState &w = W[k];
             w.ea = be->template alloc<F4>(p); w.eb = be->template alloc<F4>(p); w.ec = be->template alloc<F4>(p);
-            w.ma = be->template alloc<F4>(kNumMaterialTypes * (size_t)p); w.mb = be->template alloc<F4>(kNumMaterialTypes * (size_t)p);
-            w.mc = be->template alloc<F4>(kNumMaterialTypes * (size_t)p);
+            w.ma = be->template alloc<F4>(nq); w.mb = be->template alloc<F4>(nq); w.mc = be->template alloc<F4>(nq);
             w.sh_o = be->template alloc<F4>(p); w.sh_d = be->template alloc<F4>(p); w.sh_L = be->template alloc<F4>(p);
             w.c = be->template alloc<Counters>(1);
             w.pool = p;
+            fill_qbase(w, p);
             w.mis = nullptr;
-            w.hit_inst = inst ? be->template alloc<int32_t>(kNumMaterialTypes * (size_t)p) : nullptr;
+            w.hit_inst = inst ? be->template alloc<int32_t>(nq) : nullptr;
         }
         pool = p; pipes = np;
     }
@@ -1102,7 +1113,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     if (fixed) be.zero(sc.accum_fx, 3 * (size_t)pixels);  // init_framebuffer, render.cuh:61-66
     else be.zero(sc.accum, (size_t)pixels);
     for (int k = 0; k < np; ++k) {
-        if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(2 * kNumMaterialTypes * (size_t)pool);
+        if ((p.flags & RTB_RENDER_TRUE_MIS) && !sc.W[k].mis) sc.W[k].mis = be.template alloc<float>(2 * (size_t)sc.num_present() * (size_t)pool);
         W[k] = sc.W[k];
         if (!(p.flags & RTB_RENDER_TRUE_MIS)) W[k].mis = nullptr;
         W[k].env[0] = p.env_L[0]; W[k].env[1] = p.env_L[1]; W[k].env[2] = p.env_L[2];
@@ -1258,7 +1269,7 @@ struct HitGatherK {
     WaveState W; Bvh8View B; rtb_hit *hits; int32_t first, type, n;
     RTB_HD void operator()(int j) const {
         if (j >= n) return;
-        const size_t q = (size_t)type * W.pool + (size_t)j;
+        const size_t q = (size_t)W.qbase[type] + (size_t)j;
         const F4 a = W.ma[q], c = W.mc[q];
         const int tri = f2i(c.w);
         rtb_hit h;
@@ -1293,14 +1304,15 @@ void trace_wavefront(BE &be, SceneT<BE> &sc, const rtb_ray *d_rays, int64_t n, r
     int launches = 0;
     try {
         W.ea = be.template alloc<F4>(cap); W.eb = be.template alloc<F4>(cap); W.ec = be.template alloc<F4>(cap);
-        W.ma = be.template alloc<F4>(kNumMaterialTypes * (size_t)cap); W.mb = be.template alloc<F4>(kNumMaterialTypes * (size_t)cap);
-        W.mc = be.template alloc<F4>(kNumMaterialTypes * (size_t)cap);
+        const size_t nq = (size_t)sc.num_present() * (size_t)cap;
+        W.ma = be.template alloc<F4>(nq); W.mb = be.template alloc<F4>(nq); W.mc = be.template alloc<F4>(nq);
         W.sh_o = be.template alloc<F4>(cap); W.sh_d = be.template alloc<F4>(cap); W.sh_L = be.template alloc<F4>(cap);
         W.c = be.template alloc<Counters>(1);
-        W.mis = be.template alloc<float>(2 * kNumMaterialTypes * (size_t)cap);
-        W.hit_inst = sc.inst ? be.template alloc<int32_t>(kNumMaterialTypes * (size_t)cap) : nullptr;
+        W.mis = be.template alloc<float>(2 * nq);
+        W.hit_inst = sc.inst ? be.template alloc<int32_t>(nq) : nullptr;
         W.accum = be.template alloc<F4>((size_t)cap);
         W.pool = cap;
+        sc.fill_qbase(W, cap);
         if (n > 0) { MissFillK k; k.hits = d_hits; k.n = n; be.launch((int)n, k); }
         for (int64_t first = 0; first < most; first += cap) {
             const int32_t ne = (int32_t)(first < n ? (n - first < cap ? n - first : cap) : 0);

@@ -51,7 +51,7 @@ struct Counters {
 // 52 % of the shade kernel's stall samples sat on the return of the two queue-append atomics.
 struct WaveState {
     F4 *ea, *eb, *ec;
-    F4 *ma, *mb, *mc;  // [kNumMaterialTypes][pool]
+    F4 *ma, *mb, *mc;  // one block of `pool` entries per material type PRESENT in the scene; type t starts at qbase[t]
     F4 *sh_o, *sh_d, *sh_L;
     Counters *c;
     int32_t *host_done;  // mapped pinned host word (or null): lets the host poll without a stream sync
@@ -60,6 +60,7 @@ struct WaveState {
                                    // adds commute, so the image no longer depends on the order of the splats or on how the
                                    // samples were spread over wavefronts and GPUs
     int32_t pool;
+    int32_t qbase[kNumMaterialTypes];  // first entry of type t's hit queue (slot of t among the present types x pool)
     // beyond the reference (off in parity mode): per-hit {pdf of the BSDF sample that produced the ray, hit
     // distance} for RTB_RENDER_TRUE_MIS ([kNumMaterialTypes][pool], null otherwise); constant environment radiance
     float *mis;
@@ -171,10 +172,10 @@ RTB_HD void generate_body(const WaveState &W, const RenderConsts &rc, int tid) {
 // append to the hit queue of one material type (the queues are [kNumMaterialTypes][pool]); the branches keep each
 // warp-aggregated atomic among the lanes of one type
 RTB_HD int hit_queue_push(const WaveState &W, int type) {
-    if (type == RTB_MATTE) return queue_push(&W.c->n_mat[0]);
-    if (type == RTB_MIRROR) return W.pool + queue_push(&W.c->n_mat[1]);
-    if (type == RTB_GLASS) return 2 * W.pool + queue_push(&W.c->n_mat[2]);
-    return 3 * W.pool + queue_push(&W.c->n_mat[3]);
+    if (type == RTB_MATTE) return W.qbase[0] + queue_push(&W.c->n_mat[0]);
+    if (type == RTB_MIRROR) return W.qbase[1] + queue_push(&W.c->n_mat[1]);
+    if (type == RTB_GLASS) return W.qbase[2] + queue_push(&W.c->n_mat[2]);
+    return W.qbase[3] + queue_push(&W.c->n_mat[3]);
 }
 RTB_HD void extend_miss(const WaveState &W, uint32_t pixel, V3 beta) {  // environment light, rtb_render_params.env_L
     const V3 L = vmul(beta, v3(W.env[0], W.env[1], W.env[2]));
@@ -217,7 +218,7 @@ RTB_HD void extend_body(const WaveState &W, const SceneView &S, int qi) {
 template <int TYPE, bool EXT = true>
 RTB_HD void shade_item(const WaveState &W, const SceneView &S, const RenderConsts &rc, bool shadows, int tid, const F4 &a,
                        const F4 &b, const F4 &hr, ShadeTally &tally) {
-    const int q = TYPE * W.pool + tid;
+    const int q = W.qbase[TYPE] + tid;
     PathStepIn in;
     in.wo = xyz(a);
     in.hit.t = 0.f; in.hit.u = hr.y; in.hit.v = hr.z; in.hit.tri = f2i(hr.w);
@@ -267,7 +268,7 @@ RTB_HD void shade_item(const WaveState &W, const SceneView &S, const RenderConst
 }
 template <int TYPE, bool EXT = true>
 RTB_HD void shade_body(const WaveState &W, const SceneView &S, const RenderConsts &rc, bool shadows, int tid, ShadeTally &tally) {
-    const int q = TYPE * W.pool + tid;
+    const int q = W.qbase[TYPE] + tid;
     const F4 a = ldg(W.ma + q), b = ldg(W.mb + q), hr = ldg(W.mc + q);
     shade_item<TYPE, EXT>(W, S, rc, shadows, tid, a, b, hr, tally);
 }
