@@ -160,7 +160,7 @@ RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 // = q*a + c with a = 2^e/d and c = (origin_node - origin_ray)/d: one
 // integer->float conversion (I2F.U8 with a byte selector) and one FMA per
 // plane.  (A byte permute into the mantissa instead of the conversion was
-// measured 1.4-2x slower on the B200: profiles/r1_variants.md.)
+// measured 1.4-2x slower on the B200: profiles/r1/r1_variants.md.)
 //
 // The test is CONSERVATIVE: it never culls a box the exact reference triangle
 // test (triangle.cuh:39-58) could still hit inside.  Error of the computed t:
@@ -173,7 +173,7 @@ RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 // depends on that axis alone: a ray almost parallel to one axis (|c| huge
 // there) must not loosen the test on the other two.  (Round 1 first used one
 // pad 2^-21 max|c| for all three axes: such rays then passed every slab test
-// and walked whole slices of a 10 M-triangle scene; see profiles/README.md.)
+// and walked whole slices of a 10 M-triangle scene; see profiles/r1/README.md.)
 //
 // Byte -> float.  I2F.U8 runs on the quarter-rate XU pipe: 48 of them per node made XU the busiest pipe of k_trace
 // (ncu r1: XU 52 %, FMA 21 %).  RTB_NODE_CVT_HALF (device builds): two bytes at a time are placed under the exponent
@@ -308,7 +308,7 @@ constexpr int kStackSize = 48;
 // The traversal stack: two dynamically indexed arrays in LOCAL memory.  Its top entries live in L1 (write-back), a
 // push or pop is one STL / LDL pair per node group that leaves siblings behind; the scalar state of the traversal
 // stays in registers because the arrays are outside the Traversal struct.  (rtb_cuda.cu has a variant that keeps the
-// first entries in shared memory, HybridStack: measured, not the default — profiles/README.md.)
+// first entries in shared memory, HybridStack: measured, not the default — profiles/r1/README.md.)
 struct LocalStack {
     uint32_t x[kStackSize], y[kStackSize];
     RTB_HD void put(int i, uint32_t a, uint32_t b) { x[i] = a; y[i] = b; }

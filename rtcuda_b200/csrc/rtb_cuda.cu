@@ -51,7 +51,7 @@ constexpr int kBlock = 256;
 // the SM (8 / W blocks of 128 threads, trace_grid()), so that the wavefronts really run side by side — one's
 // issue-bound traversal next to another's DRAM-bound shading (128-thread shade blocks fit the registers left):
 // two wavefronts C2 37.4 -> 35.4 ms, C4 37.6 -> 29.2 ms, C1 3.34 -> 2.97 ms; four 34.9 / 27.5 / 2.92 ms
-// (profiles/README.md, sessions 74-77).
+// (profiles/r1/README.md, sessions 74-77).
 #ifndef RTB_TRACE_BLOCK
 #define RTB_TRACE_BLOCK 128
 #endif
@@ -132,7 +132,7 @@ struct FetchTuning {
     int tri_step;  // own-lane triangle tests: 0 = all of a node's triangles at once, k = at most k per step (the rest carries over)
 };
 
-// Pooled triangle tests (POOL).  ncu r1 (profiles/r1_ncu_full_big_launches_session6.txt and the
+// Pooled triangle tests (POOL).  ncu r1 (profiles/r1/r1_ncu_full_big_launches_session6.txt and the
 // source page of the same capture): the node step ran with 24 of 32 lanes but the per-ray triangle
 // loop with 5-8, and took 31 % of the issue slots of k_extend for ~1 triangle per ray and step.
 // With POOL the hit triangles of all the rays of a warp are gathered in shared memory after every
@@ -358,7 +358,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
                 // lane's long triangle list no longer idles the rest of the warp
                 if (has && ty == 0u) T.node_part(S.bvh, st, tx, ty);
                 // tri_step 2 (default): both triangles are fetched and tested together — the loads of the second overlap the
-                // arithmetic of the first (C3 105.0 -> 100.0 ms, C2 / C4 unchanged: profiles/README.md, session 64) — and the
+                // arithmetic of the first (C3 105.0 -> 100.0 ms, C2 / C4 unchanged: profiles/r1/README.md, session 64) — and the
                 // accept rule then runs on them in list order, so the ray's own order of events is what it was
                 if (tune.tri_step == 2) {
                   if (ty != 0u) {
@@ -402,7 +402,7 @@ __device__ __forceinline__ void persistent_trace(WarpScratch &ws, const WaveStat
 // extend and shadow rays of one iteration in ONE launch (WHICH = 3): a warp that runs out of extend
 // rays goes on with shadow rays, so the tail of the first queue overlaps the start of the second.
 // WHICH = 1 / 2: extend / shadow only (A/B, and per-stage timing).
-// Triangle tests, three schedules (profiles/README.md): each lane walks all the triangles of its node at once
+// Triangle tests, three schedules (profiles/r1/README.md): each lane walks all the triangles of its node at once
 // (tri_step 0); at most tri_step per step, the rest carried over (default, 2: C2 39.5 -> 39.1 ms, C3 116.5 ->
 // 108.9 ms); pooled per warp in shared memory (POOL, RTB_POOLED=1: C3 113.5 ms, C2 47.9 ms).
 // Tried and dropped: prefetching the next node into L2 during the triangle tests (C3 116 -> 140 ms, C2 40 -> 49 ms).
