@@ -238,7 +238,7 @@ RTB_API int rtb_context_device(const rtb_context *ctx);
  * NUM_WORKING_PATHS, constant.hpp:8).  Every schedule gives bit-identical hits; the defaults are the measured best
  * (DESIGN.md 4).  Names: "refill" (1..32), "chunk" (>= 32), "prefetch" (0/1), "tri_step" (0..4), "pooled" (-1/0/1),
  * "fused" (0/1), "smem_stack" (0/1), "pipelines" (0 = by scene size, 1..4), "pool" (path slots, >= 1024),
- * "ploc_tail" (0/1), "trace_blocks" (0 = auto, 1..8 resident blocks per SM).  Unknown names / values out of range:
+ * "ploc_tail" (0/1), "nn_tiled" (0/1), "trace_blocks" (0 = auto, 1..8 resident blocks per SM).  Unknown names / values out of range:
  * RTB_ERR_INVALID.  Takes effect for scenes built and renders started afterwards. */
 RTB_API int rtb_context_set_option(rtb_context *ctx, const char *name, int64_t value);
 RTB_API int rtb_context_get_option(const rtb_context *ctx, const char *name, int64_t *value);

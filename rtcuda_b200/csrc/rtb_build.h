@@ -141,9 +141,15 @@ struct PlocArgs {
     int32_t *cout;        // after merge: node index or -1
     int32_t *nn;          // nearest neighbour position
     int32_t *node_counter;  // next free inner node, starts at n
-    int32_t ncl;          // current cluster count
+    int32_t ncl;          // current cluster count — or, with ncl_dev set, an upper bound of it known to the host
     int32_t radius;
+    // device-driven rounds (round 2): the count lives in device memory, the host enqueues several rounds without
+    // reading it back (every PLOC round used to cost a device->host copy of the count and a stream synchronisation)
+    const int32_t *ncl_dev;  // null: ncl is the count
+    int32_t *log;            // [round] = cluster count at the start of that round (null: not kept)
+    int32_t round;
 };
+RTB_HD int ploc_ncl(const PlocArgs &a) { return a.ncl_dev ? *a.ncl_dev : a.ncl; }
 RTB_HD void ploc_leaf_body(const F4 *prim_lo, const F4 *prim_hi, const int32_t *sorted, B2Node *nodes,
                            int32_t *count, int32_t *clusters, int n, int i) {
     if (i >= n) return;
@@ -159,12 +165,14 @@ RTB_HD void ploc_leaf_body(const F4 *prim_lo, const F4 *prim_hi, const int32_t *
 // nearest neighbour by merged surface area within +-radius positions; ties go
 // to the lowest position, which guarantees at least one mutual pair per round
 RTB_HD void ploc_nn_body(const PlocArgs &a, int i) {
-    if (i >= a.ncl) return;
+    const int ncl = ploc_ncl(a);
+    if (i == 0 && a.log) a.log[a.round] = ncl;
+    if (i >= ncl) return;
     const B2Node me = a.nodes[a.cin[i]];
     float best = FLT_MAX;
     int bj = -1;
     const int j0 = i - a.radius < 0 ? 0 : i - a.radius;
-    const int j1 = i + a.radius > a.ncl - 1 ? a.ncl - 1 : i + a.radius;
+    const int j1 = i + a.radius > ncl - 1 ? ncl - 1 : i + a.radius;
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
         const float ar = union_half_area(me, a.nodes[a.cin[j]]);
@@ -173,7 +181,10 @@ RTB_HD void ploc_nn_body(const PlocArgs &a, int i) {
     a.nn[i] = bj;
 }
 RTB_HD void ploc_merge_body(const PlocArgs &a, int n_leaves, int i) {
-    if (i >= a.ncl) return;
+    if (i >= ploc_ncl(a)) {
+        if (i < a.ncl) a.cout[i] = -1;  // between the count and the host's bound: dropped by the compaction over the bound
+        return;
+    }
     const int j = a.nn[i];
     const int ci = a.cin[i];
     if (j >= 0 && a.nn[j] == i) {
@@ -296,14 +307,15 @@ struct CollapseArgs {
     int32_t *leaf_of_prim;     // caller index -> leaf order
     int32_t *node_counter;     // next free wide node (root = 0 pre-allocated)
     int32_t *tri_counter;
-    const WorkItem *work_in; int32_t n_in;
+    const WorkItem *work_in; int32_t n_in;  // (n_in_dev set: n_in is unused)
+    const int32_t *n_in_dev;                // work items of this level, in device memory: levels are enqueued without reading it back
     WorkItem *work_out; int32_t *n_out;
     float *sah;                // accumulated SAH cost (unnormalised)
     int32_t max_leaf;          // 1..3
 };
 
 RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
-    if (tid >= a.n_in) return;
+    if (tid >= (a.n_in_dev ? *a.n_in_dev : a.n_in)) return;
     const WorkItem item = a.work_in[tid];
     const B2Node self = a.nodes[item.b2];
     int ch[8];

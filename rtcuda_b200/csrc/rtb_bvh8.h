@@ -167,9 +167,11 @@ RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 // c carries two roundings and the 1-ulp reciprocal (|dc| <= 2^-22 |c|), a is
 // exact up to the reciprocal, the FMA rounds once; so per AXIS
 //   |t - t_exact| <= 2^-22 |c_axis| + 2^-21 |t|.
-// The absolute part is folded into the constant of the FMA — near planes use
-// c - 2^-21|c|, far planes c + 2^-21|c| (twice the bound) — and the relative
-// part into the final comparison tn <= tf * (1 + 2^-19).  The pad of an axis
+// Both parts are folded into the constant of the FMA — near planes use c - pad,
+// far planes c + pad with pad = 3 * 2^-21 (|c| + 256 |a|) (node_frame: twice the
+// absolute bound plus twice the relative one, |t| <= |c| + 255 |a|) — so the
+// final comparison is plain tn <= tf.  (Until round 2 the relative part sat in
+// the comparison, tn <= tf * (1 + 2^-19): one FMUL per child.)  The pad of an axis
 // depends on that axis alone: a ray almost parallel to one axis (|c| huge
 // there) must not loosen the test on the other two.  (Round 1 first used one
 // pad 2^-21 max|c| for all three axes: such rays then passed every slab test
@@ -184,6 +186,11 @@ RTB_HD uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xffu; }
 #if defined(__CUDA_ARCH__) && !defined(RTB_NODE_CVT_I2F)
 #define RTB_NODE_CVT_HALF 1
 #endif
+#if defined(RTB_NODE_REL_PAD)
+#define RTB_NODE_TF(tf) fmul(tf, 1.0000019f)
+#else
+#define RTB_NODE_TF(tf) (tf)
+#endif
 struct NodeFrame {
     float ax, ay, az;     // 2^e / d
     float nx, ny, nz;     // c lowered: for the entry planes
@@ -197,20 +204,27 @@ RTB_HD NodeFrame node_frame(const Q4 &n0, const RaySetup &r) {
     const float cx = fmul(fsub(u2f(n0.x), r.o.x), r.idir.x);
     const float cy = fmul(fsub(u2f(n0.y), r.o.y), r.idir.y);
     const float cz = fmul(fsub(u2f(n0.z), r.o.z), r.idir.z);
-    const float k = 4.76837158203125e-07f;  // 2^-21
+    // pad = 3 * 2^-21 (|c| + 256 |a|): 2^-21 (|c| + 256 |a|) for the absolute part (twice the bound above, the 256 |a|
+    // covering the rounding of c - 1024 a) plus 2^-20 (|c| + 256 |a|) >= 2 * 2^-21 |t| for the relative part, since
+    // |t| = |q a + c| <= |c| + 255 |a|.  Round 1 kept the relative part in the comparison (tn <= tf * (1 + 2^-19)): one
+    // FMUL per child and node; folded into the constants it costs nothing per child and at most a third of a
+    // quantisation step of extra box for a node a thousand times smaller than its distance.
+#if defined(RTB_NODE_REL_PAD)
+    const float k = 4.76837158203125e-07f;  // 2^-21 (A/B: relative part in the comparison)
+#else
+    const float k = 1.430511474609375e-06f;  // 3 * 2^-21
+#endif
+    const float px = fmul(ffma(fabsf(f.ax), 256.f, fabsf(cx)), k);
+    const float py = fmul(ffma(fabsf(f.ay), 256.f, fabsf(cy)), k);
+    const float pz = fmul(ffma(fabsf(f.az), 256.f, fabsf(cz)), k);
 #if defined(RTB_NODE_CVT_HALF)
-    // pad = 2^-21 (|c| + 256 |a|) = 2^-21 |c| + 2^-13 |a|;  base = c - 1024 a
-    const float px = fmul(ffma(fabsf(f.ax), 256.f, fabsf(cx)), k), bx = ffma(-1024.f, f.ax, cx);
-    const float py = fmul(ffma(fabsf(f.ay), 256.f, fabsf(cy)), k), by = ffma(-1024.f, f.ay, cy);
-    const float pz = fmul(ffma(fabsf(f.az), 256.f, fabsf(cz)), k), bz = ffma(-1024.f, f.az, cz);
+    const float bx = ffma(-1024.f, f.ax, cx), by = ffma(-1024.f, f.ay, cy), bz = ffma(-1024.f, f.az, cz);  // base = c - 1024 a
+#else
+    const float bx = cx, by = cy, bz = cz;
+#endif
     f.nx = fsub(bx, px); f.fx = fadd(bx, px);
     f.ny = fsub(by, py); f.fy = fadd(by, py);
     f.nz = fsub(bz, pz); f.fz = fadd(bz, pz);
-#else
-    f.nx = ffma(-fabsf(cx), k, cx); f.fx = ffma(fabsf(cx), k, cx);
-    f.ny = ffma(-fabsf(cy), k, cy); f.fy = ffma(fabsf(cy), k, cy);
-    f.nz = ffma(-fabsf(cz), k, cz); f.fz = ffma(fabsf(cz), k, cz);
-#endif
     return f;
 }
 #if defined(RTB_NODE_CVT_HALF)
@@ -244,7 +258,7 @@ __device__ __forceinline__ uint32_t child_hit_bits(const NodeFrame &f, uint32_t 
     const float tfz = ffma(biased_byte<J>(q.fzl, q.fzh), f.az, f.fz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-    if (tn <= fmul(tf, 1.0000019f)) return byte_of(bits4, J) << byte_of(pos4, J);
+    if (tn <= RTB_NODE_TF(tf)) return byte_of(bits4, J) << byte_of(pos4, J);
     return 0u;
 }
 #endif
@@ -259,7 +273,7 @@ RTB_HD uint32_t child_hit_bits(const NodeFrame &f, uint32_t bits4, uint32_t pos4
     const float tfz = ffma((float)byte_of(fz4, J), f.az, f.fz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.f));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-    if (tn <= fmul(tf, 1.0000019f)) return byte_of(bits4, J) << byte_of(pos4, J);
+    if (tn <= RTB_NODE_TF(tf)) return byte_of(bits4, J) << byte_of(pos4, J);
     return 0u;
 }
 // meta4 -> (bits4, pos4) for four children at once

@@ -443,20 +443,62 @@ __global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S
     if (i < W.c->n_shadow) shadow_body<COUNT>(W, S, i);
 }
 
+// Nearest-neighbour search of one PLOC round (ploc_nn_body) with the cluster boxes of a block's window staged in
+// shared memory: every cluster compares itself with 2 x radius neighbours, so the one-thread-per-cluster form reads
+// 32 boxes of 32 bytes through the cluster index for every thread — 8.1 of the 17.7 ms of kernel time of a
+// 10 M-triangle build (profiles/r2/r2_launches_c3s_session5.csv).  Same arithmetic, same tie rule, same result.
+constexpr int kNnBlock = 256, kNnMaxRadius = 64;
+__global__ void __launch_bounds__(kNnBlock) k_ploc_nn_tiled(PlocArgs a) {
+    __shared__ float lox[kNnBlock + 2 * kNnMaxRadius], loy[kNnBlock + 2 * kNnMaxRadius], loz[kNnBlock + 2 * kNnMaxRadius];
+    __shared__ float hix[kNnBlock + 2 * kNnMaxRadius], hiy[kNnBlock + 2 * kNnMaxRadius], hiz[kNnBlock + 2 * kNnMaxRadius];
+    const int ncl = ploc_ncl(a);
+    const int b0 = blockIdx.x * kNnBlock, first = b0 - a.radius;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.log) a.log[a.round] = ncl;
+    if (b0 >= ncl) return;  // (the grid covers the host's bound of the count)
+    const int span = kNnBlock + 2 * a.radius;
+    for (int t = threadIdx.x; t < span; t += kNnBlock) {
+        const int j = first + t;
+        if (j >= 0 && j < ncl) {
+            const B2Node b = a.nodes[a.cin[j]];
+            lox[t] = b.lox; loy[t] = b.loy; loz[t] = b.loz; hix[t] = b.hix; hiy[t] = b.hiy; hiz[t] = b.hiz;
+        }
+    }
+    __syncthreads();
+    const int i = b0 + threadIdx.x;
+    if (i >= ncl) return;
+    const int ti = threadIdx.x + a.radius;
+    B2Node me;
+    me.lox = lox[ti]; me.loy = loy[ti]; me.loz = loz[ti]; me.hix = hix[ti]; me.hiy = hiy[ti]; me.hiz = hiz[ti];
+    float best = FLT_MAX;
+    int bj = -1;
+    const int j0 = i - a.radius < 0 ? 0 : i - a.radius;
+    const int j1 = i + a.radius > ncl - 1 ? ncl - 1 : i + a.radius;
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const int t = j - first;
+        B2Node o;
+        o.lox = lox[t]; o.loy = loy[t]; o.loz = loz[t]; o.hix = hix[t]; o.hiy = hiy[t]; o.hiz = hiz[t];
+        const float ar = union_half_area(me, o);
+        if (bj < 0 || ar < best) { best = ar; bj = j; }
+    }
+    a.nn[i] = bj;
+}
+
 // All remaining PLOC rounds in ONE launch once the clusters fit a thread block: cluster list, nearest neighbours and
 // merge results live in shared memory, the same round bodies (rtb_build.h) run between block barriers, the
-// order-preserving compaction is a block scan.  out[0] = rounds run, out[1] = root node, out[2 + r] = nodes made by round r.
+// order-preserving compaction is a block scan.  out[0] = rounds run, out[1] = root node, counts[r] = nodes made by round r.
 constexpr int kPlocTail = 1024;
-__global__ void __launch_bounds__(kPlocTail) k_ploc_tail(PlocArgs a, int n_leaves, int32_t *out) {
+__global__ void __launch_bounds__(kPlocTail) k_ploc_tail(PlocArgs a, int n_leaves, int32_t *out, int32_t *counts) {
     __shared__ int32_t cin[kPlocTail], cout[kPlocTail], nn[kPlocTail];
     typedef cub::BlockScan<int, kPlocTail> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     const int t = threadIdx.x;
-    int n = a.ncl;
+    int n = ploc_ncl(a);
+    if (n > kPlocTail) { if (t == 0) { out[0] = -1; out[1] = -1; } return; }  // (the host launches it on a bound <= kPlocTail)
     if (t < n) cin[t] = a.cin[t];
     __syncthreads();
     PlocArgs b = a;
-    b.cin = cin; b.cout = cout; b.nn = nn;
+    b.cin = cin; b.cout = cout; b.nn = nn; b.ncl_dev = nullptr; b.log = nullptr;
     int rounds = 0;
     while (n > 1) {
         b.ncl = n;
@@ -470,7 +512,7 @@ __global__ void __launch_bounds__(kPlocTail) k_ploc_tail(PlocArgs a, int n_leave
         Scan(scan_tmp).ExclusiveSum(flag, pos, total);
         __syncthreads();
         if (flag) cin[pos] = v;
-        if (t == 0) out[2 + rounds] = n - total;
+        if (t == 0) counts[rounds] = n - total;
         const bool stuck = total >= n;  // a round that merged nothing would spin here for ever (cannot happen with finite boxes)
         n = total;
         ++rounds;
@@ -478,6 +520,12 @@ __global__ void __launch_bounds__(kPlocTail) k_ploc_tail(PlocArgs a, int n_leave
         if (stuck) break;
     }
     if (t == 0) { out[0] = n > 1 ? -1 : rounds; out[1] = cin[0]; }
+}
+
+__global__ void __launch_bounds__(kBlock) k_collapse_level(CollapseArgs a, int32_t *zero, int32_t *levels) {
+    const int n = *a.n_in_dev;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *zero = 0; if (n > 0) *levels += 1; }
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) collapse_body(a, i);
 }
 
 // NCCL, loaded on first use.  A process that already holds a libnccl.so.2 (torch brings its own) gets that one.
@@ -535,7 +583,6 @@ struct CudaBackend {
     int trace_blocks_per_sm_ = 1, trace_cap_ = 0, active_pipelines_ = 1;
     void *cub_temp_ = nullptr;
     size_t cub_temp_bytes_ = 0;
-    int32_t *d_count_ = nullptr;
     int32_t *h_done_ = nullptr, *d_done_ = nullptr;  // mapped pinned word raised by k_control
     FetchTuning tune_{24, 128, 1, 2};  // RTB_REFILL / RTB_CHUNK / RTB_PREFETCH override (tuning runs)
     int pooled_ = 0;  // RTB_POOLED: pooled triangle tests (1), each ray's lane on its own (0, default), by scene size (-1)
@@ -543,6 +590,7 @@ struct CudaBackend {
     int smem_stack_ = 0;  // "smem_stack": first stack entries in shared memory (A/B, k_trace_smem_stack)
     int pool_ = 1 << 25;    // default path pool, RTB_POOL overrides (tuning)
     int ploc_tail_off_ = 0; // RTB_PLOC_TAIL=0: every PLOC round its own launches (A/B)
+    int nn_tiled_off_ = 0;  // "nn_tiled" = 0: nearest-neighbour search of a PLOC round one thread per cluster from global memory (A/B)
 
     explicit CudaBackend(int device) {
         int count = 0;
@@ -583,7 +631,7 @@ struct CudaBackend {
         // tuning runs (tools/sweep.py) may preset the options of rtb_context_set_option through the environment:
         // RTB_<NAME IN CAPITALS>=value, read once here; the ABI call is the documented way
         static const char *const names[] = {"refill", "chunk", "prefetch", "tri_step", "pooled", "fused", "smem_stack", "pipelines", "pool",
-                                            "ploc_tail", "trace_blocks"};
+                                            "ploc_tail", "trace_blocks", "nn_tiled"};
         for (const char *nm : names) {
             std::string env = "RTB_";
             for (const char *c = nm; *c; ++c) env += (char)toupper((unsigned char)*c);
@@ -599,7 +647,7 @@ struct CudaBackend {
         stream_ = streams_[0];
         for (int k = 0; k < kMaxPipelines; ++k) if (streams_[k]) cudaStreamSynchronize(streams_[k]);
         if (cub_temp_) cudaFreeAsync(cub_temp_, stream_);
-        if (d_count_) cudaFreeAsync(d_count_, stream_);
+        if (tail_counts_) cudaFreeAsync(tail_counts_, stream_);
         if (h_done_) cudaFreeHost(h_done_);
         if (sync_ev_) cudaEventDestroy(sync_ev_);
         for (int k = 0; k < kMaxPipelines; ++k) if (streams_[k]) { cudaStreamSynchronize(streams_[k]); cudaStreamDestroy(streams_[k]); }
@@ -622,6 +670,7 @@ struct CudaBackend {
         else if (name == "pool") { if (!in(1024, 1ll << 30)) return false; pool_ = (int)v; }
         else if (name == "ploc_tail") { if (!in(0, 1)) return false; ploc_tail_off_ = v == 0; }
         else if (name == "trace_blocks") { if (!in(0, trace_blocks_per_sm_)) return false; trace_cap_ = (int)v; }
+        else if (name == "nn_tiled") { if (!in(0, 1)) return false; nn_tiled_off_ = v == 0; }
         else return false;
         return true;
     }
@@ -637,6 +686,7 @@ struct CudaBackend {
         else if (name == "pool") v = pool_;
         else if (name == "ploc_tail") v = ploc_tail_off_ ? 0 : 1;
         else if (name == "trace_blocks") v = trace_cap_;
+        else if (name == "nn_tiled") v = nn_tiled_off_ ? 0 : 1;
         else return false;
         return true;
     }
@@ -826,32 +876,41 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_temp_, bytes, dk, dv, n, 0, 63, stream_));
         if (dk.Current() != keys) copy(keys, dk.Current(), n);
         if (dv.Current() != vals) copy(vals, dv.Current(), n);
-        sync();
-        free(k2); free(v2);
+        free(k2); free(v2);  // (stream-ordered: released when the copies above have run)
     }
-    bool ploc_tail(const PlocArgs &a, int n_leaves, std::vector<int> &round_counts, int32_t &root) {
-        if (a.ncl > kPlocTail || ploc_tail_off_) return false;
-        int32_t *d_out = alloc<int32_t>(2 + kPlocTail);
-        k_ploc_tail<<<1, kPlocTail, 0, stream_>>>(a, n_leaves, d_out);
+    void ploc_nn(const PlocArgs &a) {
+        if (a.ncl <= 0) return;
+        if (a.radius > kNnMaxRadius || nn_tiled_off_) { PlocNnK k; k.a = a; launch(a.ncl, k); return; }
+        k_ploc_nn_tiled<<<(a.ncl + kNnBlock - 1) / kNnBlock, kNnBlock, 0, stream_>>>(a);
         RTB_CUDA_CHECK(cudaGetLastError());
-        std::vector<int32_t> h(2 + kPlocTail);
-        download(h.data(), d_out, h.size());
-        free(d_out);
-        if (h[0] < 0) throw Error(RTB_ERR_INVALID, "internal: a PLOC round merged nothing");
-        round_counts.assign(h.begin() + 2, h.begin() + 2 + h[0]);
-        root = h[1];
+    }
+    // all remaining rounds in one launch once the host's bound of the cluster count fits a thread block; out[0] = rounds
+    // (-1: a round merged nothing), out[1] = root, ploc_tail_counts()[r] = nodes made by round r — all left on the device
+    int32_t *tail_counts_ = nullptr;
+    int32_t *ploc_tail_counts() {
+        if (!tail_counts_) tail_counts_ = alloc<int32_t>(kPlocTail);
+        return tail_counts_;
+    }
+    bool ploc_tail(const PlocArgs &a, int n_leaves, int32_t *d_out) {
+        if (a.ncl > kPlocTail || ploc_tail_off_) return false;
+        k_ploc_tail<<<1, kPlocTail, 0, stream_>>>(a, n_leaves, d_out, ploc_tail_counts());
+        RTB_CUDA_CHECK(cudaGetLastError());
         return true;
     }
-    int compact_nonneg(const int32_t *in, int32_t *out, int n) {
-        if (!d_count_) d_count_ = alloc<int32_t>(1);
-        int32_t *d_count = d_count_;
+    // order-preserving compaction of the entries >= 0 of in[0, n) into out; their number goes to *d_count (device memory)
+    void compact_nonneg(const int32_t *in, int32_t *out, int n, int32_t *d_count) {
         size_t bytes = 0;
         RTB_CUDA_CHECK(cub::DeviceSelect::If(nullptr, bytes, in, out, d_count, n, NonNegative(), stream_));
         ensure_temp(bytes);
         RTB_CUDA_CHECK(cub::DeviceSelect::If(cub_temp_, bytes, in, out, d_count, n, NonNegative(), stream_));
-        int32_t c = 0;
-        download(&c, d_count, 1);
-        return c;
+    }
+    // one level of the collapse over the work items counted in device memory (k.a.n_in_dev): a resident grid strides
+    // over them; *zero is cleared for the level after the next, *levels counts the levels that had work
+    void collapse_level(const CollapseK &k, int bound, int32_t *zero, int32_t *levels) {
+        int grid = (bound + kBlock - 1) / kBlock;
+        if (grid > num_sms_ * 8) grid = num_sms_ * 8;
+        k_collapse_level<<<grid, kBlock, 0, stream_>>>(k.a, zero, levels);
+        RTB_CUDA_CHECK(cudaGetLastError());
     }
 
     using Time = cudaEvent_t;

@@ -418,6 +418,22 @@ struct AddK {
     int32_t *p; int32_t v; int n;
     RTB_HD void operator()(int i) const { if (i < n) p[i] += v; }
 };
+// Small constants for the build's counters, written by a kernel: an upload from a host temporary has to synchronise
+// the stream before it returns (be.upload), and the build used to do five of them.
+struct FillI32K {
+    int32_t *p; int32_t v[24]; int n;
+    RTB_HD void operator()(int i) const { if (i < n) p[i] = v[i]; }
+};
+struct RootItemK {  // the collapse starts from the root of the binary tree, which only the device knows
+    const int32_t *root_src; WorkItem *dst;
+    RTB_HD void operator()(int i) const { if (i == 0) { WorkItem r; r.b2 = *root_src; r.wide = 0; dst[0] = r; } }
+};
+// layout of the build's one block of counters (int32 unless noted): what the host reads back comes in ONE copy at the end
+enum BuildCtr {
+    kCtrB2 = 0, kCtrWide = 1, kCtrTri = 2, kCtrNcl = 4, kCtrLevels = 5, kCtrLvl0 = 6 /* 6,7,8: work items of a level, rotating */,
+    kCtrSah = 9 /* float */, kCtrBounds = 16 /* 16..21 ordered floats, 22 = bad vertex */, kCtrTail = 24 /* 24: tail rounds, 25: root */, kCtrCount = 32
+};
+constexpr int kMaxPlocLog = 1 << 16;
 template <class BE>
 BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriMeta *meta_in, const F4 *box_lo, const F4 *box_hi,
                      const rtb_build_params &bp, int max_leaf, Tri48 *tris_out, TriMeta *meta_out, int32_t *prim_out,
@@ -428,12 +444,16 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     const int radius = bp.ploc_radius > 0 ? bp.ploc_radius : 16;
     // 1. per-triangle records, bounds
     F4 *prim_lo = tmp.template alloc<F4>(n), *prim_hi = tmp.template alloc<F4>(n);
-    int32_t *bounds = tmp.template alloc<int32_t>(7);  // [6] = "a vertex is not finite / out of range"
+    int32_t *ctr = tmp.template alloc<int32_t>(kCtrCount);
+    int32_t *bounds = ctr + kCtrBounds;  // [6] = "a vertex is not finite / out of range"
+    float *sah = (float *)(ctr + kCtrSah);
     {
-        int32_t init[7];
-        for (int k = 0; k < 3; ++k) { init[k] = float_to_ordered(FLT_MAX); init[3 + k] = float_to_ordered(-FLT_MAX); }
-        init[6] = 0;
-        be.upload(bounds, init, 7);
+        FillI32K f; f.p = ctr; f.n = kCtrCount;
+        for (int k = 0; k < 24; ++k) f.v[k] = 0;
+        f.n = 24;  // (the tail's words are written by its kernel)
+        f.v[kCtrB2] = n; f.v[kCtrWide] = 1; f.v[kCtrNcl] = n; f.v[kCtrLvl0] = 1;
+        for (int k = 0; k < 3; ++k) { f.v[kCtrBounds + k] = float_to_ordered(FLT_MAX); f.v[kCtrBounds + 3 + k] = float_to_ordered(-FLT_MAX); }
+        be.launch(f.n, f);
         if (box_lo) {
             be.copy(prim_lo, box_lo, (size_t)n); be.copy(prim_hi, box_hi, (size_t)n);
             BoxBoundsK k; k.lo = box_lo; k.hi = box_hi; k.bounds = bounds; k.n = n;
@@ -443,7 +463,7 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
             k.a.scene_bounds = bounds; k.a.bad = bounds + 6; k.a.n = n;
             be.launch(n, k);
             int32_t bad = 0;
-            be.download(&bad, bounds + 6, 1);
+            be.download(&bad, bounds + 6, 1);  // (kept: a scene with a non-finite vertex must not reach the sort and the PLOC rounds)
             if (bad) {
                 throw Error(RTB_ERR_INVALID, "a triangle vertex is not finite or beyond 2^100: the scene cannot be built");
             }
@@ -457,99 +477,124 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
         be.launch(n, k);
         be.sort_pairs(keys, sorted, n);
     }
-    // 3. PLOC
+    // 3. PLOC.  The cluster count stays on the device (ctr[kCtrNcl]); the host enqueues a batch of rounds against an
+    // upper bound of it and reads the count back once per batch (round 1: after every round).
     const int n_b2 = 2 * n - 1;
     B2Node *b2 = tmp.template alloc<B2Node>(n_b2);
     int32_t *count = tmp.template alloc<int32_t>(n_b2);
     int32_t *ca = tmp.template alloc<int32_t>(n), *cb = tmp.template alloc<int32_t>(n), *nn = tmp.template alloc<int32_t>(n);
-    int32_t *ctr = tmp.template alloc<int32_t>(4);  // [0] b2 node counter, [1] wide node counter, [2] tri counter, [3] work out
+    const bool want_plan = bp.collapse == RTB_COLLAPSE_SAH_OPTIMAL && n > max_leaf;
+    int32_t *log = tmp.template alloc<int32_t>(kMaxPlocLog);
     {
         PlocLeafK k; k.lo = prim_lo; k.hi = prim_hi; k.sorted = sorted; k.nodes = b2; k.count = count; k.clusters = ca; k.n = n;
         be.launch(n, k);
-        int32_t init[4] = {n, 1, 0, 0};
-        be.upload(ctr, init, 4);
     }
-    int ncl = n, iters = 0;
-    std::vector<int> round_first, round_count;  // binary nodes created by each PLOC round: ids are handed out in merge order
-    int next_id = n;
-    int32_t root_b2 = -1;
-    while (ncl > 1) {
-        PlocArgs a; a.nodes = b2; a.count = count; a.cin = ca; a.cout = cb; a.nn = nn; a.node_counter = ctr; a.ncl = ncl; a.radius = radius;
-        // the last rounds handle a few hundred clusters each and are pure launch + host-sync latency (S1: 36 of 46
-        // rounds): once the clusters fit one thread block, one launch runs all the remaining rounds in shared memory
-        std::vector<int> tail_counts;
-        if (be.ploc_tail(a, n, tail_counts, root_b2)) {
-            for (int c : tail_counts) { round_first.push_back(next_id); round_count.push_back(c); next_id += c; ++iters; }
-            break;
+    int bound = n, rounds = 0;
+    bool tail = false;
+    while (bound > 1) {
+        PlocArgs a; a.nodes = b2; a.count = count; a.cin = ca; a.cout = cb; a.nn = nn; a.node_counter = ctr + kCtrB2; a.ncl = bound; a.radius = radius;
+        a.ncl_dev = ctr + kCtrNcl; a.log = log; a.round = rounds;
+        // the last rounds handle a few hundred clusters each and are pure launch latency (S1: 28 of 46 rounds): once
+        // the clusters fit one thread block, one launch runs all the remaining rounds in shared memory
+        if (be.ploc_tail(a, n, ctr + kCtrTail)) { tail = true; break; }
+        // rounds of this batch: the count shrinks by about a fifth per round (S1 and S2 alike); go most of the way to
+        // the tail's size, but not far on a large bound — every launch of the batch still covers the whole bound
+        const double to_tail = std::log((double)bound / 1024.0) / 0.235;
+        int batch = (int)(0.8 * to_tail);
+        const int cap = bound > (1 << 21) ? 4 : (bound > (1 << 18) ? 8 : 16);
+        if (batch > cap) batch = cap;
+        if (batch < 1) batch = 1;
+        for (int r = 0; r < batch; ++r) {
+            if (rounds >= kMaxPlocLog) throw Error(RTB_ERR_INVALID, "internal: too many PLOC rounds");
+            a.round = rounds;
+            be.ploc_nn(a);
+            PlocMergeK k2; k2.a = a; k2.n_leaves = n; be.launch(bound, k2);
+            be.compact_nonneg(cb, ca, bound, ctr + kCtrNcl);
+            ++rounds;
         }
-        PlocNnK k1; k1.a = a; be.launch(ncl, k1);
-        PlocMergeK k2; k2.a = a; k2.n_leaves = n; be.launch(ncl, k2);
-        const int before = ncl;
-        ncl = be.compact_nonneg(cb, ca, ncl);
-        if (ncl >= before) throw Error(RTB_ERR_INVALID, "internal: a PLOC round merged nothing");  // (cannot happen with finite boxes: the lowest-area pair is mutual)
-        round_first.push_back(next_id); round_count.push_back(before - ncl);
-        next_id += before - ncl;
-        ++iters;
+        int32_t now = 0;
+        be.download(&now, ctr + kCtrNcl, 1);
+        if (now >= bound) throw Error(RTB_ERR_INVALID, "internal: a PLOC round merged nothing");  // (cannot happen with finite boxes: the lowest-area pair is mutual)
+        bound = now;
     }
-    if (root_b2 < 0) be.download(&root_b2, ca, 1);
-    out.ploc_iterations = iters;
-    tmp.free(prim_lo); tmp.free(prim_hi); tmp.free(keys); tmp.free(sorted); tmp.free(cb); tmp.free(nn); tmp.free(ca);
+    tmp.free(prim_lo); tmp.free(prim_hi); tmp.free(keys); tmp.free(sorted); tmp.free(nn);
     // 4. collapse plan: bottom-up over the binary tree, one launch per PLOC round (a round's nodes only have older children)
     float *plan_cost = nullptr; uint8_t *plan = nullptr;
-    if (bp.collapse == RTB_COLLAPSE_SAH_OPTIMAL && n > max_leaf) {
+    std::vector<int32_t> hlog, htail;
+    auto read_logs = [&]() {
+        hlog.resize((size_t)rounds + 1);
+        if (rounds) be.download(hlog.data(), log, (size_t)rounds);
+        be.download(&hlog[(size_t)rounds], ctr + kCtrNcl, 1);  // count after the last round of the batches
+        if (tail) {
+            int32_t h2[2];
+            be.download(h2, ctr + kCtrTail, 2);
+            if (h2[0] < 0) throw Error(RTB_ERR_INVALID, "internal: a PLOC round merged nothing");
+            htail.resize((size_t)h2[0]);
+            if (h2[0]) be.download(htail.data(), be.ploc_tail_counts(), (size_t)h2[0]);
+        }
+    };
+    if (want_plan) {
+        read_logs();
         plan_cost = tmp.template alloc<float>((size_t)n_b2 * 7);
         plan = tmp.template alloc<uint8_t>((size_t)n_b2 * 8);
-        for (size_t r = 0; r < round_first.size(); ++r) {
-            PlanK k; k.a.nodes = b2; k.a.count = count; k.a.cost = plan_cost; k.a.plan = plan;
-            k.a.first = round_first[r]; k.a.n = round_count[r]; k.a.max_leaf = max_leaf;
-            be.launch(round_count[r], k);
-        }
+        int next_id = n;
+        auto plan_round = [&](int made) {
+            if (made > 0) {
+                PlanK k; k.a.nodes = b2; k.a.count = count; k.a.cost = plan_cost; k.a.plan = plan;
+                k.a.first = next_id; k.a.n = made; k.a.max_leaf = max_leaf;
+                be.launch(made, k);
+            }
+            next_id += made;
+        };
+        for (int r = 0; r < rounds; ++r) plan_round(hlog[(size_t)r] - hlog[(size_t)r + 1]);
+        for (int32_t c : htail) plan_round(c);
     }
-    // 5. collapse to the 8-wide compressed tree
+    // 5. collapse to the 8-wide compressed tree, level by level; the number of work items of a level stays on the
+    // device (three rotating counters: read, written, cleared), the host reads it once per batch of levels
     const int max_nodes = n > 1 ? n : 1;
     Q4 *nodes_tmp = tmp.template alloc<Q4>((size_t)max_nodes * kNodeWords);
     WorkItem *wa = tmp.template alloc<WorkItem>(max_nodes), *wb = tmp.template alloc<WorkItem>(max_nodes);
-    float *sah = tmp.template alloc<float>(1);
     {
-        float z = 0.f; be.upload(sah, &z, 1);
-        WorkItem r; r.b2 = root_b2; r.wide = 0;
-        be.upload(wa, &r, 1);
+        RootItemK r; r.root_src = tail ? ctr + kCtrTail + 1 : ca; r.dst = wa;
+        be.launch(1, r);
     }
-    int n_in = 1, levels = 0;
-    while (n_in > 0) {
-        int32_t zero = 0;
-        be.upload(ctr + 3, &zero, 1);
-        CollapseK k;
-        k.a.nodes = b2; k.a.count = count; k.a.plan = plan; k.a.tri_in = tri_in; k.a.meta_in = meta_in;
-        k.a.nodes8 = nodes_tmp; k.a.tris_out = tris_out; k.a.meta_out = meta_out; k.a.prim_out = prim_out;
-        k.a.leaf_of_prim = leaf_of_prim; k.a.node_counter = ctr + 1; k.a.tri_counter = ctr + 2;
-        k.a.work_in = wa; k.a.n_in = n_in; k.a.work_out = wb; k.a.n_out = ctr + 3; k.a.sah = sah; k.a.max_leaf = max_leaf;
-        be.launch(n_in, k);
-        int32_t n_out = 0;
-        be.download(&n_out, ctr + 3, 1);
-        n_in = n_out;
-        WorkItem *t = wa; wa = wb; wb = t;
-        ++levels;
+    int level = 0;
+    while (true) {
+        const int batch = level == 0 ? 8 : 4;
+        for (int b = 0; b < batch; ++b, ++level) {
+            CollapseK k;
+            k.a.nodes = b2; k.a.count = count; k.a.plan = plan; k.a.tri_in = tri_in; k.a.meta_in = meta_in;
+            k.a.nodes8 = nodes_tmp; k.a.tris_out = tris_out; k.a.meta_out = meta_out; k.a.prim_out = prim_out;
+            k.a.leaf_of_prim = leaf_of_prim; k.a.node_counter = ctr + kCtrWide; k.a.tri_counter = ctr + kCtrTri;
+            k.a.work_in = wa; k.a.n_in = 0; k.a.n_in_dev = ctr + kCtrLvl0 + level % 3; k.a.work_out = wb;
+            k.a.n_out = ctr + kCtrLvl0 + (level + 1) % 3; k.a.sah = sah; k.a.max_leaf = max_leaf;
+            be.collapse_level(k, max_nodes, ctr + kCtrLvl0 + (level + 2) % 3, ctr + kCtrLevels);
+            WorkItem *t = wa; wa = wb; wb = t;
+        }
+        int32_t pending = 0;
+        be.download(&pending, ctr + kCtrLvl0 + level % 3, 1);
+        if (pending == 0) break;
+        if (level > 4 * kStackSize) throw Error(RTB_ERR_INVALID, "BVH too deep for the traversal stack");
     }
-    int32_t c4[4];
-    be.download(c4, ctr, 4);
-    out.num_nodes = c4[1];
-    out.levels = levels;
-    if (c4[2] != n) throw Error(RTB_ERR_INVALID, "internal: collapse lost triangles");
+    int32_t c[kCtrCount];
+    be.download(c, ctr, kCtrCount);
+    out.num_nodes = c[kCtrWide];
+    out.levels = c[kCtrLevels];
+    if (c[kCtrTri] != n) throw Error(RTB_ERR_INVALID, "internal: collapse lost triangles");
     out.nodes8 = be.template alloc<Q4>((size_t)out.num_nodes * kNodeWords);
     be.copy(out.nodes8, nodes_tmp, (size_t)out.num_nodes * kNodeWords);
-    tmp.free(nodes_tmp); tmp.free(wa); tmp.free(wb); tmp.free(plan_cost); tmp.free(plan);
-    float sah_h = 0.f;
-    be.download(&sah_h, sah, 1);
-    int32_t bnd[6];
-    be.download(bnd, bounds, 6);
+    if (!want_plan) read_logs();
+    int iters = 0;
+    for (int r = 0; r < rounds; ++r) if (hlog[(size_t)r] > hlog[(size_t)r + 1]) ++iters;
+    out.ploc_iterations = iters + (int)htail.size();
+    float sah_h;
+    memcpy(&sah_h, &c[kCtrSah], sizeof sah_h);
     float lo[3], hi[3];
-    for (int k = 0; k < 3; ++k) { lo[k] = ordered_to_float(bnd[k]); hi[k] = ordered_to_float(bnd[3 + k]); }
+    for (int k = 0; k < 3; ++k) { lo[k] = ordered_to_float(c[kCtrBounds + k]); hi[k] = ordered_to_float(c[kCtrBounds + 3 + k]); }
     const float root_area = half_area(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
     out.sah_cost = root_area > 0.f ? sah_h / root_area : 0.f;
     for (int k = 0; k < 3; ++k) { out.bounds[2 * k] = lo[k]; out.bounds[2 * k + 1] = hi[k]; }
-    tmp.free(b2); tmp.free(count); tmp.free(ctr); tmp.free(sah); tmp.free(bounds);
-    return out;
+    return out;  // (Temps releases what is still held, on this path and on every throw)
 }
 
 // tri_in / meta_in / light_tri are device arrays in caller order; vertices may

@@ -31,7 +31,7 @@ struct HostBackend {
     std::map<std::string, long long> opts_;
     bool set_option(const std::string &name, long long v) {
         static const char *const names[] = {"refill", "chunk", "prefetch", "tri_step", "pooled", "fused", "smem_stack", "pipelines", "pool",
-                                            "ploc_tail", "trace_blocks"};
+                                            "ploc_tail", "trace_blocks", "nn_tiled"};
         for (const char *n : names) if (name == n) { if (name == "pool" && v < 1024) return false; opts_[name] = v; return true; }
         return false;
     }
@@ -120,11 +120,19 @@ struct HostBackend {
         memcpy(keys, k.data(), sizeof(uint64_t) * n);
         memcpy(vals, v.data(), sizeof(int32_t) * n);
     }
-    bool ploc_tail(const PlocArgs &, int, std::vector<int> &, int32_t &) { return false; }  // (a launch-latency measure of the CUDA backend)
-    int compact_nonneg(const int32_t *in, int32_t *out, int n) {
+    void ploc_nn(const PlocArgs &a) { PlocNnK k; k.a = a; launch(a.ncl, k); }
+    bool ploc_tail(const PlocArgs &, int, int32_t *) { return false; }  // (a launch-latency measure of the CUDA backend)
+    int32_t *ploc_tail_counts() { return nullptr; }
+    void compact_nonneg(const int32_t *in, int32_t *out, int n, int32_t *count) {
         int m = 0;
         for (int i = 0; i < n; ++i) if (in[i] >= 0) out[m++] = in[i];
-        return m;
+        *count = m;
+    }
+    void collapse_level(const CollapseK &k, int, int32_t *zero, int32_t *levels) {
+        const int n = *k.a.n_in_dev;
+        *zero = 0;
+        if (n > 0) *levels += 1;
+        for (int i = 0; i < n; ++i) collapse_body(k.a, i);
     }
     using Time = std::chrono::steady_clock::time_point;
     Time now() { return std::chrono::steady_clock::now(); }
