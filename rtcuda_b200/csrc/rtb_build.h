@@ -312,7 +312,32 @@ struct CollapseArgs {
     WorkItem *work_out; int32_t *n_out;
     float *sah;                // accumulated SAH cost (unnormalised)
     int32_t max_leaf;          // 1..3
+    int32_t *gather;           // [n] leaf order: binary subtree whose triangles start at this slot, or -1 (gather_body)
 };
+// triangles of the leaf children, in leaf order: slot d holds the binary subtree whose (<= 3) triangles go to d, d+1, ..
+// (left to right) or -1; one thread per slot, after the collapse
+RTB_HD void gather_body(const CollapseArgs &a, int n, int d) {
+    if (d >= n) return;
+    const int root = a.gather[d];
+    if (root < 0) return;
+    int st[4]; int sp = 0; st[sp++] = root;
+    int dst = d;
+    while (sp) {
+        const int ni = st[--sp];
+        const B2Node x = a.nodes[ni];
+        if (x.right < 0) {
+            if (a.tri_in) {  // (null: the tree over the instances of a two-level scene, whose leaves are boxes)
+                a.tris_out[dst] = a.tri_in[x.left];
+                a.meta_out[dst] = a.meta_in[x.left];
+            }
+            a.prim_out[dst] = x.left;
+            a.leaf_of_prim[x.left] = dst;
+            dst++;
+        } else {
+            st[sp++] = x.right; st[sp++] = x.left;
+        }
+    }
+}
 
 RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
     if (tid >= (a.n_in_dev ? *a.n_in_dev : a.n_in)) return;
@@ -320,58 +345,70 @@ RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
     const B2Node self = a.nodes[item.b2];
     int ch[8];
     int nc;
+    // boxes and triangle counts of the children chosen so far: every level of this loop costs one round trip to
+    // memory (the two nodes a child is opened into), and nothing is read twice
+    B2Node cb[8];
+    int ccnt[8];
     if (a.count[item.b2] <= a.max_leaf) { ch[0] = item.b2; nc = 1; }  // tiny scene: root is one leaf
     else if (a.plan) { nc = plan_expand(a.nodes, a.plan, item.b2, ch); }
     else { ch[0] = self.left; ch[1] = self.right; nc = 2; }
+    for (int k = 0; k < nc; ++k) { cb[k] = a.nodes[ch[k]]; ccnt[k] = a.count[ch[k]]; }
     // without a plan: open the largest child until 8 children or only leaves remain
     while (!a.plan && nc < 8) {
         int best = -1; float best_a = -1.f;
         for (int k = 0; k < nc; ++k) {
-            if (a.count[ch[k]] > a.max_leaf) {
-                const float ar = b2_half_area(a.nodes[ch[k]]);
+            if (ccnt[k] > a.max_leaf) {
+                const float ar = b2_half_area(cb[k]);
                 if (ar > best_a) { best_a = ar; best = k; }
             }
         }
         if (best < 0) break;
-        const B2Node o = a.nodes[ch[best]];
-        ch[best] = o.left;
-        ch[nc++] = o.right;
+        const int l = cb[best].left, r = cb[best].right;
+        ch[best] = l; ch[nc] = r;
+        cb[best] = a.nodes[l]; cb[nc] = a.nodes[r];
+        ccnt[best] = a.count[l]; ccnt[nc] = a.count[r];
+        ++nc;
     }
-    B2Node cb[8];
-    for (int k = 0; k < nc; ++k) cb[k] = a.nodes[ch[k]];
     // slot assignment (greedy): slot s "looks" towards (s&1?+:-, s&2?+:-, s&4?+:-);
     // a child goes to the slot best aligned with its offset from the node
     // centre, so that `slot ^ octinv` orders children front to back
     const float pcx = fmul(0.5f, fadd(self.lox, self.hix)), pcy = fmul(0.5f, fadd(self.loy, self.hiy)),
                 pcz = fmul(0.5f, fadd(self.loz, self.hiz));
+    // (every index into cost / todo / free below is a compile-time constant once the loops are unrolled: the matrix stays
+    // in registers; dynamically indexed it lived in local memory, and the 8 x 64 dependent compares of the greedy
+    // assignment were a third of a level's critical path)
     float cost[8][8];
-    for (int k = 0; k < nc; ++k) {
-        const float dx = fsub(fmul(0.5f, fadd(cb[k].lox, cb[k].hix)), pcx);
-        const float dy = fsub(fmul(0.5f, fadd(cb[k].loy, cb[k].hiy)), pcy);
-        const float dz = fsub(fmul(0.5f, fadd(cb[k].loz, cb[k].hiz)), pcz);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const B2Node &c = cb[k < nc ? k : 0];
+        const float dx = fsub(fmul(0.5f, fadd(c.lox, c.hix)), pcx);
+        const float dy = fsub(fmul(0.5f, fadd(c.loy, c.hiy)), pcy);
+        const float dz = fsub(fmul(0.5f, fadd(c.loz, c.hiz)), pcz);
+#pragma unroll
         for (int s = 0; s < 8; ++s)
             cost[k][s] = fadd(fadd((s & 1) ? dx : -dx, (s & 2) ? dy : -dy), (s & 4) ? dz : -dz);
     }
     int slot_child[8];
     for (int s = 0; s < 8; ++s) slot_child[s] = -1;
-    bool child_done[8];
-    for (int k = 0; k < 8; ++k) child_done[k] = false;
+    uint32_t todo = (1u << nc) - 1u, free_slots = 0xffu;  // children not placed yet, slots not taken yet
     for (int round = 0; round < nc; ++round) {
         float bc = -FLT_MAX; int bk = -1, bs = -1;
-        for (int k = 0; k < nc; ++k) {
-            if (child_done[k]) continue;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (!(todo >> k & 1u)) continue;
+#pragma unroll
             for (int s = 0; s < 8; ++s) {
-                if (slot_child[s] >= 0) continue;
+                if (!(free_slots >> s & 1u)) continue;
                 if (cost[k][s] > bc) { bc = cost[k][s]; bk = k; bs = s; }
             }
         }
         slot_child[bs] = bk;
-        child_done[bk] = true;
+        todo &= ~(1u << bk); free_slots &= ~(1u << bs);
     }
     // allocate children and triangles
     int n_inner = 0, n_tris = 0;
     for (int k = 0; k < nc; ++k) {
-        const int cnt = a.count[ch[k]];
+        const int cnt = ccnt[k];
         if (cnt > a.max_leaf) n_inner++; else n_tris += cnt;
     }
     const int child_base = n_inner ? atomic_add_i(a.node_counter, n_inner) : 0;
@@ -394,7 +431,7 @@ RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
         qlx[s] = quant_lo(c.lox, self.lox, ex); qhx[s] = quant_hi(c.hix, self.lox, ex);
         qly[s] = quant_lo(c.loy, self.loy, ey); qhy[s] = quant_hi(c.hiy, self.loy, ey);
         qlz[s] = quant_lo(c.loz, self.loz, ez); qhz[s] = quant_hi(c.hiz, self.loz, ez);
-        const int cnt = a.count[ch[k]];
+        const int cnt = ccnt[k];
         if (cnt > a.max_leaf) {
             meta[s] = 0x20u | (24u + (uint32_t)s);
             imask |= 1u << s;
@@ -404,24 +441,12 @@ RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
         } else {
             meta[s] = (((1u << cnt) - 1u) << 5) | (uint32_t)tri_off;
             sah = ffma(b2_half_area(c), fmul(kSahTriCost, (float)cnt), sah);
-            // gather the (<= 3) triangles of this subtree
-            int st[4]; int sp = 0; st[sp++] = ch[k];
-            while (sp) {
-                const int ni = st[--sp];
-                const B2Node x = a.nodes[ni];
-                if (x.right < 0) {
-                    const int dst = tri_base + tri_off;
-                    if (a.tri_in) {  // (null: the tree over the instances of a two-level scene, whose leaves are boxes)
-                        a.tris_out[dst] = a.tri_in[x.left];
-                        a.meta_out[dst] = a.meta_in[x.left];
-                    }
-                    a.prim_out[dst] = x.left;
-                    a.leaf_of_prim[x.left] = dst;
-                    tri_off++;
-                } else {
-                    st[sp++] = x.right; st[sp++] = x.left;
-                }
-            }
+            // the (<= 3) triangles of this subtree go to tri_base + tri_off ...: gathered by gather_body, one thread per
+            // leaf child, after the last level (walking the subtree here put 8 x 3 dependent loads on every level's
+            // critical path).  Every triangle slot is written once: the subtree at a leaf child's first slot, -1 behind it
+            a.gather[tri_base + tri_off] = ch[k];
+            for (int t = 1; t < cnt; ++t) a.gather[tri_base + tri_off + t] = -1;
+            tri_off += cnt;
         }
     }
     atomic_add_f(a.sah, sah);

@@ -490,28 +490,61 @@ __global__ void __launch_bounds__(kNnBlock) k_ploc_nn_tiled(PlocArgs a) {
 constexpr int kPlocTail = 1024;
 __global__ void __launch_bounds__(kPlocTail) k_ploc_tail(PlocArgs a, int n_leaves, int32_t *out, int32_t *counts) {
     __shared__ int32_t cin[kPlocTail], cout[kPlocTail], nn[kPlocTail];
+    // boxes of the clusters by position: the neighbour search of a round reads 2 x radius of them per thread
+    __shared__ float lox[kPlocTail], loy[kPlocTail], loz[kPlocTail], hix[kPlocTail], hiy[kPlocTail], hiz[kPlocTail];
     typedef cub::BlockScan<int, kPlocTail> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     const int t = threadIdx.x;
     int n = ploc_ncl(a);
     if (n > kPlocTail) { if (t == 0) { out[0] = -1; out[1] = -1; } return; }  // (the host launches it on a bound <= kPlocTail)
-    if (t < n) cin[t] = a.cin[t];
+    if (t < n) {
+        const int c = a.cin[t];
+        cin[t] = c;
+        const B2Node b = a.nodes[c];
+        lox[t] = b.lox; loy[t] = b.loy; loz[t] = b.loz; hix[t] = b.hix; hiy[t] = b.hiy; hiz[t] = b.hiz;
+    }
     __syncthreads();
     PlocArgs b = a;
     b.cin = cin; b.cout = cout; b.nn = nn; b.ncl_dev = nullptr; b.log = nullptr;
     int rounds = 0;
     while (n > 1) {
         b.ncl = n;
-        ploc_nn_body(b, t);
+        B2Node me;
+        if (t < n) {  // ploc_nn_body on the shared-memory boxes: same arithmetic, same tie rule
+            me.lox = lox[t]; me.loy = loy[t]; me.loz = loz[t]; me.hix = hix[t]; me.hiy = hiy[t]; me.hiz = hiz[t];
+            float best = FLT_MAX;
+            int bj = -1;
+            const int j0 = t - a.radius < 0 ? 0 : t - a.radius;
+            const int j1 = t + a.radius > n - 1 ? n - 1 : t + a.radius;
+            for (int j = j0; j <= j1; ++j) {
+                if (j == t) continue;
+                B2Node o;
+                o.lox = lox[j]; o.loy = loy[j]; o.loz = loz[j]; o.hix = hix[j]; o.hiy = hiy[j]; o.hiz = hiz[j];
+                const float ar = union_half_area(me, o);
+                if (bj < 0 || ar < best) { best = ar; bj = j; }
+            }
+            nn[t] = bj;
+        }
         __syncthreads();
         ploc_merge_body(b, n_leaves, t);  // (new nodes go to global memory: visible to the block after the barrier)
+        // box of what this position holds after the merge (the union is the one ploc_merge_body stores: same min / max)
+        if (t < n) {
+            const int j = nn[t];
+            if (j >= 0 && nn[j] == t && t < j) {
+                me.lox = fminf(me.lox, lox[j]); me.loy = fminf(me.loy, loy[j]); me.loz = fminf(me.loz, loz[j]);
+                me.hix = fmaxf(me.hix, hix[j]); me.hiy = fmaxf(me.hiy, hiy[j]); me.hiz = fmaxf(me.hiz, hiz[j]);
+            }
+        }
         __syncthreads();
         const int v = t < n ? cout[t] : -1;
         const int flag = v >= 0 ? 1 : 0;
         int pos, total;
         Scan(scan_tmp).ExclusiveSum(flag, pos, total);
         __syncthreads();
-        if (flag) cin[pos] = v;
+        if (flag) {
+            cin[pos] = v;
+            lox[pos] = me.lox; loy[pos] = me.loy; loz[pos] = me.loz; hix[pos] = me.hix; hiy[pos] = me.hiy; hiz[pos] = me.hiz;
+        }
         if (t == 0) counts[rounds] = n - total;
         const bool stuck = total >= n;  // a round that merged nothing would spin here for ever (cannot happen with finite boxes)
         n = total;

@@ -70,6 +70,7 @@ struct PlocNnK { PlocArgs a; RTB_HD void operator()(int i) const { ploc_nn_body(
 struct PlocMergeK { PlocArgs a; int n_leaves; RTB_HD void operator()(int i) const { ploc_merge_body(a, n_leaves, i); } };
 struct PlanK { PlanArgs a; RTB_HD void operator()(int i) const { plan_body(a, i); } };
 struct CollapseK { CollapseArgs a; RTB_HD void operator()(int i) const { collapse_body(a, i); } };
+struct GatherK { CollapseArgs a; int n; RTB_HD void operator()(int i) const { gather_body(a, n, i); } };
 struct LightFixK {
     LightDev *lights; const int64_t *light_tri; const int32_t *leaf_of_prim; int n;
     RTB_HD void operator()(int i) const { light_fix_body(lights, light_tri, leaf_of_prim, n, i); }
@@ -554,6 +555,8 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     const int max_nodes = n > 1 ? n : 1;
     Q4 *nodes_tmp = tmp.template alloc<Q4>((size_t)max_nodes * kNodeWords);
     WorkItem *wa = tmp.template alloc<WorkItem>(max_nodes), *wb = tmp.template alloc<WorkItem>(max_nodes);
+    int32_t *gather = tmp.template alloc<int32_t>(n);
+    CollapseArgs ga{};
     {
         RootItemK r; r.root_src = tail ? ctr + kCtrTail + 1 : ca; r.dst = wa;
         be.launch(1, r);
@@ -567,7 +570,8 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
             k.a.nodes8 = nodes_tmp; k.a.tris_out = tris_out; k.a.meta_out = meta_out; k.a.prim_out = prim_out;
             k.a.leaf_of_prim = leaf_of_prim; k.a.node_counter = ctr + kCtrWide; k.a.tri_counter = ctr + kCtrTri;
             k.a.work_in = wa; k.a.n_in = 0; k.a.n_in_dev = ctr + kCtrLvl0 + level % 3; k.a.work_out = wb;
-            k.a.n_out = ctr + kCtrLvl0 + (level + 1) % 3; k.a.sah = sah; k.a.max_leaf = max_leaf;
+            k.a.n_out = ctr + kCtrLvl0 + (level + 1) % 3; k.a.sah = sah; k.a.max_leaf = max_leaf; k.a.gather = gather;
+            ga = k.a;
             be.collapse_level(k, max_nodes, ctr + kCtrLvl0 + (level + 2) % 3, ctr + kCtrLevels);
             WorkItem *t = wa; wa = wb; wb = t;
         }
@@ -576,6 +580,7 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
         if (pending == 0) break;
         if (level > 4 * kStackSize) throw Error(RTB_ERR_INVALID, "BVH too deep for the traversal stack");
     }
+    { GatherK g; g.a = ga; g.n = n; be.launch(n, g); }  // triangles of the leaf children, one thread per leaf child
     int32_t c[kCtrCount];
     be.download(c, ctr, kCtrCount);
     out.num_nodes = c[kCtrWide];
