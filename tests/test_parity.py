@@ -174,6 +174,41 @@ def test_sah_optimal_collapse_is_a_valid_smaller_tree(L, ctx, s1, s1_dev, s1_orc
     sc.close()
 
 
+def test_build_schedules_give_the_same_tree(L, s1, s1_dev, s1_orc):
+    """The builder runs its PLOC rounds and collapse levels in batches against counts that stay on the device, searches
+    nearest neighbours from a shared-memory window and finishes the rounds in one block once the clusters fit it (round
+    2).  None of that may change the tree: the one-thread-per-cluster search ("nn_tiled" = 0) and one launch set per
+    round to the end ("ploc_tail" = 0) must give the same nodes, rounds, levels, cost and — ties included — hits."""
+    ref = s1_dev.stats()
+    rays = np.concatenate([L.primary_rays(s1.camera(1.0), 200, 200), random_rays(60000, seed=21)])
+    want = s1_orc.trace_closest(rays, capi.HIT_DTYPE)
+    for opts in ({"nn_tiled": 0}, {"ploc_tail": 0}, {"nn_tiled": 0, "ploc_tail": 0}):
+        c = L.context(0)
+        for k, v in opts.items():
+            c.set_option(k, v)
+        sc = c.scene(s1.desc)
+        st = sc.stats()
+        assert (st.num_nodes, st.ploc_iterations, st.collapse_levels) == (ref.num_nodes, ref.ploc_iterations, ref.collapse_levels), opts
+        assert abs(st.sah_cost - ref.sah_cost) <= 1e-5 * ref.sah_cost  # (a float sum over the nodes in launch order)
+        assert_hits_equal(sc.trace_closest(rays), want)
+        sc.close()
+        del sc, c
+
+
+@pytest.mark.gpu
+def test_gpu_builder_and_its_host_emulation_build_the_same_tree(gpu, emu, bunny):
+    """same bodies, two drivers (batched launches on device-resident counts / plain loops): same tree statistics"""
+    out = []
+    for lib in (gpu, emu):
+        hs = lib.host_scene(capi.RTB_SCENE_S1, *bunny)
+        sc = lib.context(0).scene(hs.desc)
+        st = sc.stats()
+        out.append((st.num_nodes, st.ploc_iterations, st.collapse_levels, st.sah_cost))
+        sc.close()
+    assert out[0][:3] == out[1][:3], out
+    assert abs(out[0][3] - out[1][3]) <= 1e-5 * out[1][3]
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 9, 33, 200])
 def test_small_and_empty_scenes(L, ctx, oracle, n):
     """empty, single-triangle and ragged triangle counts; degenerate (zero-area) triangles included"""
