@@ -506,7 +506,12 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
         if (batch > cap) batch = cap;
         if (batch < 1) batch = 1;
         for (int r = 0; r < batch; ++r) {
-            if (rounds >= kMaxPlocLog) throw Error(RTB_ERR_INVALID, "internal: too many PLOC rounds");
+            // (a scene of identical triangles merges ONE pair per round: n - 1 rounds.  The per-round counts are a
+            // statistic, and the SAH-optimal plan's launch schedule: beyond the log's size only the plan needs them)
+            if (rounds >= kMaxPlocLog) {
+                if (want_plan) throw Error(RTB_ERR_INVALID, "RTB_COLLAPSE_SAH_OPTIMAL: too many PLOC rounds (degenerate scene)");
+                a.log = nullptr;
+            }
             a.round = rounds;
             be.ploc_nn(a);
             PlocMergeK k2; k2.a = a; k2.n_leaves = n; be.launch(bound, k2);
@@ -523,9 +528,10 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     float *plan_cost = nullptr; uint8_t *plan = nullptr;
     std::vector<int32_t> hlog, htail;
     auto read_logs = [&]() {
-        hlog.resize((size_t)rounds + 1);
-        if (rounds) be.download(hlog.data(), log, (size_t)rounds);
-        be.download(&hlog[(size_t)rounds], ctr + kCtrNcl, 1);  // count after the last round of the batches
+        const int logged = rounds < kMaxPlocLog ? rounds : kMaxPlocLog;
+        hlog.resize((size_t)logged + 1);
+        if (logged) be.download(hlog.data(), log, (size_t)logged);
+        be.download(&hlog[(size_t)logged], ctr + kCtrNcl, 1);  // count after the last round of the batches
         if (tail) {
             int32_t h2[2];
             be.download(h2, ctr + kCtrTail, 2);
@@ -547,7 +553,7 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
             }
             next_id += made;
         };
-        for (int r = 0; r < rounds; ++r) plan_round(hlog[(size_t)r] - hlog[(size_t)r + 1]);
+        for (size_t r = 0; r + 1 < hlog.size(); ++r) plan_round(hlog[r] - hlog[r + 1]);
         for (int32_t c : htail) plan_round(c);
     }
     // 5. collapse to the 8-wide compressed tree, level by level; the number of work items of a level stays on the
@@ -589,8 +595,8 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
     out.nodes8 = be.template alloc<Q4>((size_t)out.num_nodes * kNodeWords);
     be.copy(out.nodes8, nodes_tmp, (size_t)out.num_nodes * kNodeWords);
     if (!want_plan) read_logs();
-    int iters = 0;
-    for (int r = 0; r < rounds; ++r) if (hlog[(size_t)r] > hlog[(size_t)r + 1]) ++iters;
+    int iters = rounds > kMaxPlocLog ? rounds - kMaxPlocLog : 0;  // (rounds beyond the log are counted, not examined)
+    for (size_t r = 0; r + 1 < hlog.size(); ++r) if (hlog[r] > hlog[r + 1]) ++iters;
     out.ploc_iterations = iters + (int)htail.size();
     float sah_h;
     memcpy(&sah_h, &c[kCtrSah], sizeof sah_h);

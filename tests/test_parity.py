@@ -195,6 +195,36 @@ def test_build_schedules_give_the_same_tree(L, s1, s1_dev, s1_orc):
         del sc, c
 
 
+def test_identical_triangles_build_one_pair_per_round(L, ctx, oracle):
+    """the builder's worst case: every cluster box is the same, area ties go to the lowest position, so a PLOC round
+    merges exactly one pair — n - 1 rounds, through the batched rounds, the single-block tail and the collapse — and the
+    binary tree is a chain.  200 copies still fit the traversal stack; 2500 do not and come back as an error status
+    (never a hang: the rounds and the levels are bounded)"""
+    tri = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0], np.float32)
+    mats = std_materials()
+
+    def desc_of(n):
+        return make_desc(np.tile(tri, (n, 1)), np.zeros(n, np.int32), np.full(n, -1, np.int32), mats, [])
+
+    n = 200
+    desc, keep = desc_of(n)
+    sc = ctx.scene(desc)
+    st = sc.stats()
+    assert st.num_triangles == n and st.ploc_iterations == n - 1
+    rays = np.zeros(2, capi.RAY_DTYPE)
+    rays["origin"] = [(0.2, 0.2, 1.0), (2.0, 2.0, 1.0)]
+    rays["dir"] = [(0, 0, -1), (0, 0, -1)]
+    rays["tmax"] = 1e30
+    hits = sc.trace_closest(rays)
+    ref = oracle.scene(desc).trace_closest(rays, capi.HIT_DTYPE)
+    assert hits["prim"][0] >= 0 and hits["prim"][1] == -1
+    assert (hits["t"].view(np.uint32) == ref["t"].view(np.uint32)).all()  # (which of the coincident triangles wins the tie is the tree's choice)
+    sc.close()
+    desc, keep = desc_of(2500)
+    with pytest.raises(capi.RtbError, match="too deep"):
+        ctx.scene(desc)
+
+
 @pytest.mark.gpu
 def test_gpu_builder_and_its_host_emulation_build_the_same_tree(gpu, emu, bunny):
     """same bodies, two drivers (batched launches on device-resident counts / plain loops): same tree statistics"""
