@@ -86,7 +86,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 #define RTB_SHADE_BLOCK 128
 #endif
 constexpr int kShadeBlock = RTB_SHADE_BLOCK;  // small blocks: they fit the registers a half-occupancy trace kernel leaves free
-constexpr int shade_blocks_per_sm(int type) { return ((type == RTB_MIRROR || type == RTB_GLASS) ? 3 : 2) * (256 / kShadeBlock); }
+#ifndef RTB_SHADE_MATTE_BLOCKS
+#define RTB_SHADE_MATTE_BLOCKS 2  // per 256 threads: 2 -> up to 128 registers; 3 -> 85 (spills), 4 -> 64 (A/B: profiles/r2)
+#endif
+constexpr int shade_blocks_per_sm(int type) { return ((type == RTB_MIRROR || type == RTB_GLASS) ? 3 : RTB_SHADE_MATTE_BLOCKS) * (256 / kShadeBlock); }
 template <int TYPE, bool EXT = false>
 __global__ void __launch_bounds__(kShadeBlock, shade_blocks_per_sm(TYPE)) k_shade(WaveState W, SceneView S, RenderConsts rc, bool shadows) {
     __shared__ float4 stage[2][3][kShadeBlock];
