@@ -70,6 +70,9 @@ struct PrimSetupArgs {
 // never below any other, so PLOC could not pair it; beyond 2^100 box extents and areas overflow.  The reference has no
 // such check: its host SAH sweep just produces a useless tree.)
 constexpr float kMaxCoord = 1.2676506e30f;
+// bounds of one triangle record, the vertex check and the scene bounds; t is triangle i's record (already stored)
+RTB_HD void prim_setup_bounds(const PrimSetupArgs &a, int i, const Tri48 &t);
+RTB_HD void prim_setup_box(const PrimSetupArgs &a, int i, const Tri48 &t, V3 &lo, V3 &hi);
 RTB_HD void prim_setup_body(const PrimSetupArgs &a, int i) {
     if (i >= a.n) return;
     Tri48 t;
@@ -80,10 +83,36 @@ RTB_HD void prim_setup_body(const PrimSetupArgs &a, int i) {
     } else {
         t = a.tri_in[i];
     }
+    prim_setup_bounds(a, i, t);
+}
+RTB_HD void prim_setup_bounds(const PrimSetupArgs &a, int i, const Tri48 &t) {
+    V3 lo, hi;
+    prim_setup_box(a, i, t, lo, hi);
+#if defined(__CUDA_ARCH__)
+    // one reduction per warp (redux.sync), then six atomics by one lane: 10 M triangles used to send 60 M atomics to six addresses
+    const unsigned m = __activemask();
+    const int lx = __reduce_min_sync(m, float_to_ordered(lo.x)), ly = __reduce_min_sync(m, float_to_ordered(lo.y)),
+              lz = __reduce_min_sync(m, float_to_ordered(lo.z));
+    const int hx = __reduce_max_sync(m, float_to_ordered(hi.x)), hy = __reduce_max_sync(m, float_to_ordered(hi.y)),
+              hz = __reduce_max_sync(m, float_to_ordered(hi.z));
+    if ((threadIdx.x & 31) == __ffs(m) - 1) {
+        atomic_min_i(a.scene_bounds + 0, lx); atomic_min_i(a.scene_bounds + 1, ly); atomic_min_i(a.scene_bounds + 2, lz);
+        atomic_max_i(a.scene_bounds + 3, hx); atomic_max_i(a.scene_bounds + 4, hy); atomic_max_i(a.scene_bounds + 5, hz);
+    }
+#else
+    atomic_min_i(a.scene_bounds + 0, float_to_ordered(lo.x));
+    atomic_min_i(a.scene_bounds + 1, float_to_ordered(lo.y));
+    atomic_min_i(a.scene_bounds + 2, float_to_ordered(lo.z));
+    atomic_max_i(a.scene_bounds + 3, float_to_ordered(hi.x));
+    atomic_max_i(a.scene_bounds + 4, float_to_ordered(hi.y));
+    atomic_max_i(a.scene_bounds + 5, float_to_ordered(hi.z));
+#endif
+}
+RTB_HD void prim_setup_box(const PrimSetupArgs &a, int i, const Tri48 &t, V3 &lo, V3 &hi) {
     // Triangle::bounding_box, triangle.cuh:23-37 (p1 = p0 - e1, p2 = p0 + e2)
     V3 p0 = tri_p0(t), p1 = vsub(p0, tri_e1(t)), p2 = vadd(p0, tri_e2(t));
-    V3 lo = v3(fminf(p0.x, fminf(p1.x, p2.x)), fminf(p0.y, fminf(p1.y, p2.y)), fminf(p0.z, fminf(p1.z, p2.z)));
-    V3 hi = v3(fmaxf(p0.x, fmaxf(p1.x, p2.x)), fmaxf(p0.y, fmaxf(p1.y, p2.y)), fmaxf(p0.z, fmaxf(p1.z, p2.z)));
+    lo = v3(fminf(p0.x, fminf(p1.x, p2.x)), fminf(p0.y, fminf(p1.y, p2.y)), fminf(p0.z, fminf(p1.z, p2.z)));
+    hi = v3(fmaxf(p0.x, fmaxf(p1.x, p2.x)), fmaxf(p0.y, fmaxf(p1.y, p2.y)), fmaxf(p0.z, fmaxf(p1.z, p2.z)));
     // (fminf / fmaxf drop a NaN operand, so the vertices are looked at themselves)
     const float worst = fmaxf(fmaxf(fmaxf(fabsf(p0.x), fabsf(p0.y)), fmaxf(fabsf(p0.z), fabsf(p1.x))),
                               fmaxf(fmaxf(fabsf(p1.y), fabsf(p1.z)), fmaxf(fabsf(p2.x), fmaxf(fabsf(p2.y), fabsf(p2.z)))));
@@ -93,12 +122,6 @@ RTB_HD void prim_setup_body(const PrimSetupArgs &a, int i) {
     F4 l; l.x = lo.x; l.y = lo.y; l.z = lo.z; l.w = 0.f;
     F4 h; h.x = hi.x; h.y = hi.y; h.z = hi.z; h.w = 0.f;
     a.prim_lo[i] = l; a.prim_hi[i] = h;
-    atomic_min_i(a.scene_bounds + 0, float_to_ordered(lo.x));
-    atomic_min_i(a.scene_bounds + 1, float_to_ordered(lo.y));
-    atomic_min_i(a.scene_bounds + 2, float_to_ordered(lo.z));
-    atomic_max_i(a.scene_bounds + 3, float_to_ordered(hi.x));
-    atomic_max_i(a.scene_bounds + 4, float_to_ordered(hi.y));
-    atomic_max_i(a.scene_bounds + 5, float_to_ordered(hi.z));
 }
 
 // ------------------------------------------------------------ 2. morton
@@ -449,7 +472,17 @@ RTB_HD void collapse_body(const CollapseArgs &a, int tid) {
             tri_off += cnt;
         }
     }
+#if defined(__CUDA_ARCH__)
+    {   // one float atomic per warp (a level of a 10 M-triangle build has a million nodes, and floating-point
+        // reductions to one address are not aggregated by the compiler); the cost is a statistic, its summation order is free
+        const unsigned m = __activemask();  // (whatever lanes arrive here together: the loops above diverge)
+        float v = 0.f;
+        for (unsigned r = m; r != 0u; r &= r - 1u) v += __shfl_sync(m, sah, __ffs(r) - 1);
+        if ((threadIdx.x & 31) == __ffs(m) - 1) atomic_add_f(a.sah, v);
+    }
+#else
     atomic_add_f(a.sah, sah);
+#endif
     Q4 w0, w1, w2, w3, w4;
     w0.x = f2u(self.lox); w0.y = f2u(self.loy); w0.z = f2u(self.loz);
     w0.w = ex | (ey << 8) | (ez << 16) | (imask << 24);

@@ -446,6 +446,59 @@ __global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S
     if (i < W.c->n_shadow) shadow_body<COUNT>(W, S, i);
 }
 
+// prim_setup_body with the block's vertices (36 bytes per triangle) and records (48 bytes) passing through shared memory,
+// so that global memory sees whole 128-bit words at consecutive addresses: one thread per triangle reading nine floats at a
+// 36-byte stride and storing twelve at a 48-byte stride took 1.48 ms for the 1.2 GB of a 10 M-triangle scene.
+constexpr int kSetupBlock = 256;
+__global__ void __launch_bounds__(kSetupBlock) k_prim_setup_tiled(PrimSetupArgs a) {
+    __shared__ float vin[kSetupBlock * 9];
+    __shared__ float4 rec[kSetupBlock * 3];
+    const int b0 = blockIdx.x * kSetupBlock;
+    const int cnt = min(kSetupBlock, a.n - b0);
+    const float *src = a.vertices + 9 * (size_t)b0;  // (36 * 256 bytes per block: 16-byte aligned like the array)
+    if (cnt == kSetupBlock && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(vin);
+        for (int t = threadIdx.x; t < kSetupBlock * 9 / 4; t += kSetupBlock) d4[t] = s4[t];
+    } else {
+        for (int t = threadIdx.x; t < cnt * 9; t += kSetupBlock) vin[t] = src[t];
+    }
+    __syncthreads();
+    const int i = b0 + threadIdx.x;
+    Tri48 tr;
+    if (i < a.n) {
+        const float *v = vin + 9 * threadIdx.x;
+        tr = tri_from_vertices(v3(v[0], v[1], v[2]), v3(v[3], v[4], v[5]), v3(v[6], v[7], v[8]));
+        float4 *r = rec + 3 * threadIdx.x;
+        r[0] = make_float4(tr.p0x, tr.p0y, tr.p0z, tr.e1x);
+        r[1] = make_float4(tr.e1y, tr.e1z, tr.e2x, tr.e2y);
+        r[2] = make_float4(tr.e2z, tr.nx, tr.ny, tr.nz);
+    }
+    __syncthreads();
+    float4 *dst = reinterpret_cast<float4 *>(a.tri_in + b0);
+    for (int t = threadIdx.x; t < cnt * 3; t += kSetupBlock) dst[t] = rec[t];
+    // scene bounds: one reduction per warp, one per block, SIX atomics per block (one per warp was still 1.9 M atomics
+    // to six addresses for 10 M triangles — the kernel's whole 1.5 ms)
+    __shared__ int32_t part[kSetupBlock / 32][6];
+    int32_t o[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int32_t)0x80000000, (int32_t)0x80000000, (int32_t)0x80000000};
+    if (i < a.n) {
+        V3 lo, hi;
+        prim_setup_box(a, i, tr, lo, hi);
+        o[0] = float_to_ordered(lo.x); o[1] = float_to_ordered(lo.y); o[2] = float_to_ordered(lo.z);
+        o[3] = float_to_ordered(hi.x); o[4] = float_to_ordered(hi.y); o[5] = float_to_ordered(hi.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = __reduce_min_sync(0xffffffffu, o[k]); o[3 + k] = __reduce_max_sync(0xffffffffu, o[3 + k]); }
+    if ((threadIdx.x & 31) == 0) for (int k = 0; k < 6; ++k) part[threadIdx.x >> 5][k] = o[k];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        int32_t v = part[0][k];
+        for (int w = 1; w < kSetupBlock / 32; ++w) v = k < 3 ? min(v, part[w][k]) : max(v, part[w][k]);
+        if (k < 3) atomicMin(a.scene_bounds + k, v); else atomicMax(a.scene_bounds + k, v);
+    }
+}
+
 // Nearest-neighbour search of one PLOC round (ploc_nn_body) with the cluster boxes of a block's window staged in
 // shared memory: every cluster compares itself with 2 x radius neighbours, so the one-thread-per-cluster form reads
 // 32 boxes of 32 bytes through the cluster index for every thread — 8.1 of the 17.7 ms of kernel time of a
@@ -913,6 +966,12 @@ struct CudaBackend {
         if (dk.Current() != keys) copy(keys, dk.Current(), n);
         if (dv.Current() != vals) copy(vals, dv.Current(), n);
         free(k2); free(v2);  // (stream-ordered: released when the copies above have run)
+    }
+    void prim_setup(const PrimSetupArgs &a) {
+        if (a.n <= 0) return;
+        if (!a.vertices) { PrimSetupK k; k.a = a; launch(a.n, k); return; }  // records already filled (reference-pointer ingest)
+        k_prim_setup_tiled<<<(a.n + kSetupBlock - 1) / kSetupBlock, kSetupBlock, 0, stream_>>>(a);
+        RTB_CUDA_CHECK(cudaGetLastError());
     }
     void ploc_nn(const PlocArgs &a) {
         if (a.ncl <= 0) return;

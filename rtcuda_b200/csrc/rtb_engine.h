@@ -462,7 +462,7 @@ BuiltTree build_tree(BE &be, int n, const float *d_vertices, Tri48 *tri_in, TriM
         } else {
             PrimSetupK k; k.a.vertices = d_vertices; k.a.tri_in = tri_in; k.a.prim_lo = prim_lo; k.a.prim_hi = prim_hi;
             k.a.scene_bounds = bounds; k.a.bad = bounds + 6; k.a.n = n;
-            be.launch(n, k);
+            be.prim_setup(k.a);
             int32_t bad = 0;
             be.download(&bad, bounds + 6, 1);  // (kept: a scene with a non-finite vertex must not reach the sort and the PLOC rounds)
             if (bad) {

@@ -120,6 +120,7 @@ struct HostBackend {
         memcpy(keys, k.data(), sizeof(uint64_t) * n);
         memcpy(vals, v.data(), sizeof(int32_t) * n);
     }
+    void prim_setup(const PrimSetupArgs &a) { PrimSetupK k; k.a = a; launch(a.n, k); }
     void ploc_nn(const PlocArgs &a) { PlocNnK k; k.a = a; launch(a.ncl, k); }
     bool ploc_tail(const PlocArgs &, int, int32_t *) { return false; }  // (a launch-latency measure of the CUDA backend)
     int32_t *ploc_tail_counts() { return nullptr; }
