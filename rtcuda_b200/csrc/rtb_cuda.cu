@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_flat(WaveState W, SceneView S
 // 36-byte stride and storing twelve at a 48-byte stride took 1.48 ms for the 1.2 GB of a 10 M-triangle scene.
 constexpr int kSetupBlock = 256;
 __global__ void __launch_bounds__(kSetupBlock) k_prim_setup_tiled(PrimSetupArgs a) {
-    __shared__ float vin[kSetupBlock * 9];
+    __shared__ __align__(16) float vin[kSetupBlock * 9];
     __shared__ float4 rec[kSetupBlock * 3];
     const int b0 = blockIdx.x * kSetupBlock;
     const int cnt = min(kSetupBlock, a.n - b0);
