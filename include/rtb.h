@@ -419,7 +419,8 @@ RTB_API int rtb_kat_eval(rtb_context *ctx, int32_t which, const float *h_in, int
 
 /* ---- host-side scene I/O and procedural scenes (host C++, no GPU work) ---- */
 typedef struct rtb_host_scene rtb_host_scene; /* owns the arrays a rtb_scene_desc points to */
-/* ASCII PLY (what main.cu:60-62 reads through happly.h:1289,1451,1498) */
+/* PLY, ASCII (what main.cu:60-62 reads through happly.h:1289,1451,1498) or binary_little_endian: vertex x y z first
+ * (float32; float64 in a binary file), face index lists, polygons fanned into triangles */
 RTB_API int rtb_mesh_load_ply(const char *path, float **verts_out, int64_t *num_verts,
                               int32_t **faces_out, int64_t *num_faces);
 /* compact binary mesh fixture: "RTBM" u32 nv u32 nf, f32 verts[3nv], i32 faces[3nf] */

@@ -367,49 +367,130 @@ int rtb_camera_look_at(const float from[3], const float at[3], const float up[3]
 }
 
 // ------------------------------------------------------------------ mesh I/O
+// size in bytes of a PLY scalar type name, 0 = unknown
+static int ply_type_size(const std::string &t) {
+    if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+    if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+    if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+    if (t == "double" || t == "float64") return 8;
+    return 0;
+}
+static bool ply_type_signed(const std::string &t) { return t == "char" || t == "int8" || t == "short" || t == "int16" || t == "int" || t == "int32"; }
+// one little-endian integer of `size` bytes at p (the library is built for little-endian hosts only)
+static int64_t ply_read_int(const unsigned char *p, int size, bool is_signed) {
+    uint64_t v = 0;
+    for (int k = 0; k < size; ++k) v |= (uint64_t)p[k] << (8 * k);
+    if (is_signed && size < 8 && (v >> (8 * size - 1) & 1u)) v |= ~0ull << (8 * size);
+    return (int64_t)v;
+}
+// ASCII (the form of the reference's bun_zipper.ply, read there by happly: main.cu:60) and binary_little_endian PLY:
+// vertex element with x y z as its first three properties (float32, or float64 in a binary file), any further scalar
+// properties skipped; face element whose first property is the vertex index list; polygons are fanned into triangles
 int rtb_mesh_load_ply(const char *path, float **verts_out, int64_t *nv_out, int32_t **faces_out, int64_t *nf_out) {
     if (!path || !verts_out || !nv_out || !faces_out || !nf_out) return rtb::set_error(RTB_ERR_INVALID, "rtb_mesh_load_ply: null argument");
     return rtb::host_guarded(RTB_ERR_IO, [&]() -> int {
-    std::ifstream in(path);
+    std::ifstream in(path, std::ios::binary);
     if (!in) return rtb::set_error(RTB_ERR_IO, std::string("cannot open ") + path);
     std::string line, tok;
     int64_t nv = -1, nf = -1;
     int vprops = 0;
-    bool ascii = false, in_vertex = false;
+    bool ascii = false, binary_le = false;
+    enum { kNone, kVertex, kFace, kOther } cur = kNone;
+    std::vector<int> vsizes;                 // byte sizes of the vertex element's scalar properties
+    int cnt_size = 0, idx_size = 0;          // face list: count type, index type
+    bool idx_signed = true;
+    int face_extra = 0;                      // bytes of scalar face properties behind the list
+    bool face_list_first = false, unsupported = false;
+    auto strip_cr = [](std::string &l) { if (!l.empty() && l.back() == '\r') l.pop_back(); };
     std::getline(in, line);
+    strip_cr(line);
     if (line.substr(0, 3) != "ply") return rtb::set_error(RTB_ERR_IO, "not a PLY file");
+    bool ended = false;
     while (std::getline(in, line)) {
+        strip_cr(line);
         std::istringstream ss(line);
+        tok.clear();
         ss >> tok;
-        if (tok == "format") { ss >> tok; ascii = (tok == "ascii"); }
+        if (tok == "format") { ss >> tok; ascii = (tok == "ascii"); binary_le = (tok == "binary_little_endian"); }
         else if (tok == "element") {
-            std::string name; int64_t cnt;
+            std::string name; int64_t cnt = -1;
             ss >> name >> cnt;
-            in_vertex = (name == "vertex");
-            if (name == "vertex") nv = cnt;
-            if (name == "face") nf = cnt;
-        } else if (tok == "property" && in_vertex) vprops++;
-        else if (tok == "end_header") break;
+            cur = name == "vertex" ? kVertex : (name == "face" ? kFace : kOther);
+            if (cur == kVertex) nv = cnt;
+            else if (cur == kFace) { if (nv < 0) unsupported = true; nf = cnt; }  // (vertices must come first)
+            else if (cnt != 0 && nf < 0) unsupported = true;  // an unknown element in front of the ones we read
+        } else if (tok == "property") {
+            std::string t;
+            ss >> t;
+            if (cur == kVertex) {
+                if (t == "list") unsupported = true;
+                vsizes.push_back(ply_type_size(t));
+                vprops++;
+            } else if (cur == kFace) {
+                if (t == "list") {
+                    std::string ct, it;
+                    ss >> ct >> it;
+                    if (cnt_size == 0 && face_extra == 0) { cnt_size = ply_type_size(ct); idx_size = ply_type_size(it); idx_signed = ply_type_signed(it); face_list_first = true; }
+                    else unsupported = true;  // a second list per face
+                } else {
+                    if (!face_list_first) unsupported = true;
+                    face_extra += ply_type_size(t);
+                }
+            }
+        } else if (tok == "end_header") { ended = true; break; }
     }
-    if (!ascii || nv < 0 || nf < 0 || vprops < 3) return rtb::set_error(RTB_ERR_IO, "unsupported PLY (need ascii, vertex x y z first, face lists)");
+    if (!ended || !(ascii || binary_le) || nv < 0 || nf < 0 || vprops < 3 || unsupported)
+        return rtb::set_error(RTB_ERR_IO, "unsupported PLY (need ascii or binary_little_endian, vertex x y z first, then face lists)");
     if (nv > 0x7fffffff || nf > 0x7fffffff) return rtb::set_error(RTB_ERR_IO, "PLY: element count out of range");
     std::vector<float> verts(3 * (size_t)nv);
     std::vector<int32_t> faces;
-    for (int64_t i = 0; i < nv; ++i) {
-        if (!std::getline(in, line)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the vertex list");
-        std::istringstream ss(line);
-        if (!(ss >> verts[3 * i] >> verts[3 * i + 1] >> verts[3 * i + 2]))  // x y z are the first three properties
-            return rtb::set_error(RTB_ERR_IO, "PLY: bad vertex line");
-    }
-    for (int64_t i = 0; i < nf; ++i) {
-        if (!std::getline(in, line)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the face list");
-        std::istringstream ss(line);
-        int k = -1;
-        if (!(ss >> k) || k < 3 || k > 64) return rtb::set_error(RTB_ERR_IO, "PLY: bad face vertex count");
-        int32_t idx[64];
-        for (int j = 0; j < k; ++j)
-            if (!(ss >> idx[j]) || idx[j] < 0 || idx[j] >= nv) return rtb::set_error(RTB_ERR_IO, "PLY: face index out of range");
-        for (int j = 1; j + 1 < k; ++j) { faces.push_back(idx[0]); faces.push_back(idx[j]); faces.push_back(idx[j + 1]); }
+    if (ascii) {
+        for (int64_t i = 0; i < nv; ++i) {
+            if (!std::getline(in, line)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the vertex list");
+            std::istringstream ss(line);
+            if (!(ss >> verts[3 * i] >> verts[3 * i + 1] >> verts[3 * i + 2]))  // x y z are the first three properties
+                return rtb::set_error(RTB_ERR_IO, "PLY: bad vertex line");
+        }
+        for (int64_t i = 0; i < nf; ++i) {
+            if (!std::getline(in, line)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the face list");
+            std::istringstream ss(line);
+            int k = -1;
+            if (!(ss >> k) || k < 3 || k > 64) return rtb::set_error(RTB_ERR_IO, "PLY: bad face vertex count");
+            int32_t idx[64];
+            for (int j = 0; j < k; ++j)
+                if (!(ss >> idx[j]) || idx[j] < 0 || idx[j] >= nv) return rtb::set_error(RTB_ERR_IO, "PLY: face index out of range");
+            for (int j = 1; j + 1 < k; ++j) { faces.push_back(idx[0]); faces.push_back(idx[j]); faces.push_back(idx[j + 1]); }
+        }
+    } else {
+        int stride = 0;
+        for (int sz : vsizes) { if (sz == 0) return rtb::set_error(RTB_ERR_IO, "PLY: unknown vertex property type"); stride += sz; }
+        const int csz = vsizes[0];
+        if ((csz != 4 && csz != 8) || vsizes[1] != csz || vsizes[2] != csz) return rtb::set_error(RTB_ERR_IO, "PLY: x y z must be float32 or float64");
+        if (cnt_size == 0 || idx_size == 0 || idx_size > 4) return rtb::set_error(RTB_ERR_IO, "PLY: unsupported face list types");
+        std::vector<unsigned char> row((size_t)stride);
+        for (int64_t i = 0; i < nv; ++i) {
+            if (!in.read((char *)row.data(), stride)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the vertex list");
+            for (int a = 0; a < 3; ++a) {
+                if (csz == 4) { float f; memcpy(&f, row.data() + 4 * a, 4); verts[3 * i + a] = f; }
+                else { double d; memcpy(&d, row.data() + 8 * a, 8); verts[3 * i + a] = (float)d; }
+            }
+        }
+        unsigned char buf[64 * 4 + 8];
+        std::vector<char> skip((size_t)face_extra);
+        for (int64_t i = 0; i < nf; ++i) {
+            if (!in.read((char *)buf, cnt_size)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the face list");
+            const int64_t k = ply_read_int(buf, cnt_size, false);
+            if (k < 3 || k > 64) return rtb::set_error(RTB_ERR_IO, "PLY: bad face vertex count");
+            if (!in.read((char *)buf, (std::streamsize)(k * idx_size))) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the face list");
+            int32_t idx[64];
+            for (int j = 0; j < k; ++j) {
+                const int64_t v = ply_read_int(buf + j * idx_size, idx_size, idx_signed);
+                if (v < 0 || v >= nv) return rtb::set_error(RTB_ERR_IO, "PLY: face index out of range");
+                idx[j] = (int32_t)v;
+            }
+            for (int j = 1; j + 1 < k; ++j) { faces.push_back(idx[0]); faces.push_back(idx[j]); faces.push_back(idx[j + 1]); }
+            if (face_extra && !in.read(skip.data(), face_extra)) return rtb::set_error(RTB_ERR_IO, "PLY: file ends inside the face list");
+        }
     }
     float *v = (float *)malloc(sizeof(float) * (verts.size() ? verts.size() : 1));
     int32_t *f = (int32_t *)malloc(sizeof(int32_t) * (faces.size() ? faces.size() : 1));

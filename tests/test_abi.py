@@ -88,6 +88,38 @@ def test_ply_reader_and_ppm_writer(emu, tmp_path):
     assert out.read_text().split() == ["P3", "2", "1", "255", "0", "128", "255", "255", "0", "255"]
 
 
+def test_binary_ply_reads_like_its_ascii_form(emu, tmp_path):
+    """binary_little_endian PLY (what most scanned meshes ship as; the reference reads either through happly): float32 or
+    float64 coordinates, extra vertex and face properties skipped, uchar / ushort / int index lists, truncated files refused"""
+    import struct
+    import numpy as np
+    rng = np.random.default_rng(3)
+    verts = rng.standard_normal((50, 3)).astype(np.float32)
+    polys = [list(rng.choice(50, size=k, replace=False)) for k in (3, 4, 3, 5, 3, 4)]
+    want = [[p[0], p[j], p[j + 1]] for p in polys for j in range(1, len(p) - 1)]
+    for coord, cnt_t, idx_t, cnt_f, idx_f in (("float", "uchar", "int", "<B", "<i"), ("double", "uchar", "uint", "<B", "<I"),
+                                               ("float32", "uint8", "uint16", "<B", "<H")):
+        hdr = (f"ply\nformat binary_little_endian 1.0\ncomment made by a test\nelement vertex {len(verts)}\nproperty {coord} x\nproperty {coord} y\n"
+               f"property {coord} z\nproperty uchar red\nelement face {len(polys)}\nproperty list {cnt_t} {idx_t} vertex_indices\n"
+               f"property float quality\nend_header\n").encode()
+        body = b""
+        for v in verts:
+            body += struct.pack("<3d" if coord == "double" else "<3f", *[float(x) for x in v]) + b"\x07"
+        for p in polys:
+            body += struct.pack(cnt_f, len(p)) + b"".join(struct.pack(idx_f, int(i)) for i in p) + struct.pack("<f", 0.25)
+        path = tmp_path / f"b_{coord}_{idx_t}.ply"
+        path.write_bytes(hdr + body)
+        v, f = emu.load_mesh(str(path))
+        assert (v == verts).all() and f.tolist() == want
+        (tmp_path / "cut.ply").write_bytes((hdr + body)[:-9])
+        with pytest.raises(capi.RtbError):
+            emu.load_mesh(str(tmp_path / "cut.ply"))
+    (tmp_path / "be.ply").write_bytes(b"ply\nformat binary_big_endian 1.0\nelement vertex 0\nproperty float x\nproperty float y\nproperty float z\n"
+                                      b"element face 0\nproperty list uchar int vertex_indices\nend_header\n")
+    with pytest.raises(capi.RtbError):
+        emu.load_mesh(str(tmp_path / "be.ply"))
+
+
 def test_host_entry_points_reject_bad_files_instead_of_throwing(emu, tmp_path):
     """the host I/O entry points validate counts / indices and never let an exception cross the C ABI"""
     import struct
