@@ -225,6 +225,19 @@ def test_identical_triangles_build_one_pair_per_round(L, ctx, oracle):
         ctx.scene(desc)
 
 
+@pytest.mark.parametrize("n", [1019, 1020, 1021, 1400, 2700, 5000])
+def test_triangle_counts_around_the_builder_s_batch_and_tail_sizes(L, ctx, oracle, n):
+    """n + 4 triangles (soup + floor + emitters) = 1023, 1024 and 1025 — the single-block tail takes over at <= 1024
+    clusters — and sizes whose first batch is a fraction of a round, one round and several: hits equal the oracle's"""
+    verts, mat, lid = small_scene_arrays(seed=100 + n, n=n)
+    desc, keep = make_desc(verts, mat, lid, std_materials(), [area_light(len(verts) - 2), area_light(len(verts) - 1)])
+    sc = ctx.scene(desc)
+    assert sc.stats().num_triangles == n + 4
+    rays = random_rays(20000, seed=n)
+    assert_hits_equal(sc.trace_closest(rays), oracle.scene(desc).trace_closest(rays, capi.HIT_DTYPE))
+    sc.close()
+
+
 @pytest.mark.gpu
 def test_gpu_builder_and_its_host_emulation_build_the_same_tree(gpu, emu, bunny):
     """same bodies, two drivers (batched launches on device-resident counts / plain loops): same tree statistics"""
