@@ -462,8 +462,9 @@ class Job:
                 "l2_traffic": l2_per_ray * rays_per_launch if l2_per_ray is not None else None,
                 "l2_frac": (l2_per_ray * rays_per_launch / (avg_launch_ms * 1e-3) * 1e-9 / pk["l2"]) if l2_per_ray is not None and pk["l2"] and avg_launch_ms > 0 else None,
                 "issue_slot_pct": prof.get("k_trace_issue_slot_pct"), "lanes_per_inst": prof.get("k_trace_lanes_per_inst"),
-                "warps_active_pct": prof.get("k_trace_warps_active_pct"), "profile_source": prof.get("source"),
-                "limiter": "instruction issue and load latency (issue slots and lanes per instruction above), not memory bandwidth: "
+                "warps_active_pct": prof.get("k_trace_warps_active_pct"), "pipe_pct": prof.get("k_trace_pipe_pct"), "profile_source": prof.get("source"),
+                "limiter": "no single unit: issue slots, the ALU pipe and the L1 data pipe each 55-70 % busy at 19-25 of 32 lanes with half the warps an SM "
+                           "can hold (64 registers), a third of the stall samples on load latency; not memory bandwidth: "
                            + ("the scene is L2-resident, DRAM carries only the ray / hit queues" if resident else
                               "incoherent rays on a scene 5x the L2: DRAM traffic stays far below the HBM peak"),
                 "algorithmic_bytes_per_extend_ray": bytes_extend, "algorithmic_bytes_per_shadow_ray": bytes_shadow,
