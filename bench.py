@@ -605,9 +605,11 @@ def main():
     line = None
     if rank == 0:
         roofline = job.roofline(args.steps)
-        pool_used = min(int(job.p.pool_size) or rig.ctx.get_option("pool"), int(stats[0].paths))
+        pool_used = int(stats[0].pool) * int(stats[0].pipelines)  # path slots the render ran with (rtb_render_stats.pool, per wavefront)
         cfg = config_block(args.workload, world, spp, total_spp, pool=pool_used, strong=strong)
-        cfg["l2"] += "; the ray / hit queues (%.1f GB) are streamed every iteration" % (pool_used * 288 / 1e9)
+        n_types = {"c4": 3}.get(args.workload, 1)
+        cfg["l2"] += "; the ray / hit queues (%.1f GB: pool %s) are streamed every iteration" % (
+            pool_used * (96 + 48 * n_types) / 1e9, "as asked" if int(job.p.pool_size) else "automatic, an eighth of the free device memory at most")
         line = {"metric": METRIC, "value": res["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": cfg,

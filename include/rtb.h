@@ -174,7 +174,7 @@ typedef struct rtb_render_params {
     uint32_t seed;          /* RAND_SEED, render.cuh:417 (default 1) */
     int32_t first_sample;   /* index of the first sample of this call (sample-pass sharding) */
     int32_t total_spp;      /* divisor used by the tonemap; 0 means spp */
-    int32_t pool_size;      /* path slots (NUM_WORKING_PATHS, constant.hpp:8); 0 = auto */
+    int32_t pool_size;      /* path slots (NUM_WORKING_PATHS, constant.hpp:8); 0 = the context's "pool" option */
     int32_t flags;          /* RTB_RENDER_* */
     uint32_t device_mask;   /* rtb_multi_render: bit i set = use GPU i of the rtb_multi; 0 = all of them.  rtb_render /
                                rtb_render_accumulate run on the one GPU of the scene's context and reject a mask without it */
@@ -222,7 +222,8 @@ typedef struct rtb_render_stats {
                               is the duration of that launch and ms_shadow is 0 */
     int32_t pipelines;     /* independent wavefronts run on concurrent streams (1..4); the per-stage
                               times above are only measured with 1 (RTB_RENDER_SINGLE_PIPELINE) */
-    int32_t _pad;
+    int32_t pool;          /* path slots each wavefront ran with (rtb_render_params.pool_size, the "pool" option, or the
+                              automatic size: see rtb_context_set_option) */
 } rtb_render_stats;
 
 typedef struct rtb_context rtb_context; /* one per GPU */
@@ -237,7 +238,11 @@ RTB_API int rtb_context_device(const rtb_context *ctx);
 /* Schedule of the traversal / wavefront kernels (replaces compile-time choices such as BLOCK_SIZE, render.cuh:413, and
  * NUM_WORKING_PATHS, constant.hpp:8).  Every schedule gives bit-identical hits; the defaults are the measured best
  * (DESIGN.md 4).  Names: "refill" (1..32), "chunk" (>= 32), "prefetch" (0/1), "tri_step" (0..4), "pooled" (-1/0/1),
- * "fused" (0/1), "smem_stack" (0/1), "pipelines" (0 = by scene size, 1..4), "pool" (path slots, >= 1024),
+ * "fused" (0/1), "smem_stack" (0/1), "pipelines" (0 = by scene size, 1..4), "pool" (path slots, >= 1024; 0 = automatic, the default:
+ * as many paths as fit an eighth of the device memory that was free when the context was created, at least 4 Mi, at most the
+ * paths of the render — C2 on an empty B200: all 132.7 M paths, 19 GB of ray / hit queues; the queues of the last scene
+ * that was destroyed stay with the context for the next scene that renders with the same shape, until
+ * rtb_context_destroy),
  * "ploc_tail" (0/1), "nn_tiled" (0/1), "trace_blocks" (0 = auto, 1..8 resident blocks per SM).  Unknown names / values out of range:
  * RTB_ERR_INVALID.  Takes effect for scenes built and renders started afterwards. */
 RTB_API int rtb_context_set_option(rtb_context *ctx, const char *name, int64_t value);

@@ -77,7 +77,7 @@ class RenderStats(C.Structure):
                 ("extend_nodes", C.c_uint64), ("extend_tris", C.c_uint64), ("shadow_nodes", C.c_uint64),
                 ("shadow_tris", C.c_uint64), ("extend_launches", C.c_uint64), ("shadow_launches", C.c_uint64), ("hits", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_extend", C.c_float), ("ms_shadow", C.c_float), ("ms_other", C.c_float),
-                ("ms_shade", C.c_float), ("fused_trace", C.c_int32), ("pipelines", C.c_int32), ("_pad", C.c_int32)]
+                ("ms_shade", C.c_float), ("fused_trace", C.c_int32), ("pipelines", C.c_int32), ("pool", C.c_int32)]
 
 
 RAY_DTYPE = np.dtype([("origin", np.float32, 3), ("dir", np.float32, 3), ("tmax", np.float32)])

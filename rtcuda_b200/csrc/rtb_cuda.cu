@@ -677,7 +677,10 @@ struct CudaBackend {
     int pooled_ = 0;  // RTB_POOLED: pooled triangle tests (1), each ray's lane on its own (0, default), by scene size (-1)
     int fused_ = 1;   // "fused": extend + shadow rays of one iteration in one launch
     int smem_stack_ = 0;  // "smem_stack": first stack entries in shared memory (A/B, k_trace_smem_stack)
-    int pool_ = 1 << 25;    // default path pool, RTB_POOL overrides (tuning)
+    WaveCache wave_cache_;  // queues of the last destroyed scene (rtb_engine.h)
+    WaveCache &wave_cache() { return wave_cache_; }
+    int pool_ = 0;          // "pool": path slots of a render; 0 = automatic (default_pool)
+    size_t pool_budget_ = 0;  // an eighth of the device memory that was free when the context was created
     int ploc_tail_off_ = 0; // RTB_PLOC_TAIL=0: every PLOC round its own launches (A/B)
     int nn_tiled_off_ = 0;  // "nn_tiled" = 0: nearest-neighbour search of a PLOC round one thread per cluster from global memory (A/B)
 
@@ -711,6 +714,11 @@ struct CudaBackend {
         RTB_CUDA_CHECK(cudaMemPoolCreate(&pool_mem_, &props));
         unsigned long long keep = ~0ull;
         RTB_CUDA_CHECK(cudaMemPoolSetAttribute(pool_mem_, cudaMemPoolAttrReleaseThreshold, &keep));
+        {
+            size_t free_b = 0, total_b = 0;
+            RTB_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+            pool_budget_ = free_b / 8;
+        }
         RTB_CUDA_CHECK(cudaHostAlloc((void **)&h_done_, kMaxPipelines * sizeof(int32_t), cudaHostAllocMapped));
         RTB_CUDA_CHECK(cudaHostGetDevicePointer((void **)&d_done_, h_done_, 0));
         for (int k = 0; k < kMaxPipelines; ++k) h_done_[k] = 0;
@@ -735,6 +743,7 @@ struct CudaBackend {
         cudaSetDevice(dev_);
         stream_ = streams_[0];
         for (int k = 0; k < kMaxPipelines; ++k) if (streams_[k]) cudaStreamSynchronize(streams_[k]);
+        wave_cache_release(*this, wave_cache_);
         if (cub_temp_) cudaFreeAsync(cub_temp_, stream_);
         if (tail_counts_) cudaFreeAsync(tail_counts_, stream_);
         if (h_done_) cudaFreeHost(h_done_);
@@ -756,7 +765,7 @@ struct CudaBackend {
         else if (name == "fused") { if (!in(0, 1)) return false; fused_ = (int)v; }
         else if (name == "smem_stack") { if (!in(0, 1)) return false; smem_stack_ = (int)v; }
         else if (name == "pipelines") { if (!in(0, kMaxPipelines)) return false; pipelines_ = (int)v; }
-        else if (name == "pool") { if (!in(1024, 1ll << 30)) return false; pool_ = (int)v; }
+        else if (name == "pool") { if (v != 0 && !in(1024, 1ll << 30)) return false; pool_ = (int)v; }
         else if (name == "ploc_tail") { if (!in(0, 1)) return false; ploc_tail_off_ = v == 0; }
         else if (name == "trace_blocks") { if (!in(0, trace_blocks_per_sm_)) return false; trace_cap_ = (int)v; }
         else if (name == "nn_tiled") { if (!in(0, 1)) return false; nn_tiled_off_ = v == 0; }
@@ -782,7 +791,17 @@ struct CudaBackend {
     int device() const { return dev_; }
     void make_current() { RTB_CUDA_CHECK(cudaSetDevice(dev_)); }
     void sync() { RTB_CUDA_CHECK(cudaStreamSynchronize(stream_)); }
-    int default_pool() const { return pool_; }
+    // Path slots of a render that does not name a pool.  Fewer, larger iterations win (C2, four wavefronts: 34.5 ms at
+    // 32 Mi slots, 34.3 at 64 Mi, 33.7 with all 132.7 M paths in flight; C4 27.6 / 27.2 / 26.4 ms: profiles/README.md,
+    // session 45), and a B200 has 180 GB: as many slots as fit an eighth of what was free when the context was created,
+    // at least 4 Mi; render_accumulate caps it at the paths of the render.
+    long long default_pool(size_t slot_bytes) const {
+        if (pool_ > 0) return pool_;
+        long long n = (long long)(pool_budget_ / (slot_bytes ? slot_bytes : 144));
+        if (n < (1ll << 22)) n = 1ll << 22;
+        if (n > (1ll << 28)) n = 1ll << 28;
+        return n;
+    }
 
     template <class T> T *alloc(size_t n) {
         void *p = nullptr;

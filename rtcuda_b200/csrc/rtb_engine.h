@@ -309,6 +309,27 @@ struct AovK {
 
 // ---- scene ----
 constexpr int kMaxPipelines = 4;
+// The ray / hit queues of the last scene that was destroyed, kept by the context for the next scene that renders with the
+// same shape (rtb_scene_create + rtb_render + rtb_scene_destroy per frame is the end-to-end step of bench.py).  Returning
+// 19 GB of queues to the stream-ordered pool and asking for them again works only while nothing else carves the cached
+// blocks up in between: the temporaries of a 10 M-triangle build do, and the next render then waited ~190 ms for fresh
+// memory from the driver.
+struct WaveCache {
+    WaveState W[kMaxPipelines]{};
+    int32_t pool = 0, pipes = 0;
+    size_t nq = 0;
+    bool inst = false;
+};
+template <class BE>
+void wave_cache_release(BE &be, WaveCache &c) {
+    for (int k = 0; k < c.pipes; ++k) {
+        WaveState &w = c.W[k];
+        be.free(w.ea); be.free(w.eb); be.free(w.ec); be.free(w.ma); be.free(w.mb); be.free(w.mc);
+        be.free(w.sh_o); be.free(w.sh_d); be.free(w.sh_L); be.free(w.c); be.free(w.hit_inst);
+        w = WaveState{};
+    }
+    c.pool = 0; c.pipes = 0; c.nq = 0; c.inst = false;
+}
 template <class BE>
 struct SceneT {
     BE *be = nullptr;
@@ -349,7 +370,16 @@ struct SceneT {
         S.num_lights = num_lights; S.num_materials = num_materials;
         return S;
     }
-    void free_wave() {
+    // keep = true (the scene is being destroyed): the queues go to the context's cache for the next scene
+    void free_wave(bool keep = false) {
+        WaveCache &cache = be->wave_cache();
+        if (keep && pipes > 0) {
+            wave_cache_release(*be, cache);
+            for (int k = 0; k < pipes; ++k) { be->free(W[k].mis); W[k].mis = nullptr; cache.W[k] = W[k]; W[k] = WaveState{}; }
+            cache.pool = pool; cache.pipes = pipes; cache.nq = (size_t)num_present() * (size_t)pool; cache.inst = inst != nullptr;
+            pool = 0; pipes = 0;
+            return;
+        }
         for (int k = 0; k < pipes; ++k) {
             WaveState &w = W[k];
             be->free(w.ea); be->free(w.eb); be->free(w.ec); be->free(w.ma); be->free(w.mb); be->free(w.mc);
@@ -372,6 +402,18 @@ struct SceneT {
         if (pool == p && pipes == np) return;
         free_wave();
         const size_t nq = (size_t)num_present() * (size_t)p;
+        WaveCache &cache = be->wave_cache();
+        if (cache.pipes == np && cache.pool == p && cache.nq == nq && cache.inst == (inst != nullptr)) {  // the last scene's queues fit
+            for (int k = 0; k < np; ++k) {
+                W[k] = cache.W[k]; cache.W[k] = WaveState{};
+                W[k].pool = p; W[k].mis = nullptr;
+                fill_qbase(W[k], p);
+            }
+            cache.pool = 0; cache.pipes = 0; cache.nq = 0;
+            pool = p; pipes = np;
+            return;
+        }
+        wave_cache_release(*be, cache);  // (another shape: its memory is needed now)
         for (int k = 0; k < np; ++k) {
             WaveState &w = W[k];
             w.ea = be->template alloc<F4>(p); w.eb = be->template alloc<F4>(p); w.ec = be->template alloc<F4>(p);
@@ -387,7 +429,7 @@ struct SceneT {
     }
     ~SceneT() {
         if (!be) return;
-        free_wave();
+        free_wave(true);
         be->free(accum); be->free(accum_fx); be->free(own_out);
         be->free(nodes8); be->free(tris); be->free(meta); be->free(prim); be->free(leaf_of_prim);
         be->free(materials); be->free(lights); be->free(inst); be->free(top_inst); be->free((void *)deferred_light_ptr);
@@ -1148,7 +1190,9 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
     const unsigned long long total = (unsigned long long)p.width * (unsigned long long)p.height * (unsigned long long)p.spp;
     if ((unsigned long long)p.width * (unsigned long long)p.height > 0x7fffffffull) throw Error(RTB_ERR_INVALID, "image too large");
     const int mode = (p.flags & RTB_RENDER_COUNT_WORK) ? 2 : ((p.flags & RTB_RENDER_NONPERSISTENT) ? 1 : 0);
-    long long pool_all = p.pool_size > 0 ? p.pool_size : be.default_pool();
+    // queue bytes of one path slot: two ray queues of 48 B and a 48-byte hit queue per material type present (+ side arrays)
+    const size_t slot_bytes = 96 + (size_t)sc.num_present() * (48 + ((p.flags & RTB_RENDER_TRUE_MIS) ? 8 : 0) + (sc.inst ? 4 : 0));
+    long long pool_all = p.pool_size > 0 ? p.pool_size : be.default_pool(slot_bytes);
     if ((unsigned long long)pool_all > total) pool_all = (long long)total;
     int np = be.pipelines(sc.view());
     if (np > kMaxPipelines) np = kMaxPipelines;
@@ -1279,6 +1323,7 @@ void render_accumulate(BE &be, SceneT<BE> &sc, const rtb_camera &cam, const rtb_
         stats->ms_shade = ms_shade;
         stats->fused_trace = fused ? 1 : 0;
         stats->pipelines = np;
+        stats->pool = pool;
     }
 }
 

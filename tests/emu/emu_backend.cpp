@@ -23,6 +23,9 @@ namespace rtb {
 struct HostBackend {
     int ordinal_;
     explicit HostBackend(int ordinal) : ordinal_(ordinal) {}
+    ~HostBackend() { wave_cache_release(*this, wave_cache_); }
+    WaveCache wave_cache_;
+    WaveCache &wave_cache() { return wave_cache_; }
     int device() const { return -1; }  // (no GPU: device masks are not checked against it)
     void make_current() {}
     void sync() {}
@@ -32,7 +35,7 @@ struct HostBackend {
     bool set_option(const std::string &name, long long v) {
         static const char *const names[] = {"refill", "chunk", "prefetch", "tri_step", "pooled", "fused", "smem_stack", "pipelines", "pool",
                                             "ploc_tail", "trace_blocks", "nn_tiled"};
-        for (const char *n : names) if (name == n) { if (name == "pool" && v < 1024) return false; opts_[name] = v; return true; }
+        for (const char *n : names) if (name == n) { if (name == "pool" && v != 0 && v < 1024) return false; opts_[name] = v; return true; }
         return false;
     }
     bool get_option(const std::string &name, long long &v) const {
@@ -41,7 +44,7 @@ struct HostBackend {
         v = it->second;
         return true;
     }
-    int default_pool() const { auto it = opts_.find("pool"); return it == opts_.end() ? 1 << 16 : (int)it->second; }
+    long long default_pool(size_t) const { auto it = opts_.find("pool"); return it == opts_.end() || it->second == 0 ? 1 << 16 : it->second; }
 
     template <class T> T *alloc(size_t n) {
         void *p = nullptr;
