@@ -20,7 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c2")
 ap.add_argument("--refill", default="24")
 ap.add_argument("--chunk", default="128")
-ap.add_argument("--pool", default="33554432")
+ap.add_argument("--pool", default="0")
 ap.add_argument("--pooled", default="0")
 ap.add_argument("--fused", default="1")
 ap.add_argument("--prefetch", default="1")
